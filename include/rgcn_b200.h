@@ -1,0 +1,122 @@
+/* rgcn_b200.h — C ABI of the B200-native R-GCN message-passing engine (librgcn_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of tiddoloos/Scaling-RGCN-training: the R-GCN layer
+ * forward/backward that the reference reaches through torch_geometric.nn.RGCNConv
+ * (reference model/layers.py:7,15-16 construct; :21,23,62,64,108,110 call; autograd backward
+ * triggered at model/modelTrainer.py:66), the edge tensors that feed it
+ * (graphs/graph.py:55-69) and the summary->original embedding map-gather that feeds its first
+ * layer (model/embeddingTricks.py:8-49).  The reference is pure Python and has no FFI of its
+ * own; these entry points are what a ctypes binding on the reference side would bind
+ * (INTEGRATION.md shows that stub).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types, no exceptions cross the boundary.
+ *   - every call returns int: 0 = ok, <0 = rgcn_status, >0 = cudaError_t.  rgcn_last_error()
+ *     returns a thread-local message for the last non-zero return.
+ *   - all data pointers are DEVICE pointers on the current CUDA device unless named host_*.
+ *     Tensors are owned by the caller (PyTorch); the engine retains none of them past the call.
+ *     The only engine-owned object is the opaque rgcn_graph.
+ *   - `stream` is a cudaStream_t passed as void*; every launch goes to it; no hidden syncs in
+ *     rgcn_layer_fwd/bwd/map_gather (rgcn_graph_create synchronises: it is a one-time build).
+ *   - features/parameters are fp32, row-major, leading dimension given in elements.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef RGCN_B200_H
+#define RGCN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGCN_B200_ABI_VERSION 1
+
+typedef enum {
+    RGCN_OK = 0,
+    RGCN_ERR_INVALID_ARG = -1,   /* null pointer, negative size, bad enum */
+    RGCN_ERR_INDEX_RANGE = -2,   /* src/dst outside [0,N) or type outside [0,R) */
+    RGCN_ERR_UNSUPPORTED = -3,   /* shape not supported by any kernel */
+    RGCN_ERR_WORKSPACE = -4      /* workspace too small */
+} rgcn_status;
+
+typedef struct rgcn_graph rgcn_graph;
+
+/* Which blocked relational CSR (BRC) of a graph: owner = dst (forward), owner = src
+ * (transposed, for dL/dx), or forward in pure relation-major order (for dL/dW). */
+enum { RGCN_BRC_FWD = 0, RGCN_BRC_BWD = 1, RGCN_BRC_FWD_REL = 2 };
+
+/* rgcn_graph_query keys */
+enum {
+    RGCN_Q_NUM_NODES = 0, RGCN_Q_NUM_EDGES = 1, RGCN_Q_NUM_RELATIONS = 2,
+    RGCN_Q_NUM_SEGMENTS = 3, RGCN_Q_NUM_ENTRIES = 4, RGCN_Q_NUM_CHUNKS = 5,
+    RGCN_Q_NUM_GROUPS = 6, RGCN_Q_NUM_BATCHES = 7, RGCN_Q_RANGE_NODES = 8,
+    RGCN_Q_DEVICE_BYTES = 9
+};
+
+/* rgcn_graph_export array ids (element type in brackets) */
+enum {
+    RGCN_A_PERM = 0 /*i32[E+N]*/, RGCN_A_SEG_PTR = 1 /*i32[S+1]*/, RGCN_A_SEG_OWN = 2 /*i32[S]*/,
+    RGCN_A_SEG_REL = 3 /*i32[S]*/, RGCN_A_SEG_PTR0 = 4 /*i32[S+1] before chunking; diff = multiplicity*/, RGCN_A_E_IDX = 5 /*u32[E3]*/,
+    RGCN_A_E_W = 6 /*f32[E3]*/, RGCN_A_RAW_IDX = 7 /*i32[E+N]*/, RGCN_A_RAW_W = 8 /*f32[E+N]*/,
+    RGCN_A_CHUNK_BEG = 9 /*i32[NC]*/, RGCN_A_CHUNK_END = 10 /*i32[NC]*/,
+    RGCN_A_BAT_SEG0 = 11 /*i32[NB]*/, RGCN_A_BAT_INFO = 12 /*i32[NB]*/
+};
+
+/* layer flags */
+#define RGCN_F_RELU_IN     1u  /* apply max(0,.) to every gathered input row (fuses the reference's
+                                  F.relu between the two layers, model/layers.py:22) */
+#define RGCN_F_FORCE_SIMPLE 2u /* use the generic (any-shape, scalar-FMA) kernels */
+
+const char* rgcn_last_error(void);
+int rgcn_abi_version(void);
+
+/* K0 — replaces nothing in the reference one-to-one: PyG re-derives `edge_type == r` masks on
+ * every forward; the engine sorts once.  Inputs are the tensors of
+ * graphs/graph.py:65-69 as they are: int64, possibly strided (element strides given).
+ * range_nodes <= 0, split_threshold <= 0, chunk_size <= 0 pick defaults. */
+int rgcn_graph_create(const int64_t* src, int64_t src_stride,
+                      const int64_t* dst, int64_t dst_stride,
+                      const int64_t* etype, int64_t etype_stride,
+                      int64_t num_edges, int64_t num_nodes, int32_t num_relations,
+                      int32_t range_nodes, int32_t split_threshold, int32_t chunk_size,
+                      void* stream, rgcn_graph** out);
+void rgcn_graph_destroy(rgcn_graph* g);
+int rgcn_graph_query(const rgcn_graph* g, int32_t brc, int32_t key, int64_t* out);
+int rgcn_graph_export(const rgcn_graph* g, int32_t brc, int32_t array, void* host_dst,
+                      int64_t bytes, void* stream);
+
+/* Workspace size (bytes) for one forward or backward call of an (fin -> fout) layer. */
+int64_t rgcn_layer_workspace_bytes(const rgcn_graph* g, int32_t fin, int32_t fout, int32_t backward);
+
+/* RGCNConv.forward (reference call sites model/layers.py:21,23):
+ *   out[i] = sum_r mean_{e: type=r, dst=i} x[src_e] . W_r + x[i] . root + bias
+ * weight [R, fin, fout] (basis form is expanded by the caller), root/bias nullable.
+ * out is fully overwritten. */
+int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin,
+                   const float* weight, const float* root, const float* bias,
+                   float* out, int64_t ldo, int32_t fout, uint32_t flags,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Autograd backward of the above (reference model/modelTrainer.py:66).  Any of
+ * gx / gweight / groot / gbias may be null = not needed (-e_freeze / -w_grad False).
+ * Non-null outputs are fully overwritten.  With RGCN_F_RELU_IN, x is the pre-activation and
+ * gx is the gradient w.r.t. that pre-activation (ReLU mask applied). */
+int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin,
+                   const float* weight, const float* root,
+                   const float* gout, int64_t ldg, int32_t fout,
+                   float* gx, int64_t ldgx, float* gweight, float* groot, float* gbias,
+                   uint32_t flags, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* K5 — get_tensor_list + sum/concat/stack (reference model/embeddingTricks.py:8-49).
+ * For summary s: row i of T_s = emb[s][idx[s][i]] if idx[s][i] >= 0 else fallback[s][i]
+ * (the reference's torch.rand row).  host_* are HOST arrays of num_sums device pointers.
+ * mode 0: out[N,F] = T_0 + T_1 + ... (that order);  1: out[N,S*F] concat;  2: out[S,N,F] stack. */
+int rgcn_map_gather(const float* const* host_emb, const int32_t* const* host_idx,
+                    const float* const* host_fallback, int32_t num_sums,
+                    int64_t num_nodes, int32_t feat, int32_t mode, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGCN_B200_H */

@@ -1,0 +1,127 @@
+"""CPU ORACLE (numpy) for the engine's on-device graph build (kernel group K0) — test
+infrastructure only.
+
+The reference has no CSR: PyG's loop path masks ``edge_type == r`` per relation
+ over the tensors ``Graph.init_graph`` emits
+(/root/reference/graphs/graph.py:55-69).  The engine re-sorts those edges once; this file
+restates that integer mapping with numpy (stable lexsort) so the device build can be
+checked bit-exactly, and so that "the CSR is a pure permutation of the reference's
+edges" is a testable property (``edges_from_brc``).
+
+Blocked relational CSR (BRC), spec shared with scaling-rgcn-training_b200/csrc/graph_build.cu:
+  entries   the E edges plus one self-loop per node (relation id R, weight 1)  -> root term
+  key       (owner // NR) * (R+1) * NR + rel * NR + owner % NR ; stable sort
+  segment   maximal run of equal key = one (relation, owner) pair; cnt = multiplicity
+  weight    1/cnt of the FORWARD segment of the entry (per-(relation, dst) mean normaliser)
+  chunking  segments with cnt > T are replaced by ceil(cnt/CH) virtual entries N+chunk_id
+            (weight 1) whose rows a pre-pass fills with the weighted partial sums
+  group     maximal run of segments with equal (range, rel)
+  batch     <= BS consecutive segments of one group
+"""
+from __future__ import annotations
+
+import numpy as np
+
+BS = 16
+LAST_FLAG = np.uint32(0x80000000)
+
+
+def build_brc(own, gat, rel, n, r, nr, t, ch, w_entry=None):
+    own = np.asarray(own, dtype=np.int64)
+    gat = np.asarray(gat, dtype=np.int64)
+    rel = np.asarray(rel, dtype=np.int64)
+    e = own.size
+    nr = int(min(max(nr, 1), max(n, 1)))
+    loops = np.arange(n, dtype=np.int64)
+    own2 = np.concatenate([own, loops])
+    gat2 = np.concatenate([gat, loops])
+    rel2 = np.concatenate([rel, np.full(n, r, dtype=np.int64)])
+    key = (own2 // nr) * ((r + 1) * nr) + rel2 * nr + own2 % nr
+    perm = np.argsort(key, kind='stable')
+    skey = key[perm]
+    e2 = e + n
+    head = np.ones(e2, dtype=bool)
+    head[1:] = skey[1:] != skey[:-1]
+    seg_of = np.cumsum(head) - 1
+    seg_ptr0 = np.flatnonzero(head).astype(np.int64)
+    s = seg_ptr0.size
+    seg_ptr0 = np.concatenate([seg_ptr0, [e2]])
+    cnt = np.diff(seg_ptr0)
+    seg_key = skey[seg_ptr0[:-1]]
+    seg_range = seg_key // ((r + 1) * nr)
+    seg_rel = (seg_key // nr) % (r + 1)
+    seg_own = seg_range * nr + seg_key % nr
+    if w_entry is None:
+        w_entry = np.empty(e2, dtype=np.float32)
+        w_entry[perm] = (np.float32(1.0) / cnt.astype(np.float32))[seg_of]
+    raw_idx = gat2[perm].astype(np.int32)
+    raw_w = w_entry[perm].astype(np.float32)
+    # chunking
+    split = cnt > t
+    nchunk = np.where(split, (cnt + ch - 1) // ch, 0)
+    chunk_base = np.concatenate([[0], np.cumsum(nchunk)])
+    nc = int(chunk_base[-1])
+    out_cnt = np.where(split, nchunk, cnt)
+    seg_ptr = np.concatenate([[0], np.cumsum(out_cnt)]).astype(np.int64)
+    e3 = int(seg_ptr[-1])
+    e_idx = np.zeros(e3, dtype=np.uint32)
+    e_w = np.zeros(e3, dtype=np.float32)
+    chunk_beg = np.zeros(nc, dtype=np.int32)
+    chunk_end = np.zeros(nc, dtype=np.int32)
+    for si in range(s):
+        a, b = seg_ptr0[si], seg_ptr0[si + 1]
+        o = seg_ptr[si]
+        if split[si]:
+            for j in range(int(nchunk[si])):
+                c = chunk_base[si] + j
+                chunk_beg[c] = a + j * ch
+                chunk_end[c] = min(a + (j + 1) * ch, b)
+                e_idx[o + j] = n + c
+                e_w[o + j] = 1.0
+        else:
+            e_idx[o:o + (b - a)] = raw_idx[a:b].astype(np.uint32)
+            e_w[o:o + (b - a)] = raw_w[a:b]
+    if s:
+        e_idx[seg_ptr[1:] - 1] |= LAST_FLAG
+    # groups and batches
+    gkey = seg_range * (r + 1) + seg_rel
+    ghead = np.ones(s, dtype=bool)
+    ghead[1:] = gkey[1:] != gkey[:-1]
+    grp_seg = np.concatenate([np.flatnonzero(ghead), [s]]).astype(np.int64)
+    g = grp_seg.size - 1
+    grp_rel = seg_rel[grp_seg[:-1]] if g else np.zeros(0, dtype=np.int64)
+    grp_n = np.diff(grp_seg)
+    grp_nb = (grp_n + BS - 1) // BS
+    nb = int(grp_nb.sum())
+    bat_seg0 = np.zeros(nb, dtype=np.int32)
+    bat_info = np.zeros(nb, dtype=np.int32)
+    b = 0
+    for gi in range(g):
+        for j in range(int(grp_nb[gi])):
+            s0 = grp_seg[gi] + j * BS
+            ns = min(BS, grp_seg[gi + 1] - s0)
+            bat_seg0[b] = s0
+            bat_info[b] = (int(grp_rel[gi]) << 8) | int(ns)
+            b += 1
+    return dict(perm=perm.astype(np.int32), num_seg=s, seg_ptr=seg_ptr.astype(np.int32),
+                seg_own=seg_own.astype(np.int32), seg_rel=seg_rel.astype(np.int32), cnt=cnt.astype(np.int32),
+                e_idx=e_idx, e_w=e_w, raw_idx=raw_idx, raw_w=raw_w, w_entry=w_entry,
+                chunk_beg=chunk_beg, chunk_end=chunk_end, num_chunks=nc,
+                num_groups=g, num_batches=nb, bat_seg0=bat_seg0, bat_info=bat_info)
+
+
+def build_graph(src, dst, rel, n, r, nr, t, ch):
+    """Forward (owner = dst) and transposed (owner = src) BRCs as the engine builds them."""
+    fwd = build_brc(dst, src, rel, n, r, nr, t, ch)
+    bwd = build_brc(src, dst, rel, n, r, nr, t, ch, w_entry=fwd['w_entry'])
+    return fwd, bwd
+
+
+def edges_from_brc(brc, n):
+    """Recover the (owner, gather, rel) entry multiset the BRC encodes (self-loops carry
+    rel == R; chunked segments are read from the raw sorted arrays).  Restricted to
+    rel < R it must equal the reference's edge list as a multiset."""
+    seg_ptr0 = np.concatenate([[0], np.cumsum(brc['cnt'])])
+    seg_of = np.repeat(np.arange(brc['num_seg']), brc['cnt'])
+    assert seg_of.size == seg_ptr0[-1]
+    return np.stack([brc['seg_own'][seg_of], brc['raw_idx'], brc['seg_rel'][seg_of]], axis=1)

@@ -1,0 +1,3 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))))
+from rgcn_oracle import Data  # noqa: E402,F401

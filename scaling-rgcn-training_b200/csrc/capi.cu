@@ -1,0 +1,195 @@
+// capi.cu — extern "C" layer entry points (include/rgcn_b200.h): orchestration of the passes.
+#include <algorithm>
+
+#include "common.cuh"
+
+using namespace rgcn;
+
+namespace {
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct WsCarver {
+    char* base;
+    int64_t cap, off = 0;
+    bool ok = true;
+    WsCarver(void* p, int64_t bytes) : base((char*)p), cap(bytes) {}
+    template <typename T>
+    T* take(int64_t count) {
+        const int64_t bytes = align_up(std::max<int64_t>(count, 1) * (int64_t)sizeof(T), 256);
+        if (off + bytes > cap || base == nullptr) {
+            ok = false;
+            return nullptr;
+        }
+        T* r = (T*)(base + off);
+        off += bytes;
+        return r;
+    }
+};
+
+inline int64_t ws_take(int64_t count, int64_t elem) { return align_up(std::max<int64_t>(count, 1) * elem, 256); }
+
+bool direct_target(const void* p, int64_t ld, int width) {
+    return ld == width && width % 4 == 0 && ((uintptr_t)p & 15) == 0;
+}
+
+int64_t fwd_ws(const rgcn_graph* g, int fin, int fout) {
+    const int kp = pad_dim(fin), np = pad_dim(fout);
+    if (!kp || !np) return 256;
+    int64_t b = 0;
+    b += ws_take((int64_t)(g->R + 1) * kp * np * 2, 4);                      // wfrag (hi,lo)
+    b += ws_take((int64_t)g->brc[RGCN_BRC_FWD].num_chunks * kp, 4);          // chunk rows
+    b += ws_take((int64_t)g->N * np, 4);                                     // padded accumulate target
+    return b;
+}
+
+int64_t bwd_ws(const rgcn_graph* g, int fin, int fout) {
+    const int kp = pad_dim(fin), np = pad_dim(fout);
+    if (!kp || !np) return 256;
+    int64_t b = 0;
+    b += ws_take((int64_t)g->brc[RGCN_BRC_FWD_REL].num_chunks * kp, 4);      // chunk rows of x (dW pass)
+    b += ws_take((int64_t)(g->R + 1) * kp * np * 2, 4);                      // W^T frags
+    b += ws_take((int64_t)g->brc[RGCN_BRC_BWD].num_chunks * np, 4);          // chunk rows of gout (dx pass)
+    b += ws_take((int64_t)g->N * kp, 4);                                     // padded dx target
+    return b;
+}
+
+}  // namespace
+
+extern "C" int64_t rgcn_layer_workspace_bytes(const rgcn_graph* g, int32_t fin, int32_t fout, int32_t backward) {
+    if (!g || fin <= 0 || fout <= 0) return -1;
+    return backward ? bwd_ws(g, fin, fout) : fwd_ws(g, fin, fout);
+}
+
+extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, const float* weight,
+                              const float* root, const float* bias, float* out, int64_t ldo, int32_t fout,
+                              uint32_t flags, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!g || !x || !weight || !out || fin <= 0 || fout <= 0 || ldx < fin || ldo < fout)
+        return fail(RGCN_ERR_INVALID_ARG, "rgcn_layer_fwd: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool relu = (flags & RGCN_F_RELU_IN) != 0;
+    const int kp = pad_dim(fin), np = pad_dim(fout);
+    if ((flags & RGCN_F_FORCE_SIMPLE) || !kp || !np) {
+        RGCN_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)fout * 4, (size_t)g->N, st));
+        SimplePass p{};
+        p.brc = &g->brc[RGCN_BRC_FWD];
+        p.n_nodes = g->N;
+        p.self_rel = g->R;
+        p.feat = x; p.ldf = ldx; p.kin = fin;
+        p.weight = weight; p.root = root; p.bias = bias; p.transpose = false; p.w_rows = fin; p.w_cols = fout;
+        p.out = out; p.ldo = ldo; p.nout = fout; p.relu_in = relu;
+        return launch_simple_pass(p, st);
+    }
+    WsCarver ws(workspace, workspace_bytes);
+    float4* wfrag = (float4*)ws.take<float>((int64_t)(g->R + 1) * kp * np * 2);
+    float* aux = ws.take<float>((int64_t)g->brc[RGCN_BRC_FWD].num_chunks * kp);
+    const bool direct = direct_target(out, ldo, fout);
+    float* target = direct ? out : ws.take<float>((int64_t)g->N * np);
+    if (!ws.ok) return fail(RGCN_ERR_WORKSPACE, "rgcn_layer_fwd: workspace too small (see rgcn_layer_workspace_bytes)");
+    const int64_t tld = direct ? ldo : np;
+    const int tn = direct ? fout : np;
+    int rc;
+    WPrep wp{weight, root, g->R, fin, fout, kp, np, false, wfrag};
+    if ((rc = launch_wprep(wp, st))) return rc;
+    TilePass p{};
+    p.brc = &g->brc[RGCN_BRC_FWD];
+    p.n_nodes = g->N;
+    p.self_rel = g->R;
+    p.feat = x; p.ldf = ldx; p.kin = fin;
+    p.aux = aux;
+    p.wfrag = wfrag;
+    p.bias = bias; p.nbias = fout;
+    p.out = target; p.ldo = tld; p.nout = tn;
+    p.kp = kp; p.np = np;
+    p.relu_in = relu;
+    if ((rc = launch_chunk_prepass(p, st))) return rc;
+    RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->N * tld * 4, st));
+    if ((rc = launch_tile_pass(p, g->num_sms, st))) return rc;
+    if (!direct) return launch_copy_cols(target, tld, out, ldo, g->N, fout, st);
+    return 0;
+}
+
+extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, const float* weight,
+                              const float* root, const float* gout, int64_t ldg, int32_t fout, float* gx,
+                              int64_t ldgx, float* gweight, float* groot, float* gbias, uint32_t flags,
+                              void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!g || !x || !weight || !gout || fin <= 0 || fout <= 0 || ldx < fin || ldg < fout || (gx && ldgx < fin))
+        return fail(RGCN_ERR_INVALID_ARG, "rgcn_layer_bwd: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool relu = (flags & RGCN_F_RELU_IN) != 0;
+    const int kp = pad_dim(fin), np = pad_dim(fout);
+    const bool simple = (flags & RGCN_F_FORCE_SIMPLE) || !kp || !np;
+    const bool need_w = gweight || groot || gbias;
+    int rc;
+    if (gweight) RGCN_CUDA(cudaMemsetAsync(gweight, 0, (size_t)g->R * fin * fout * 4, st));
+    if (groot) RGCN_CUDA(cudaMemsetAsync(groot, 0, (size_t)fin * fout * 4, st));
+    if (gbias) RGCN_CUDA(cudaMemsetAsync(gbias, 0, (size_t)fout * 4, st));
+    if (simple) {
+        if (need_w) {
+            SimpleWGrad p{};
+            p.brc = &g->brc[RGCN_BRC_FWD_REL];
+            p.n_nodes = g->N; p.self_rel = g->R;
+            p.feat = x; p.ldf = ldx; p.kin = fin;
+            p.gout = gout; p.ldg = ldg; p.nout = fout;
+            p.gweight = gweight; p.groot = groot; p.gbias = gbias; p.relu_in = relu;
+            if ((rc = launch_simple_wgrad(p, st))) return rc;
+        }
+        if (gx) {
+            RGCN_CUDA(cudaMemset2DAsync(gx, (size_t)ldgx * 4, 0, (size_t)fin * 4, (size_t)g->N, st));
+            SimplePass p{};
+            p.brc = &g->brc[RGCN_BRC_BWD];
+            p.n_nodes = g->N; p.self_rel = g->R;
+            p.feat = gout; p.ldf = ldg; p.kin = fout;
+            p.weight = weight; p.root = root; p.bias = nullptr; p.transpose = true; p.w_rows = fin; p.w_cols = fout;
+            p.out = gx; p.ldo = ldgx; p.nout = fin; p.relu_in = false;
+            if ((rc = launch_simple_pass(p, st))) return rc;
+            if (relu && (rc = launch_relu_mask(gx, ldgx, x, ldx, g->N, fin, st))) return rc;
+        }
+        return 0;
+    }
+    WsCarver ws(workspace, workspace_bytes);
+    float* xaux = ws.take<float>((int64_t)g->brc[RGCN_BRC_FWD_REL].num_chunks * kp);
+    float4* wtfrag = (float4*)ws.take<float>((int64_t)(g->R + 1) * kp * np * 2);
+    float* gaux = ws.take<float>((int64_t)g->brc[RGCN_BRC_BWD].num_chunks * np);
+    const bool direct = gx && direct_target(gx, ldgx, fin);
+    float* target = gx ? (direct ? gx : ws.take<float>((int64_t)g->N * kp)) : nullptr;
+    if (!ws.ok) return fail(RGCN_ERR_WORKSPACE, "rgcn_layer_bwd: workspace too small (see rgcn_layer_workspace_bytes)");
+    if (need_w) {
+        // chunk rows of x in the relation-major ordering, then dW / droot / dbias
+        TilePass pre{};
+        pre.brc = &g->brc[RGCN_BRC_FWD_REL];
+        pre.n_nodes = g->N;
+        pre.feat = x; pre.ldf = ldx; pre.kin = fin; pre.aux = xaux; pre.kp = kp; pre.relu_in = relu;
+        if ((rc = launch_chunk_prepass(pre, st))) return rc;
+        WGradPass p{};
+        p.brc = &g->brc[RGCN_BRC_FWD_REL];
+        p.n_nodes = g->N; p.self_rel = g->R;
+        p.feat = x; p.ldf = ldx; p.kin = fin; p.aux = xaux;
+        p.gout = gout; p.ldg = ldg; p.nout = fout;
+        p.gweight = gweight; p.groot = groot; p.gbias = gbias;
+        p.kp = kp; p.np = np; p.relu_in = relu;
+        if ((rc = launch_wgrad_pass(p, g->num_sms, st))) return rc;
+    }
+    if (gx) {
+        // dx: transposed structure, gathers gout rows (width fout), B = W^T : [np x kp]
+        WPrep wp{weight, root, g->R, fin, fout, np, kp, true, wtfrag};
+        if ((rc = launch_wprep(wp, st))) return rc;
+        const int64_t tld = direct ? ldgx : kp;
+        TilePass p{};
+        p.brc = &g->brc[RGCN_BRC_BWD];
+        p.n_nodes = g->N; p.self_rel = g->R;
+        p.feat = gout; p.ldf = ldg; p.kin = fout;
+        p.aux = gaux;
+        p.wfrag = wtfrag;
+        p.bias = nullptr; p.nbias = 0;
+        p.out = target; p.ldo = tld; p.nout = direct ? fin : kp;
+        p.kp = np; p.np = kp;
+        p.relu_in = false;
+        if ((rc = launch_chunk_prepass(p, st))) return rc;
+        RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->N * tld * 4, st));
+        if ((rc = launch_tile_pass(p, g->num_sms, st))) return rc;
+        if (!direct && (rc = launch_copy_cols(target, tld, gx, ldgx, g->N, fin, st))) return rc;
+        if (relu && (rc = launch_relu_mask(gx, ldgx, x, ldx, g->N, fin, st))) return rc;
+    }
+    return 0;
+}

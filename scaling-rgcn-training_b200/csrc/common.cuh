@@ -1,0 +1,136 @@
+// common.cuh — shared declarations of the sm_100a R-GCN engine (internal; the public C ABI is
+// include/rgcn_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/rgcn_b200.h"
+
+namespace rgcn {
+
+constexpr int BS = 16;                        // segments per batch (MMA M)
+constexpr uint32_t LAST_FLAG = 0x80000000u;   // bit 31 of e_idx: last entry of its segment
+constexpr uint32_t IDX_MASK = 0x7fffffffu;
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define RGCN_CUDA(call)                                                                      \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            return ::rgcn::fail((int)_e, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+        }                                                                                    \
+    } while (0)
+
+// One blocked relational CSR (spec: oracle/csr_oracle.py; built by graph_build.cu).
+struct Brc {
+    int64_t num_entries0 = 0;   // E + N (edges + self loops)
+    int64_t num_entries = 0;    // after chunking (E3)
+    int32_t num_seg = 0, num_chunks = 0, num_groups = 0, num_batches = 0;
+    int32_t range_nodes = 0;
+    int32_t* perm = nullptr;       // [E+N] entry id per sorted position
+    int32_t* seg_ptr0 = nullptr;   // [S+1] into raw_* (before chunking)
+    int32_t* seg_ptr = nullptr;    // [S+1] into e_*
+    int32_t* seg_own = nullptr;    // [S]
+    int32_t* seg_rel = nullptr;    // [S]
+    uint32_t* e_idx = nullptr;     // [E3] gather row | LAST_FLAG ; rows >= N are chunk rows
+    float* e_w = nullptr;          // [E3]
+    int32_t* raw_idx = nullptr;    // [E+N]
+    float* raw_w = nullptr;        // [E+N]
+    int32_t* chunk_beg = nullptr;  // [NC] into raw_*
+    int32_t* chunk_end = nullptr;  // [NC]
+    int32_t* bat_seg0 = nullptr;   // [NB]
+    int32_t* bat_info = nullptr;   // [NB] rel << 8 | nseg
+    int64_t bytes = 0;
+    void release();
+};
+
+}  // namespace rgcn
+
+struct rgcn_graph {
+    int64_t N = 0, E = 0;
+    int32_t R = 0;
+    int32_t range_nodes = 0, split_threshold = 0, chunk_size = 0;
+    int device = 0;
+    int num_sms = 148;
+    rgcn::Brc brc[3];
+    bool rel_is_fwd = false;   // FWD_REL aliases FWD (graph fits one range)
+    float* w_entry = nullptr;  // [E+N] 1/cnt of the forward segment, by entry id
+};
+
+namespace rgcn {
+
+// ---- launchers implemented in layer_kernels.cu / simple_kernels.cu / map_gather.cu --------------
+struct LayerDims {
+    int fin, fout;   // logical
+    int kp, np;      // padded to {16,32,64}; 0 when unsupported by the MMA path
+};
+int pad_dim(int f);   // 16/32/64 or 0
+
+// Tile pass: out[own] += sum over a BRC's segments of (weighted gathered rows) . B_rel
+// (forward: B = W ; transposed: B = W^T), self-loop relation carries root (+ bias).
+struct TilePass {
+    const Brc* brc;
+    int64_t n_nodes;
+    int self_rel;
+    const float* feat; int64_t ldf; int kin;       // gathered rows
+    float* aux;                                     // [num_chunks, kp] chunk rows (written by pre-pass)
+    const float4* wfrag;                            // [(R+1), kp/8, np/8, 32] fragment-ordered hi/lo split
+    const float* bias; int nbias;                   // nullable, [nbias]
+    float* out; int64_t ldo; int nout;              // accumulate target (zeroed by caller), nout % 4 == 0
+    int kp, np;
+    bool relu_in;
+};
+int launch_chunk_prepass(const TilePass& p, cudaStream_t st);
+int launch_tile_pass(const TilePass& p, int num_sms, cudaStream_t st);
+
+struct WPrep {
+    const float* weight;   // [R, fin, fout]
+    const float* root;     // [fin, fout] nullable
+    int R, fin, fout;
+    int kp, np;            // padded dims of the pass (kp x np B-operand)
+    bool transpose;        // B[k][n] = W[n][k]
+    float4* wfrag;
+};
+int launch_wprep(const WPrep& p, cudaStream_t st);
+
+struct WGradPass {
+    const Brc* brc;        // relation-major forward BRC
+    int64_t n_nodes;
+    int self_rel;
+    const float* feat; int64_t ldf; int kin;
+    float* aux;            // forward chunk rows [num_chunks, kp]
+    const float* gout; int64_t ldg; int nout;
+    float* gweight;        // [R, kin, nout] nullable (zeroed by caller)
+    float* groot;          // [kin, nout] nullable (zeroed)
+    float* gbias;          // [nout] nullable (zeroed)
+    int kp, np;
+    bool relu_in;
+};
+int launch_wgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st);
+
+int launch_copy_cols(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t n, int cols, cudaStream_t st);
+int launch_relu_mask(float* g, int64_t ldg, const float* pre, int64_t ldp, int64_t n, int cols, cudaStream_t st);
+
+// generic scalar path (any fin/fout)
+struct SimplePass {
+    const Brc* brc; int64_t n_nodes; int self_rel;
+    const float* feat; int64_t ldf; int kin;
+    const float* weight; const float* root; const float* bias; bool transpose; int w_rows, w_cols;   // W_r is [w_rows, w_cols]
+    float* out; int64_t ldo; int nout;
+    bool relu_in;
+};
+int launch_simple_pass(const SimplePass& p, cudaStream_t st);
+struct SimpleWGrad {
+    const Brc* brc; int64_t n_nodes; int self_rel;
+    const float* feat; int64_t ldf; int kin;
+    const float* gout; int64_t ldg; int nout;
+    float* gweight; float* groot; float* gbias;
+    bool relu_in;
+};
+int launch_simple_wgrad(const SimpleWGrad& p, cudaStream_t st);
+
+}  // namespace rgcn

@@ -1,0 +1,489 @@
+// graph_build.cu — K0: one-time on-device build of the blocked relational CSRs (BRC).
+//
+// Consumes the reference's edge tensors as they are (graphs/graph.py:55-69: int64, strided
+// views of one [E,3] buffer, inverse edges as relation 2r+1, multi-edges kept) and produces
+// the relation-then-owner sorted structures every layer kernel reads.  Integer work only;
+// checked bit-exactly against oracle/csr_oracle.py.  Device-wide sort/scan primitives are CUB
+// (ships with the CUDA toolkit); everything else is hand-written.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace rgcn {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+const char* last_error_cstr() { return g_last_error.c_str(); }
+
+void Brc::release() {
+    void* ptrs[] = {perm, seg_ptr0, seg_ptr, seg_own, seg_rel, e_idx, e_w, raw_idx, raw_w,
+                    chunk_beg, chunk_end, bat_seg0, bat_info};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    *this = Brc();
+}
+
+namespace {
+
+template <typename T>
+struct Dev {   // scratch buffer freed at scope exit
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        n = count;
+        return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    }
+    T* take() {
+        T* r = p;
+        p = nullptr;
+        return r;
+    }
+    ~Dev() {
+        if (p) cudaFree(p);
+    }
+};
+
+constexpr int TPB = 256;
+inline int blocks_for(int64_t n) { return (int)std::max<int64_t>(1, (n + TPB - 1) / TPB); }
+
+// entries [0,E): edges (validated) ; [E, E+N): self loops with relation R
+__global__ void k_entries(const int64_t* __restrict__ src, int64_t ss, const int64_t* __restrict__ dst, int64_t ds,
+                          const int64_t* __restrict__ et, int64_t es, int64_t E, int64_t N, int R,
+                          int32_t* __restrict__ src32, int32_t* __restrict__ dst32, int32_t* __restrict__ rel32,
+                          int* __restrict__ err) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= E + N) return;
+    if (i < E) {
+        int64_t s = src[i * ss], d = dst[i * ds], r = et[i * es];
+        if (s < 0 || s >= N || d < 0 || d >= N || r < 0 || r >= R) {
+            atomicOr(err, 1);
+            s = d = 0;
+            r = 0;
+        }
+        src32[i] = (int32_t)s;
+        dst32[i] = (int32_t)d;
+        rel32[i] = (int32_t)r;
+    } else {
+        int32_t v = (int32_t)(i - E);
+        src32[i] = v;
+        dst32[i] = v;
+        rel32[i] = R;
+    }
+}
+
+__global__ void k_keys(const int32_t* __restrict__ own, const int32_t* __restrict__ rel, int64_t n2, int R, int NR,
+                       uint64_t* __restrict__ key, int32_t* __restrict__ eid) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    uint64_t o = (uint64_t)own[i];
+    key[i] = (o / NR) * ((uint64_t)(R + 1) * NR) + (uint64_t)rel[i] * NR + (o % NR);
+    eid[i] = (int32_t)i;
+}
+
+__global__ void k_heads(const uint64_t* __restrict__ skey, int64_t n2, int32_t* __restrict__ head) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    head[i] = (i == 0 || skey[i] != skey[i - 1]) ? 1 : 0;
+}
+
+// segid = inclusive_scan(head) - 1 ; at heads record the segment's start / owner / relation
+__global__ void k_seg_fill(const uint64_t* __restrict__ skey, const int32_t* __restrict__ head,
+                           const int32_t* __restrict__ scan, int64_t n2, int R, int NR, int32_t* __restrict__ seg_ptr0,
+                           int32_t* __restrict__ seg_own, int32_t* __restrict__ seg_rel) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n2 || !head[i]) return;
+    int32_t s = scan[i] - 1;
+    uint64_t k = skey[i];
+    uint64_t span = (uint64_t)(R + 1) * NR;
+    uint64_t rng = k / span, rem = k % span;
+    seg_ptr0[s] = (int32_t)i;
+    seg_rel[s] = (int32_t)(rem / NR);
+    seg_own[s] = (int32_t)(rng * NR + rem % NR);
+}
+
+__global__ void k_weights(const int32_t* __restrict__ perm, const int32_t* __restrict__ scan,
+                          const int32_t* __restrict__ seg_ptr0, int64_t n2, float* __restrict__ w_entry) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    int32_t s = scan[i] - 1;
+    int32_t cnt = seg_ptr0[s + 1] - seg_ptr0[s];
+    w_entry[perm[i]] = 1.0f / (float)cnt;
+}
+
+__global__ void k_raw(const int32_t* __restrict__ perm, const int32_t* __restrict__ gat,
+                      const float* __restrict__ w_entry, int64_t n2, int32_t* __restrict__ raw_idx,
+                      float* __restrict__ raw_w) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    int32_t e = perm[i];
+    raw_idx[i] = gat[e];
+    raw_w[i] = w_entry[e];
+}
+
+__global__ void k_seg_counts(const int32_t* __restrict__ seg_ptr0, int32_t S, int T, int CH,
+                             int32_t* __restrict__ out_cnt, int32_t* __restrict__ nchunk) {
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    int32_t cnt = seg_ptr0[s + 1] - seg_ptr0[s];
+    int32_t nc = cnt > T ? (cnt + CH - 1) / CH : 0;
+    nchunk[s] = nc;
+    out_cnt[s] = cnt > T ? nc : cnt;
+}
+
+__global__ void k_compact(const int32_t* __restrict__ scan, const int32_t* __restrict__ seg_ptr0,
+                          const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ chunk_base,
+                          const int32_t* __restrict__ raw_idx, const float* __restrict__ raw_w, int64_t n2, int64_t N,
+                          int T, int CH, uint32_t* __restrict__ e_idx, float* __restrict__ e_w,
+                          int32_t* __restrict__ chunk_beg, int32_t* __restrict__ chunk_end) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    int32_t s = scan[i] - 1;
+    int32_t a = seg_ptr0[s], b = seg_ptr0[s + 1];
+    int32_t cnt = b - a, p = (int32_t)i - a;
+    int32_t o = seg_ptr[s];
+    if (cnt <= T) {
+        e_idx[o + p] = (uint32_t)raw_idx[i] | (p == cnt - 1 ? LAST_FLAG : 0u);
+        e_w[o + p] = raw_w[i];
+    } else if (p % CH == 0) {
+        int32_t j = p / CH, nc = (cnt + CH - 1) / CH;
+        int32_t c = chunk_base[s] + j;
+        chunk_beg[c] = (int32_t)i;
+        chunk_end[c] = min((int32_t)i + CH, b);
+        e_idx[o + j] = (uint32_t)(N + c) | (j == nc - 1 ? LAST_FLAG : 0u);
+        e_w[o + j] = 1.0f;
+    }
+}
+
+__global__ void k_group_heads(const int32_t* __restrict__ seg_own, const int32_t* __restrict__ seg_rel, int32_t S,
+                              int NR, int32_t* __restrict__ ghead) {
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    int h = 1;
+    if (s > 0) h = (seg_rel[s] != seg_rel[s - 1]) || (seg_own[s] / NR != seg_own[s - 1] / NR);
+    ghead[s] = h;
+}
+
+__global__ void k_group_fill(const int32_t* __restrict__ ghead, const int32_t* __restrict__ gscan, int32_t S,
+                             int32_t* __restrict__ grp_seg) {
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= S || !ghead[s]) return;
+    grp_seg[gscan[s] - 1] = (int32_t)s;
+}
+
+__global__ void k_group_nb(const int32_t* __restrict__ grp_seg, int32_t G, int32_t* __restrict__ nb) {
+    int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    nb[g] = (grp_seg[g + 1] - grp_seg[g] + BS - 1) / BS;
+}
+
+__global__ void k_batch_fill(const int32_t* __restrict__ bat_base, const int32_t* __restrict__ grp_seg,
+                             const int32_t* __restrict__ seg_rel, int32_t G, int32_t NB,
+                             int32_t* __restrict__ bat_seg0, int32_t* __restrict__ bat_info) {
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= NB) return;
+    // largest g with bat_base[g] <= b
+    int lo = 0, hi = G - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (bat_base[mid] <= (int32_t)b) lo = mid;
+        else hi = mid - 1;
+    }
+    int32_t s0 = grp_seg[lo] + ((int32_t)b - bat_base[lo]) * BS;
+    int32_t ns = min(BS, grp_seg[lo + 1] - s0);
+    bat_seg0[b] = s0;
+    bat_info[b] = (seg_rel[s0] << 8) | ns;
+}
+
+__global__ void k_set_i32(int32_t* p, int32_t v) { *p = v; }
+
+template <typename T>
+cudaError_t scan_inclusive(const T* in, T* out, int64_t n, cudaStream_t st) {
+    size_t tmp_bytes = 0;
+    cudaError_t e = cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, in, out, (int)n, st);
+    if (e != cudaSuccess) return e;
+    Dev<char> tmp;
+    if ((e = tmp.alloc(tmp_bytes)) != cudaSuccess) return e;
+    e = cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, in, out, (int)n, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);
+}
+template <typename T>
+cudaError_t scan_exclusive(const T* in, T* out, int64_t n, cudaStream_t st) {
+    size_t tmp_bytes = 0;
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, st);
+    if (e != cudaSuccess) return e;
+    Dev<char> tmp;
+    if ((e = tmp.alloc(tmp_bytes)) != cudaSuccess) return e;
+    e = cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, in, out, (int)n, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);
+}
+
+int bit_length(uint64_t v) {
+    int b = 0;
+    while (v) {
+        ++b;
+        v >>= 1;
+    }
+    return std::max(b, 1);
+}
+
+// Build one BRC.  own/gat/rel: [E+N] int32 entry arrays.  w_entry: in/out ([E+N]); computed when
+// compute_w.
+int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, int64_t n2, int64_t N, int R, int NR, int T,
+              int CH, float* w_entry, bool compute_w, cudaStream_t st, Brc* out) {
+    Brc b;
+    b.num_entries0 = n2;
+    b.range_nodes = NR;
+    Dev<uint64_t> key, skey;
+    Dev<int32_t> eid, head, scan;
+    RGCN_CUDA(key.alloc(n2));
+    RGCN_CUDA(skey.alloc(n2));
+    RGCN_CUDA(eid.alloc(n2));
+    RGCN_CUDA(head.alloc(n2));
+    RGCN_CUDA(scan.alloc(n2));
+    RGCN_CUDA(cudaMalloc(&b.perm, std::max<int64_t>(n2, 1) * 4));
+    k_keys<<<blocks_for(n2), TPB, 0, st>>>(own, rel, n2, R, NR, key.p, eid.p);
+    {
+        uint64_t nranges = (uint64_t)((N + NR - 1) / NR);
+        uint64_t max_key = std::max<uint64_t>(nranges, 1) * (uint64_t)(R + 1) * (uint64_t)NR;
+        int end_bit = std::min(64, bit_length(max_key));
+        size_t tmp_bytes = 0;
+        RGCN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key.p, skey.p, eid.p, b.perm, (int)n2, 0,
+                                                  end_bit, st));
+        Dev<char> tmp;
+        RGCN_CUDA(tmp.alloc(tmp_bytes));
+        RGCN_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key.p, skey.p, eid.p, b.perm, (int)n2, 0, end_bit,
+                                                  st));
+        RGCN_CUDA(cudaStreamSynchronize(st));
+    }
+    k_heads<<<blocks_for(n2), TPB, 0, st>>>(skey.p, n2, head.p);
+    RGCN_CUDA(scan_inclusive(head.p, scan.p, n2, st));
+    int32_t S = 0;
+    if (n2 > 0) RGCN_CUDA(cudaMemcpy(&S, scan.p + (n2 - 1), 4, cudaMemcpyDeviceToHost));
+    b.num_seg = S;
+    RGCN_CUDA(cudaMalloc(&b.seg_ptr0, (size_t)(S + 1) * 4));
+    RGCN_CUDA(cudaMalloc(&b.seg_ptr, (size_t)(S + 1) * 4));
+    RGCN_CUDA(cudaMalloc(&b.seg_own, std::max(S, 1) * 4));
+    RGCN_CUDA(cudaMalloc(&b.seg_rel, std::max(S, 1) * 4));
+    k_seg_fill<<<blocks_for(n2), TPB, 0, st>>>(skey.p, head.p, scan.p, n2, R, NR, b.seg_ptr0, b.seg_own, b.seg_rel);
+    k_set_i32<<<1, 1, 0, st>>>(b.seg_ptr0 + S, (int32_t)n2);
+    if (compute_w) k_weights<<<blocks_for(n2), TPB, 0, st>>>(b.perm, scan.p, b.seg_ptr0, n2, w_entry);
+    RGCN_CUDA(cudaMalloc(&b.raw_idx, std::max<int64_t>(n2, 1) * 4));
+    RGCN_CUDA(cudaMalloc(&b.raw_w, std::max<int64_t>(n2, 1) * 4));
+    k_raw<<<blocks_for(n2), TPB, 0, st>>>(b.perm, gat, w_entry, n2, b.raw_idx, b.raw_w);
+
+    // chunking of long segments
+    Dev<int32_t> out_cnt, nchunk, chunk_base;
+    RGCN_CUDA(out_cnt.alloc(S + 1));
+    RGCN_CUDA(nchunk.alloc(S + 1));
+    RGCN_CUDA(chunk_base.alloc(S + 1));
+    RGCN_CUDA(cudaMemsetAsync(out_cnt.p, 0, (size_t)(S + 1) * 4, st));
+    RGCN_CUDA(cudaMemsetAsync(nchunk.p, 0, (size_t)(S + 1) * 4, st));
+    k_seg_counts<<<blocks_for(S), TPB, 0, st>>>(b.seg_ptr0, S, T, CH, out_cnt.p, nchunk.p);
+    RGCN_CUDA(scan_exclusive(out_cnt.p, b.seg_ptr, (int64_t)S + 1, st));
+    RGCN_CUDA(scan_exclusive(nchunk.p, chunk_base.p, (int64_t)S + 1, st));
+    int32_t E3 = 0, NC = 0;
+    RGCN_CUDA(cudaMemcpy(&E3, b.seg_ptr + S, 4, cudaMemcpyDeviceToHost));
+    RGCN_CUDA(cudaMemcpy(&NC, chunk_base.p + S, 4, cudaMemcpyDeviceToHost));
+    b.num_entries = E3;
+    b.num_chunks = NC;
+    RGCN_CUDA(cudaMalloc(&b.e_idx, std::max(E3, 1) * 4));
+    RGCN_CUDA(cudaMalloc(&b.e_w, std::max(E3, 1) * 4));
+    RGCN_CUDA(cudaMalloc(&b.chunk_beg, std::max(NC, 1) * 4));
+    RGCN_CUDA(cudaMalloc(&b.chunk_end, std::max(NC, 1) * 4));
+    k_compact<<<blocks_for(n2), TPB, 0, st>>>(scan.p, b.seg_ptr0, b.seg_ptr, chunk_base.p, b.raw_idx, b.raw_w, n2, N, T,
+                                              CH, b.e_idx, b.e_w, b.chunk_beg, b.chunk_end);
+
+    // groups and batches
+    Dev<int32_t> ghead, gscan;
+    RGCN_CUDA(ghead.alloc(S));
+    RGCN_CUDA(gscan.alloc(S));
+    int32_t G = 0;
+    if (S > 0) {
+        k_group_heads<<<blocks_for(S), TPB, 0, st>>>(b.seg_own, b.seg_rel, S, NR, ghead.p);
+        RGCN_CUDA(scan_inclusive(ghead.p, gscan.p, S, st));
+        RGCN_CUDA(cudaMemcpy(&G, gscan.p + (S - 1), 4, cudaMemcpyDeviceToHost));
+    }
+    b.num_groups = G;
+    Dev<int32_t> grp_seg, nb, bat_base;
+    RGCN_CUDA(grp_seg.alloc(G + 1));
+    RGCN_CUDA(nb.alloc(G + 1));
+    RGCN_CUDA(bat_base.alloc(G + 1));
+    int32_t NB = 0;
+    if (G > 0) {
+        k_group_fill<<<blocks_for(S), TPB, 0, st>>>(ghead.p, gscan.p, S, grp_seg.p);
+        k_set_i32<<<1, 1, 0, st>>>(grp_seg.p + G, S);
+        RGCN_CUDA(cudaMemsetAsync(nb.p, 0, (size_t)(G + 1) * 4, st));
+        k_group_nb<<<blocks_for(G), TPB, 0, st>>>(grp_seg.p, G, nb.p);
+        RGCN_CUDA(scan_exclusive(nb.p, bat_base.p, (int64_t)G + 1, st));
+        RGCN_CUDA(cudaMemcpy(&NB, bat_base.p + G, 4, cudaMemcpyDeviceToHost));
+    }
+    b.num_batches = NB;
+    RGCN_CUDA(cudaMalloc(&b.bat_seg0, std::max(NB, 1) * 4));
+    RGCN_CUDA(cudaMalloc(&b.bat_info, std::max(NB, 1) * 4));
+    if (NB > 0)
+        k_batch_fill<<<blocks_for(NB), TPB, 0, st>>>(bat_base.p, grp_seg.p, b.seg_rel, G, NB, b.bat_seg0, b.bat_info);
+    RGCN_CUDA(cudaStreamSynchronize(st));
+    RGCN_CUDA(cudaGetLastError());
+    b.bytes = n2 * 12 + (int64_t)S * 16 + (int64_t)E3 * 8 + (int64_t)NC * 8 + (int64_t)NB * 8;
+    *out = b;
+    return 0;
+}
+
+}  // namespace
+}  // namespace rgcn
+
+using namespace rgcn;
+
+extern "C" const char* rgcn_last_error(void) { return rgcn::last_error_cstr(); }
+extern "C" int rgcn_abi_version(void) { return RGCN_B200_ABI_VERSION; }
+
+extern "C" void rgcn_graph_destroy(rgcn_graph* g) {
+    if (!g) return;
+    for (int i = 0; i < 3; ++i) {
+        if (i == RGCN_BRC_FWD_REL && g->rel_is_fwd) continue;
+        g->brc[i].release();
+    }
+    if (g->w_entry) cudaFree(g->w_entry);
+    delete g;
+}
+
+extern "C" int rgcn_graph_create(const int64_t* src, int64_t src_stride, const int64_t* dst, int64_t dst_stride,
+                                 const int64_t* etype, int64_t etype_stride, int64_t num_edges, int64_t num_nodes,
+                                 int32_t num_relations, int32_t range_nodes, int32_t split_threshold,
+                                 int32_t chunk_size, void* stream, rgcn_graph** out) {
+    if (!out) return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_create: out is null");
+    *out = nullptr;
+    if (num_edges < 0 || num_nodes <= 0 || num_relations <= 0)
+        return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_create: need num_edges >= 0, num_nodes > 0, num_relations > 0");
+    if (num_edges > 0 && (!src || !dst || !etype))
+        return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_create: null edge tensor");
+    if (num_edges + num_nodes >= (int64_t)0x7fffffff - 65536 || num_relations >= (1 << 22))
+        return fail(RGCN_ERR_UNSUPPORTED, "rgcn_graph_create: graph too large for int32 indexing");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(ce != cudaSuccess ? (int)ce : (int)cudaErrorNoDevice,
+                    "rgcn_graph_create: no CUDA device (the engine has no CPU fallback)");
+    cudaStream_t st = (cudaStream_t)stream;
+    rgcn_graph* g = new rgcn_graph();
+    g->N = num_nodes;
+    g->E = num_edges;
+    g->R = num_relations;
+    cudaGetDevice(&g->device);
+    cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, g->device);
+    g->split_threshold = split_threshold > 0 ? split_threshold : 256;
+    g->chunk_size = chunk_size > 0 ? chunk_size : 256;
+    int64_t nr = range_nodes > 0 ? range_nodes : 4096;
+    // small graphs: one range (pure relation-major); large: blocked so accumulate targets stay L2-hot
+    if (nr >= num_nodes) nr = num_nodes;
+    g->range_nodes = (int32_t)nr;
+
+    int64_t n2 = num_edges + num_nodes;
+    Dev<int32_t> src32, dst32, rel32;
+    Dev<int> err;
+    int rc = 0;
+    auto bail = [&](int code) {
+        rgcn_graph_destroy(g);
+        return code;
+    };
+#define RGCN_CUDA_G(call)                                                                          \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return bail(fail((int)_e, std::string(#call) + ": " + cudaGetErrorString(_e)));        \
+    } while (0)
+    RGCN_CUDA_G(src32.alloc(n2));
+    RGCN_CUDA_G(dst32.alloc(n2));
+    RGCN_CUDA_G(rel32.alloc(n2));
+    RGCN_CUDA_G(err.alloc(1));
+    RGCN_CUDA_G(cudaMemsetAsync(err.p, 0, sizeof(int), st));
+    k_entries<<<blocks_for(n2), TPB, 0, st>>>(src, src_stride, dst, dst_stride, etype, etype_stride, num_edges,
+                                              num_nodes, num_relations, src32.p, dst32.p, rel32.p, err.p);
+    int herr = 0;
+    RGCN_CUDA_G(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RGCN_CUDA_G(cudaStreamSynchronize(st));
+    if (herr)
+        return bail(fail(RGCN_ERR_INDEX_RANGE,
+                         "rgcn_graph_create: edge_index outside [0,num_nodes) or edge_type outside [0,num_relations)"));
+    RGCN_CUDA_G(cudaMalloc(&g->w_entry, std::max<int64_t>(n2, 1) * 4));
+    const int T = g->split_threshold, CH = g->chunk_size;
+    // forward: owner = dst, gather = src ; defines the per-(relation,dst) mean weights
+    if ((rc = build_brc(dst32.p, src32.p, rel32.p, n2, num_nodes, num_relations, (int)nr, T, CH, g->w_entry, true, st,
+                        &g->brc[RGCN_BRC_FWD])))
+        return bail(rc);
+    // transposed: owner = src, gather = dst, same per-entry weights
+    if ((rc = build_brc(src32.p, dst32.p, rel32.p, n2, num_nodes, num_relations, (int)nr, T, CH, g->w_entry, false, st,
+                        &g->brc[RGCN_BRC_BWD])))
+        return bail(rc);
+    if (nr >= num_nodes) {
+        g->brc[RGCN_BRC_FWD_REL] = g->brc[RGCN_BRC_FWD];
+        g->rel_is_fwd = true;
+    } else {
+        if ((rc = build_brc(dst32.p, src32.p, rel32.p, n2, num_nodes, num_relations, (int)num_nodes, T, CH, g->w_entry,
+                            false, st, &g->brc[RGCN_BRC_FWD_REL])))
+            return bail(rc);
+    }
+#undef RGCN_CUDA_G
+    *out = g;
+    return 0;
+}
+
+extern "C" int rgcn_graph_query(const rgcn_graph* g, int32_t brc, int32_t key, int64_t* out) {
+    if (!g || !out || brc < 0 || brc > 2) return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_query: bad argument");
+    const Brc& b = g->brc[brc];
+    switch (key) {
+        case RGCN_Q_NUM_NODES: *out = g->N; break;
+        case RGCN_Q_NUM_EDGES: *out = g->E; break;
+        case RGCN_Q_NUM_RELATIONS: *out = g->R; break;
+        case RGCN_Q_NUM_SEGMENTS: *out = b.num_seg; break;
+        case RGCN_Q_NUM_ENTRIES: *out = b.num_entries; break;
+        case RGCN_Q_NUM_CHUNKS: *out = b.num_chunks; break;
+        case RGCN_Q_NUM_GROUPS: *out = b.num_groups; break;
+        case RGCN_Q_NUM_BATCHES: *out = b.num_batches; break;
+        case RGCN_Q_RANGE_NODES: *out = b.range_nodes; break;
+        case RGCN_Q_DEVICE_BYTES:
+            *out = g->brc[0].bytes + g->brc[1].bytes + (g->rel_is_fwd ? 0 : g->brc[2].bytes) + (g->E + g->N) * 4;
+            break;
+        default: return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_query: unknown key");
+    }
+    return 0;
+}
+
+extern "C" int rgcn_graph_export(const rgcn_graph* g, int32_t brc, int32_t array, void* host_dst, int64_t bytes,
+                                 void* stream) {
+    if (!g || !host_dst || brc < 0 || brc > 2) return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_export: bad argument");
+    const Brc& b = g->brc[brc];
+    const void* p = nullptr;
+    int64_t n = 0;
+    switch (array) {
+        case RGCN_A_PERM: p = b.perm; n = b.num_entries0; break;
+        case RGCN_A_SEG_PTR: p = b.seg_ptr; n = (int64_t)b.num_seg + 1; break;
+        case RGCN_A_SEG_OWN: p = b.seg_own; n = b.num_seg; break;
+        case RGCN_A_SEG_REL: p = b.seg_rel; n = b.num_seg; break;
+        case RGCN_A_SEG_PTR0: p = b.seg_ptr0; n = (int64_t)b.num_seg + 1; break;
+        case RGCN_A_E_IDX: p = b.e_idx; n = b.num_entries; break;
+        case RGCN_A_E_W: p = b.e_w; n = b.num_entries; break;
+        case RGCN_A_RAW_IDX: p = b.raw_idx; n = b.num_entries0; break;
+        case RGCN_A_RAW_W: p = b.raw_w; n = b.num_entries0; break;
+        case RGCN_A_CHUNK_BEG: p = b.chunk_beg; n = b.num_chunks; break;
+        case RGCN_A_CHUNK_END: p = b.chunk_end; n = b.num_chunks; break;
+        case RGCN_A_BAT_SEG0: p = b.bat_seg0; n = b.num_batches; break;
+        case RGCN_A_BAT_INFO: p = b.bat_info; n = b.num_batches; break;
+        default: return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_export: unknown array");
+    }
+    if (bytes != n * 4) return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_export: byte count mismatch");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    RGCN_CUDA(cudaMemcpyAsync(host_dst, p, (size_t)bytes, cudaMemcpyDeviceToHost, st));
+    RGCN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}

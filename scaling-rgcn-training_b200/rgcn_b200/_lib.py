@@ -1,0 +1,71 @@
+"""ctypes binding of librgcn_b200.so (C ABI: include/rgcn_b200.h).
+
+The library is the product; there is no Python or CPU fallback.  Importing this module
+without the built library raises immediately (build it with ``python -c "import
+__graft_entry__ as g; g.build()"`` or ``make -C scaling-rgcn-training_b200``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'librgcn_b200.so')
+
+# every symbol include/rgcn_b200.h declares
+EXPORTS = (
+    'rgcn_last_error', 'rgcn_abi_version', 'rgcn_graph_create', 'rgcn_graph_destroy', 'rgcn_graph_query',
+    'rgcn_graph_export', 'rgcn_layer_workspace_bytes', 'rgcn_layer_fwd', 'rgcn_layer_bwd', 'rgcn_map_gather',
+)
+
+BRC_FWD, BRC_BWD, BRC_FWD_REL = 0, 1, 2
+Q_NUM_NODES, Q_NUM_EDGES, Q_NUM_RELATIONS, Q_NUM_SEGMENTS, Q_NUM_ENTRIES, Q_NUM_CHUNKS, Q_NUM_GROUPS, \
+    Q_NUM_BATCHES, Q_RANGE_NODES, Q_DEVICE_BYTES = range(10)
+A_PERM, A_SEG_PTR, A_SEG_OWN, A_SEG_REL, A_SEG_PTR0, A_E_IDX, A_E_W, A_RAW_IDX, A_RAW_W, A_CHUNK_BEG, \
+    A_CHUNK_END, A_BAT_SEG0, A_BAT_INFO = range(13)
+F_RELU_IN, F_FORCE_SIMPLE = 1, 2
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(
+            f'{LIB_PATH} is missing: the CUDA engine is not built. There is no CPU fallback; '
+            'run __graft_entry__.build() (nvcc, sm_100a) first.')
+    lib = C.CDLL(LIB_PATH)
+    vp, i64, i32, u32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32
+    lib.rgcn_last_error.restype = C.c_char_p
+    lib.rgcn_last_error.argtypes = []
+    lib.rgcn_abi_version.restype = C.c_int
+    lib.rgcn_graph_create.restype = C.c_int
+    lib.rgcn_graph_create.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, i32, i32, vp, C.POINTER(vp)]
+    lib.rgcn_graph_destroy.restype = None
+    lib.rgcn_graph_destroy.argtypes = [vp]
+    lib.rgcn_graph_query.restype = C.c_int
+    lib.rgcn_graph_query.argtypes = [vp, i32, i32, C.POINTER(i64)]
+    lib.rgcn_graph_export.restype = C.c_int
+    lib.rgcn_graph_export.argtypes = [vp, i32, i32, vp, i64, vp]
+    lib.rgcn_layer_workspace_bytes.restype = i64
+    lib.rgcn_layer_workspace_bytes.argtypes = [vp, i32, i32, i32]
+    lib.rgcn_layer_fwd.restype = C.c_int
+    lib.rgcn_layer_fwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, i64, i32, u32, vp, i64, vp]
+    lib.rgcn_layer_bwd.restype = C.c_int
+    lib.rgcn_layer_bwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, i64, i32, vp, i64, vp, vp, vp, u32, vp, i64, vp]
+    lib.rgcn_map_gather.restype = C.c_int
+    lib.rgcn_map_gather.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i32, i64, i32, i32, vp, vp]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = '') -> None:
+    if rc != 0:
+        msg = load().rgcn_last_error()
+        raise EngineError(f'{what} failed (code {rc}): {msg.decode() if msg else "?"}')

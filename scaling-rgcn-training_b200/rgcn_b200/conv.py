@@ -1,0 +1,161 @@
+"""RGCNConv — the drop-in for ``torch_geometric.nn.RGCNConv`` (PyG 2.3.1) at the reference's
+call sites: constructed at /root/reference/model/layers.py:15-16,54-55,98-99, its ``weight``
+re-initialised in place at :17-18, called at :21,23,62,64,108,110, its parameters cloned at
+model/modelTrainer.py:28-35 and replaced by attribute assignment at model/layers.py:34-46.
+
+Same constructor, same parameter names/shapes, same forward signature.  The arithmetic runs
+only in librgcn_b200.so (hand-written sm_100a kernels); CPU tensors are rejected — there is no
+fallback path.  Parameters are read at call time, never cached, so in-place init and
+re-assignment keep working.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+from .graph import RGCNGraph, cached_graph
+
+
+def _glorot_(t: Tensor) -> None:   # PyG inits.glorot
+    a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+    with torch.no_grad():
+        t.uniform_(-a, a)
+
+
+def _ptr(t: Optional[Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _RGCNLayerFn(torch.autograd.Function):
+    """One R-GCN layer. forward -> rgcn_layer_fwd, backward -> rgcn_layer_bwd."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, root: Optional[Tensor], bias: Optional[Tensor],
+                graph: RGCNGraph, flags: int) -> Tensor:
+        lib = _lib.load()
+        if not x.is_cuda:
+            raise _lib.EngineError('RGCNConv: input is not a CUDA tensor; the B200 engine has no CPU path')
+        if x.dtype != torch.float32 or weight.dtype != torch.float32:
+            raise TypeError('RGCNConv: fp32 features and parameters expected')
+        if x.dim() != 2 or x.size(0) != graph.num_nodes:
+            raise ValueError(f'RGCNConv: x must be [num_nodes={graph.num_nodes}, in_channels]')
+        x = x if x.stride(1) == 1 or x.size(1) == 1 else x.contiguous()
+        weight = weight.contiguous()
+        root_c = root.contiguous() if root is not None else None
+        bias_c = bias.contiguous() if bias is not None else None
+        n, fin = x.shape
+        r, fin_w, fout = weight.shape
+        if fin_w != fin or r != graph.num_relations:
+            raise ValueError('RGCNConv: weight shape does not match input / num_relations')
+        out = torch.empty((n, fout), dtype=torch.float32, device=x.device)
+        ws_bytes = graph.workspace_bytes(fin, fout, False)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.rgcn_layer_fwd(graph.handle, x.data_ptr(), x.stride(0), fin, weight.data_ptr(), _ptr(root_c),
+                                    _ptr(bias_c), out.data_ptr(), out.stride(0), fout, flags, ws.data_ptr(), ws_bytes,
+                                    _stream(x.device))
+        _lib.check(rc, 'rgcn_layer_fwd')
+        ctx.graph, ctx.flags = graph, flags
+        ctx.has_root, ctx.has_bias = root is not None, bias is not None
+        ctx.save_for_backward(x, weight, root_c if root_c is not None else x.new_empty(0))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout: Tensor):
+        lib = _lib.load()
+        x, weight, root = ctx.saved_tensors
+        root = root if ctx.has_root else None
+        graph = ctx.graph
+        need_x, need_w, need_root, need_bias = ctx.needs_input_grad[:4]
+        need_root = need_root and ctx.has_root
+        need_bias = need_bias and ctx.has_bias
+        gout = gout.contiguous()
+        n, fin = x.shape
+        fout = weight.size(2)
+        dev = x.device
+        gx = torch.empty((n, fin), dtype=torch.float32, device=dev) if need_x else None
+        gw = torch.empty_like(weight) if need_w else None
+        groot = torch.empty((fin, fout), dtype=torch.float32, device=dev) if need_root else None
+        gbias = torch.empty((fout,), dtype=torch.float32, device=dev) if need_bias else None
+        if need_x or need_w or need_root or need_bias:
+            ws_bytes = graph.workspace_bytes(fin, fout, True)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                rc = lib.rgcn_layer_bwd(graph.handle, x.data_ptr(), x.stride(0), fin, weight.data_ptr(), _ptr(root),
+                                        gout.data_ptr(), gout.stride(0), fout, _ptr(gx), fin, _ptr(gw), _ptr(groot),
+                                        _ptr(gbias), ctx.flags, ws.data_ptr(), ws_bytes, _stream(dev))
+            _lib.check(rc, 'rgcn_layer_bwd')
+        return gx, gw, groot, gbias, None, None
+
+
+def rgcn_layer(x: Tensor, weight: Tensor, root: Optional[Tensor], bias: Optional[Tensor], graph: RGCNGraph,
+               relu_in: bool = False, force_simple: bool = False) -> Tensor:
+    flags = (_lib.F_RELU_IN if relu_in else 0) | (_lib.F_FORCE_SIMPLE if force_simple else 0)
+    return _RGCNLayerFn.apply(x, weight, root, bias, graph, flags)
+
+
+class RGCNConv(nn.Module):
+    """``RGCNConv(in_channels, out_channels, num_relations, num_bases=None, ...)`` with parameters
+    ``weight [R, in, out]`` (or ``[B, in, out]`` + ``comp [R, B]``), ``root [in, out]``, ``bias [out]``."""
+
+    def __init__(self, in_channels: int, out_channels: int, num_relations: int, num_bases: Optional[int] = None,
+                 num_blocks: Optional[int] = None, aggr: str = 'mean', root_weight: bool = True,
+                 is_sorted: bool = False, bias: bool = True, **kwargs) -> None:
+        super().__init__()
+        if num_blocks is not None:
+            raise NotImplementedError('RGCNConv(num_blocks=...) is outside the reference path (never used there)')
+        if aggr != 'mean':
+            raise NotImplementedError("RGCNConv: only aggr='mean' (PyG default, what the reference runs)")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_relations, self.num_bases, self.num_blocks = num_relations, num_bases, None
+        self.relu_in = False        # engine extension: apply ReLU to the input on load (fused F.relu)
+        self.force_simple = False   # engine extension: generic scalar kernels (cross-check)
+        w_slots = num_bases if num_bases is not None else num_relations
+        self.weight = nn.Parameter(torch.empty(w_slots, in_channels, out_channels))
+        if num_bases is not None:
+            self.comp = nn.Parameter(torch.empty(num_relations, num_bases))
+        else:
+            self.register_parameter('comp', None)
+        if root_weight:
+            self.root = nn.Parameter(torch.empty(in_channels, out_channels))
+        else:
+            self.register_parameter('root', None)
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        _glorot_(self.weight)
+        if self.comp is not None:
+            _glorot_(self.comp)
+        if self.root is not None:
+            _glorot_(self.root)
+        if self.bias is not None:
+            with torch.no_grad():
+                self.bias.zero_()
+
+    def forward(self, x: Tensor, edge_index, edge_type: Optional[Tensor] = None) -> Tensor:
+        if isinstance(edge_index, RGCNGraph):
+            graph = edge_index
+        else:
+            if edge_type is None:
+                raise ValueError('RGCNConv.forward: edge_type is required')
+            graph = cached_graph(edge_index, edge_type, x.size(0), self.num_relations)
+        weight = self.weight
+        if self.num_bases is not None:   # basis decomposition: tiny dense product, autograd carries comp/bases
+            weight = (self.comp @ weight.view(self.num_bases, -1)).view(
+                self.num_relations, self.in_channels, self.out_channels)
+        return rgcn_layer(x, weight, self.root, self.bias, graph, self.relu_in, self.force_simple)
+
+    def __repr__(self) -> str:
+        return f'{self.__class__.__name__}({self.in_channels}, {self.out_channels}, num_relations={self.num_relations})'

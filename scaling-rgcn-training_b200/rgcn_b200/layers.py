@@ -1,0 +1,108 @@
+"""Host-side mirror of the reference's three 2-layer R-GCN models (the API above the hot path):
+``Emb_Layers`` (/root/reference/model/layers.py:11-46), ``Emb_ATT_Layers`` (:49-87) and
+``Emb_MLP_Layers`` (:90-130).  Same class names, constructor argument order, attribute names
+(``embedding``, ``rgcn1``, ``rgcn2``, ``att``, ``lin1``, ``lin2``), ``forward(training_data,
+activation)``, ``reset_embedding`` / ``load_embedding`` / ``override_params`` behaviour — so the
+parity tests read like the reference and bench.py can run on a box where /root/reference does
+not exist.  Written against the engine's RGCNConv; one shared base instead of three copies.
+
+``fused=True`` (engine extension, default off = reference-identical op sequence) folds the
+inter-layer ``F.relu`` (model/layers.py:22) into the second layer's input load and backward.
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from .conv import RGCNConv
+
+
+class _TwoLayerRGCN(nn.Module):
+    def _build_convs(self, num_relations: int, hidden_l: int, num_labels: int, emb_dim: int) -> None:
+        self.rgcn1 = RGCNConv(in_channels=emb_dim, out_channels=hidden_l, num_relations=num_relations, num_bases=None)
+        self.rgcn2 = RGCNConv(hidden_l, num_labels, num_relations, num_bases=None)
+        for conv in (self.rgcn1, self.rgcn2):          # reference re-inits .weight only (layers.py:17-18)
+            nn.init.kaiming_uniform_(conv.weight, mode='fan_in')
+        self.fused = False
+
+    def _input_features(self) -> Tensor:
+        raise NotImplementedError
+
+    def forward(self, training_data, activation: Callable) -> Tensor:
+        x = self._input_features()
+        ei, et = training_data.edge_index, training_data.edge_type
+        h = self.rgcn1(x, ei, et)
+        if self.fused:
+            self.rgcn2.relu_in = True
+        else:
+            self.rgcn2.relu_in = False
+            h = F.relu(h)
+        return activation(self.rgcn2(h, ei, et))
+
+    def override_params(self, weight_1: Tensor, bias_1: Tensor, root_1: Tensor, weight_2: Tensor, bias_2: Tensor,
+                        root_2: Tensor, grad: bool = True) -> None:
+        """Weight transfer target (modelTrainer.py:26-39): re-wrap six tensors as fresh Parameters."""
+        new = {self.rgcn1: (weight_1, bias_1, root_1), self.rgcn2: (weight_2, bias_2, root_2)}
+        for conv, (w, b, r) in new.items():
+            for name, value in (('weight', w), ('bias', b), ('root', r)):
+                setattr(conv, name, nn.Parameter(value, requires_grad=grad))
+
+
+class Emb_Layers(_TwoLayerRGCN):
+    """summation / baseline / summary-graph model: x0 = embedding.weight."""
+
+    def __init__(self, num_relations: int, hidden_l: int, num_labels: int, num_nodes: int, emb_dim: int, _=None):
+        super().__init__()
+        self.embedding = nn.Embedding(num_nodes, emb_dim)
+        self._build_convs(num_relations, hidden_l, num_labels, emb_dim)
+
+    def _input_features(self) -> Tensor:
+        return self.embedding.weight
+
+    def reset_embedding(self, num_nodes: int, emb_dim: int) -> None:
+        self.embedding = nn.Embedding(num_nodes, emb_dim)
+
+    def load_embedding(self, embedding: Tensor, freeze: bool = True) -> None:
+        self.embedding = nn.Embedding.from_pretrained(embedding, freeze=freeze)
+
+
+class Emb_MLP_Layers(_TwoLayerRGCN):
+    """mlp transfer head: x0 = lin2(tanh(lin1(concat of S summary embeddings)))."""
+
+    def __init__(self, num_relations: int, hidden_l: int, num_labels: int, num_nodes: int, emb_dim: int, num_sums: int):
+        super().__init__()
+        width_in = num_sums * emb_dim
+        width_mid = round((width_in * (2 / 3)) + num_labels)
+        self.embedding = nn.Embedding(num_nodes, emb_dim)
+        self.lin1 = nn.Linear(in_features=width_in, out_features=width_mid)
+        self.lin2 = nn.Linear(in_features=width_mid, out_features=emb_dim)
+        for lin in (self.lin1, self.lin2):
+            nn.init.kaiming_uniform_(lin.weight, mode='fan_in')
+        self._build_convs(num_relations, hidden_l, num_labels, emb_dim)
+
+    def _input_features(self) -> Tensor:
+        return self.lin2(torch.tanh(self.lin1(self.embedding.weight)))
+
+    def load_embedding(self, embedding: Tensor, freeze: bool = True) -> None:
+        self.embedding = nn.Embedding.from_pretrained(embedding, freeze=freeze)
+
+
+class Emb_ATT_Layers(_TwoLayerRGCN):
+    """attention transfer head: MHA over the S stacked summary embeddings, first output row."""
+
+    def __init__(self, num_relations: int, hidden_l: int, num_labels: int, _, emb_dim: int, num_embs: int):
+        super().__init__()
+        self.embedding = None
+        self.att = nn.MultiheadAttention(embed_dim=emb_dim, num_heads=num_embs, dropout=0.2)
+        self._build_convs(num_relations, hidden_l, num_labels, emb_dim)
+
+    def _input_features(self) -> Tensor:
+        e = self.embedding
+        attended, _ = self.att(e, e, e, average_attn_weights=True)
+        return attended[0]
+
+    def load_embedding(self, embedding: Tensor, freeze: bool = True) -> None:
+        self.embedding = nn.Parameter(embedding, requires_grad=not freeze)
