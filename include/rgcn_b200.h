@@ -116,6 +116,16 @@ int rgcn_map_gather(const float* const* host_emb, const int32_t* const* host_idx
                     const float* const* host_fallback, int32_t num_sums,
                     int64_t num_nodes, int32_t feat, int32_t mode, float* out, void* stream);
 
+/* Instrumentation (no reference counterpart).  rgcn_kernel_launch_count: engine kernels launched
+ * by this process so far.  rgcn_profile_enable(1): every pass launch is bracketed by a CUDA-event
+ * pair on its own stream; rgcn_profile_collect synchronises those events, returns up to
+ * max_records (tag, dims[2], milliseconds) records and clears the log.  Tags: 1 weight-fragment
+ * prep, 2 chunk pre-pass, 3 forward tile pass, 4 dL/dx tile pass, 5 dL/dW pass, 6 column copy,
+ * 7 ReLU mask, 8 generic kernels, 9 map gather.  dims = (gathered width, output width). */
+int64_t rgcn_kernel_launch_count(void);
+int rgcn_profile_enable(int32_t on);
+int rgcn_profile_collect(int32_t* tags, int32_t* dims, float* ms, int32_t max_records, int32_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

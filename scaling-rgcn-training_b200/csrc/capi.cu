@@ -185,6 +185,7 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
         p.out = target; p.ldo = tld; p.nout = direct ? fin : kp;
         p.kp = np; p.np = kp;
         p.relu_in = false;
+        p.transposed = true;
         if ((rc = launch_chunk_prepass(p, st))) return rc;
         RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->N * tld * 4, st));
         if ((rc = launch_tile_pass(p, g->num_sms, st))) return rc;

@@ -17,6 +17,17 @@ constexpr uint32_t IDX_MASK = 0x7fffffffu;
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 
+// pass tags reported by rgcn_profile_collect (see include/rgcn_b200.h)
+enum { TAG_WPREP = 1, TAG_PREPASS = 2, TAG_TILE_FWD = 3, TAG_TILE_BWD = 4, TAG_WGRAD = 5, TAG_COPY = 6, TAG_MASK = 7,
+       TAG_SIMPLE = 8, TAG_MAP = 9 };
+void note_launch(int n);
+struct ProfScope {   // records a CUDA-event pair around a launch when profiling is enabled
+    ProfScope(int tag, int d0, int d1, cudaStream_t st);
+    ~ProfScope();
+    cudaStream_t st_;
+    int idx_;
+};
+
 #define RGCN_CUDA(call)                                                                      \
     do {                                                                                     \
         cudaError_t _e = (call);                                                             \
@@ -83,6 +94,7 @@ struct TilePass {
     float* out; int64_t ldo; int nout;              // accumulate target (zeroed by caller), nout % 4 == 0
     int kp, np;
     bool relu_in;
+    bool transposed;                                // dL/dx pass (profiling tag only)
 };
 int launch_chunk_prepass(const TilePass& p, cudaStream_t st);
 int launch_tile_pass(const TilePass& p, int num_sms, cudaStream_t st);

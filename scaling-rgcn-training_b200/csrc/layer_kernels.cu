@@ -530,6 +530,8 @@ int launch_chunk_prepass(const TilePass& p, cudaStream_t st) {
     const int wpb = 8;
     const int grid = (b.num_chunks + wpb - 1) / wpb;
     const int relu = p.relu_in ? 1 : 0;
+    ProfScope prof(TAG_PREPASS, p.kin, b.num_chunks, st);
+    note_launch(1);
     switch (p.kp) {
         case 16:
             k_chunk_sum<16><<<grid, wpb * 32, 0, st>>>(b.raw_idx, b.raw_w, b.chunk_beg, b.chunk_end, b.num_chunks,
@@ -553,6 +555,8 @@ int launch_wprep(const WPrep& p, cudaStream_t st) {
     const int KT = p.kp / 8, NT = p.np / 8;
     const int64_t total = (int64_t)(p.R + 1) * KT * NT * 32;
     const int tpb = 256;
+    ProfScope prof(TAG_WPREP, p.fin, p.fout, st);
+    note_launch(1);
     k_wprep<<<(int)((total + tpb - 1) / tpb), tpb, 0, st>>>(p.weight, p.root, p.R, p.fin, p.fout, KT, NT,
                                                             p.transpose ? 1 : 0, p.wfrag);
     RGCN_CUDA(cudaGetLastError());
@@ -583,6 +587,8 @@ int launch_tile_pass(const TilePass& p, int num_sms, cudaStream_t st) {
     a.ldo = p.ldo;
     a.nout = p.nout;
     a.relu_in = p.relu_in ? 1 : 0;
+    ProfScope prof(p.transposed ? TAG_TILE_BWD : TAG_TILE_FWD, p.kin, p.nout, st);
+    note_launch(1);
     RGCN_DISPATCH_KN(run_tile, p.kp, p.np, a, num_sms, st);
 }
 
@@ -610,12 +616,16 @@ int launch_wgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st) {
     a.groot = p.groot;
     a.gbias = p.gbias;
     a.relu_in = p.relu_in ? 1 : 0;
+    ProfScope prof(TAG_WGRAD, p.kin, p.nout, st);
+    note_launch(1);
     RGCN_DISPATCH_KN(run_wgrad, p.kp, p.np, a, num_sms, st);
 }
 
 int launch_copy_cols(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t n, int cols, cudaStream_t st) {
     const int64_t total = n * cols;
     if (total == 0) return 0;
+    ProfScope prof(TAG_COPY, cols, 0, st);
+    note_launch(1);
     k_copy_cols<<<(int)((total + 255) / 256), 256, 0, st>>>(src, lds, dst, ldd, n, cols);
     RGCN_CUDA(cudaGetLastError());
     return 0;
@@ -624,6 +634,8 @@ int launch_copy_cols(const float* src, int64_t lds, float* dst, int64_t ldd, int
 int launch_relu_mask(float* g, int64_t ldg, const float* pre, int64_t ldp, int64_t n, int cols, cudaStream_t st) {
     const int64_t total = n * cols;
     if (total == 0) return 0;
+    ProfScope prof(TAG_MASK, cols, 0, st);
+    note_launch(1);
     k_relu_mask<<<(int)((total + 255) / 256), 256, 0, st>>>(g, ldg, pre, ldp, n, cols);
     RGCN_CUDA(cudaGetLastError());
     return 0;

@@ -69,6 +69,8 @@ extern "C" int rgcn_map_gather(const float* const* host_emb, const int32_t* cons
     a.mode = mode;
     a.out = out;
     const int wpb = 8;
+    ProfScope prof(TAG_MAP, feat, num_sums, (cudaStream_t)stream);
+    note_launch(1);
     k_map_gather<<<(int)((num_nodes + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(a);
     RGCN_CUDA(cudaGetLastError());
     return 0;

@@ -96,6 +96,8 @@ int launch_simple_pass(const SimplePass& p, cudaStream_t st) {
     a.out = p.out; a.ldo = p.ldo; a.nout = p.nout; a.self_rel = p.self_rel; a.relu_in = p.relu_in ? 1 : 0;
     const size_t smem = (size_t)SW * p.kin * sizeof(float);
     if (smem > 48 * 1024) return fail(RGCN_ERR_UNSUPPORTED, "simple pass: feature width too large");
+    ProfScope prof(TAG_SIMPLE, p.kin, p.nout, st);
+    note_launch(1);
     k_simple_pass<<<(b.num_seg + SW - 1) / SW, SW * 32, smem, st>>>(a);
     RGCN_CUDA(cudaGetLastError());
     return 0;
@@ -111,6 +113,8 @@ int launch_simple_wgrad(const SimpleWGrad& p, cudaStream_t st) {
     a.self_rel = p.self_rel; a.relu_in = p.relu_in ? 1 : 0;
     const size_t smem = (size_t)SW * p.kin * sizeof(float);
     if (smem > 48 * 1024) return fail(RGCN_ERR_UNSUPPORTED, "simple wgrad: feature width too large");
+    ProfScope prof(TAG_SIMPLE, p.kin, p.nout, st);
+    note_launch(1);
     k_simple_wgrad<<<(b.num_seg + SW - 1) / SW, SW * 32, smem, st>>>(a);
     RGCN_CUDA(cudaGetLastError());
     return 0;

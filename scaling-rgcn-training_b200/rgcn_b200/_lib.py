@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'librgcn_b200.so')
 EXPORTS = (
     'rgcn_last_error', 'rgcn_abi_version', 'rgcn_graph_create', 'rgcn_graph_destroy', 'rgcn_graph_query',
     'rgcn_graph_export', 'rgcn_layer_workspace_bytes', 'rgcn_layer_fwd', 'rgcn_layer_bwd', 'rgcn_map_gather',
+    'rgcn_kernel_launch_count', 'rgcn_profile_enable', 'rgcn_profile_collect',
 )
 
 BRC_FWD, BRC_BWD, BRC_FWD_REL = 0, 1, 2
@@ -61,6 +62,12 @@ def load():
     lib.rgcn_layer_bwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, i64, i32, vp, i64, vp, vp, vp, u32, vp, i64, vp]
     lib.rgcn_map_gather.restype = C.c_int
     lib.rgcn_map_gather.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i32, i64, i32, i32, vp, vp]
+    lib.rgcn_kernel_launch_count.restype = i64
+    lib.rgcn_kernel_launch_count.argtypes = []
+    lib.rgcn_profile_enable.restype = C.c_int
+    lib.rgcn_profile_enable.argtypes = [i32]
+    lib.rgcn_profile_collect.restype = C.c_int
+    lib.rgcn_profile_collect.argtypes = [vp, vp, vp, i32, C.POINTER(i32)]
     _lib = lib
     return lib
 
@@ -69,3 +76,28 @@ def check(rc: int, what: str = '') -> None:
     if rc != 0:
         msg = load().rgcn_last_error()
         raise EngineError(f'{what} failed (code {rc}): {msg.decode() if msg else "?"}')
+
+
+PASS_NAMES = {1: 'wprep', 2: 'chunk_prepass', 3: 'tile_fwd', 4: 'tile_dx', 5: 'wgrad', 6: 'copy_cols', 7: 'relu_mask',
+              8: 'generic', 9: 'map_gather'}
+
+
+def launch_count() -> int:
+    return int(load().rgcn_kernel_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    load().rgcn_profile_enable(1 if on else 0)
+
+
+def profile_collect(max_records: int = 65536):
+    """-> list of (pass name, (gathered width, output width), milliseconds)."""
+    import numpy as np
+    tags = np.zeros(max_records, dtype=np.int32)
+    dims = np.zeros(2 * max_records, dtype=np.int32)
+    ms = np.zeros(max_records, dtype=np.float32)
+    n = C.c_int32()
+    check(load().rgcn_profile_collect(tags.ctypes.data, dims.ctypes.data, ms.ctypes.data, max_records, C.byref(n)),
+          'rgcn_profile_collect')
+    return [(PASS_NAMES.get(int(tags[i]), str(int(tags[i]))), (int(dims[2 * i]), int(dims[2 * i + 1])), float(ms[i]))
+            for i in range(n.value)]

@@ -1,0 +1,334 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs, against the committed golden fixtures, and through
+size-independent properties at larger sizes.  Tolerance (BASELINE.json north_star): integer
+work bit-exact; fp32 outputs and gradients within 1e-5 relative (max-norm), identical argmax."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_graph, load_golden, rel_err
+
+import csr_oracle
+import rgcn_oracle
+from rgcn_b200 import (Data, Emb_ATT_Layers, Emb_Layers, Emb_MLP_Layers, RGCNConv, RGCNGraph, _lib, map_gather,
+                       rgcn_layer)
+from rgcn_b200.synthetic import am_shape, random_multigraph
+from rgcn_b200.trainer import bce_loss, ce_loss
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = 'cuda:0'
+
+GRAPHS = ['TEST_complete', 'TEST_sum_in_out', 'AIFB_sum_in', 'AIFB_sum_in_out', 'MUTAG_bisim_k1', 'AIFB_bisim_k3']
+
+
+# ------------------------------------------------------------------ K0: integer, bit-exact
+def _check_brc(g, which, want):
+    S = g.query(_lib.Q_NUM_SEGMENTS, which)
+    assert S == want['num_seg']
+    assert g.query(_lib.Q_NUM_CHUNKS, which) == want['num_chunks']
+    assert g.query(_lib.Q_NUM_BATCHES, which) == want['num_batches']
+    assert g.query(_lib.Q_NUM_GROUPS, which) == want['num_groups']
+    pairs = [(_lib.A_PERM, 'perm'), (_lib.A_SEG_PTR, 'seg_ptr'), (_lib.A_SEG_OWN, 'seg_own'), (_lib.A_SEG_REL, 'seg_rel'),
+             (_lib.A_E_IDX, 'e_idx'), (_lib.A_E_W, 'e_w'), (_lib.A_RAW_IDX, 'raw_idx'), (_lib.A_RAW_W, 'raw_w'),
+             (_lib.A_CHUNK_BEG, 'chunk_beg'), (_lib.A_CHUNK_END, 'chunk_end'), (_lib.A_BAT_SEG0, 'bat_seg0'),
+             (_lib.A_BAT_INFO, 'bat_info')]
+    for aid, name in pairs:
+        got = g.export(aid, which)
+        assert got.dtype == want[name].dtype or got.view(want[name].dtype).dtype == want[name].dtype
+        assert np.array_equal(got.view(want[name].dtype), want[name]), name
+    assert np.array_equal(np.diff(g.export(_lib.A_SEG_PTR0, which)), want['cnt'])
+
+
+@pytest.mark.parametrize('name', GRAPHS)
+@pytest.mark.parametrize('nr,t,ch', [(0, 0, 0), (64, 8, 4), (5, 2, 2)])
+def test_graph_build_bit_exact(name, nr, t, ch):
+    ei, et, n, r = golden_graph(name)
+    g = RGCNGraph(ei.to(DEV), et.to(DEV), n, r, range_nodes=nr, split_threshold=t, chunk_size=ch)
+    nr_eff, t_eff, ch_eff = (nr or 4096), (t or 256), (ch or 256)
+    src, dst, rel = ei[0].numpy(), ei[1].numpy(), et.numpy()
+    fwd, bwd = csr_oracle.build_graph(src, dst, rel, n, r, nr_eff, t_eff, ch_eff)
+    _check_brc(g, _lib.BRC_FWD, fwd)
+    _check_brc(g, _lib.BRC_BWD, bwd)
+    fwd_rel = csr_oracle.build_brc(dst, src, rel, n, r, n, t_eff, ch_eff, w_entry=fwd['w_entry'])
+    _check_brc(g, _lib.BRC_FWD_REL, fwd_rel)
+
+
+def test_graph_build_rejects_bad_indices_and_cpu_tensors():
+    ei = torch.tensor([[0, 1], [1, 5]], device=DEV)
+    with pytest.raises(_lib.EngineError, match='outside'):
+        RGCNGraph(ei, torch.tensor([0, 1], device=DEV), 3, 2)
+    with pytest.raises(_lib.EngineError, match='outside'):
+        RGCNGraph(torch.tensor([[0, 1], [1, 2]], device=DEV), torch.tensor([0, 2], device=DEV), 3, 2)
+    with pytest.raises(_lib.EngineError):
+        RGCNGraph(torch.tensor([[0, 1], [1, 2]]), torch.tensor([0, 1]), 3, 2)
+
+
+def test_graph_build_empty_edge_list():
+    ei = torch.zeros((2, 0), dtype=torch.long, device=DEV)
+    et = torch.zeros((0,), dtype=torch.long, device=DEV)
+    conv = RGCNConv(5, 3, 4).to(DEV)
+    x = torch.randn(6, 5, device=DEV)
+    out = conv(x, ei, et)
+    ref = x.cpu() @ conv.root.detach().cpu() + conv.bias.detach().cpu()
+    assert rel_err(out, ref) < TOL
+
+
+# ------------------------------------------------------------------ K1/K3/K4 vs oracle
+def _layer_case(ei, et, n, r, fin, fout, seed, relu_in=False, force_simple=False, graph_kw=None, need=(True,) * 4):
+    torch.manual_seed(seed)
+    x = torch.randn(n, fin)
+    w = (torch.rand(r, fin, fout) - 0.5) * 0.4
+    root = (torch.rand(fin, fout) - 0.5) * 0.4
+    bias = (torch.rand(fout) - 0.5) * 0.2
+    gout = torch.randn(n, fout)
+    leaves = [t.clone().requires_grad_(nd) for t, nd in zip((x, w, root, bias), need)]
+    xin = torch.relu(leaves[0]) if relu_in else leaves[0]
+    ref = rgcn_oracle.rgcn_forward(xin, ei, et, leaves[1], leaves[2], leaves[3])
+    if any(need):
+        ref.backward(gout)
+    # fp64 truth for an accuracy bound that does not depend on the oracle's own fp32 round-off
+    x64 = torch.relu(x.double()) if relu_in else x.double()
+    ref64 = rgcn_oracle.rgcn_forward(x64, ei, et, w.double(), root.double(), bias.double())
+    g = RGCNGraph(ei.to(DEV), et.to(DEV), n, r, **(graph_kw or {}))
+    dl = [t.clone().to(DEV).requires_grad_(nd) for t, nd in zip((x, w, root, bias), need)]
+    out = rgcn_layer(dl[0], dl[1], dl[2], dl[3], g, relu_in=relu_in, force_simple=force_simple)
+    if any(need):
+        out.backward(gout.to(DEV))
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < TOL, ('out', rel_err(out, ref))
+    assert rel_err(out, ref64) < TOL
+    for name, a, b, nd in zip(('gx', 'gw', 'groot', 'gbias'), dl, leaves, need):
+        if nd:
+            assert rel_err(a.grad, b.grad) < TOL, (name, rel_err(a.grad, b.grad))
+        else:
+            assert a.grad is None
+    return out
+
+
+@pytest.mark.parametrize('name', GRAPHS)
+@pytest.mark.parametrize('fin,fout', [(63, 16), (16, 11), (64, 26)])
+def test_layer_fwd_bwd_on_reference_graphs(name, fin, fout):
+    ei, et, n, r = golden_graph(name)
+    _layer_case(ei, et, n, r, fin, fout, seed=fin + fout)
+
+
+@pytest.mark.parametrize('fin,fout', [(1, 1), (3, 2), (16, 16), (17, 33), (20, 7), (32, 64), (60, 60), (64, 64), (63, 11)])
+def test_layer_shapes_on_random_multigraph(fin, fout):
+    ei, et = random_multigraph(257, 3000, 7, seed=fin * 100 + fout, hub_frac=0.25, dup_frac=0.2)
+    _layer_case(ei, et, 257, 7, fin, fout, seed=1)
+
+
+@pytest.mark.parametrize('fin,fout', [(100, 70), (65, 3), (5, 130)])
+def test_layer_wide_shapes_use_generic_kernels(fin, fout):
+    ei, et = random_multigraph(90, 800, 5, seed=7, hub_frac=0.2, dup_frac=0.1)
+    _layer_case(ei, et, 90, 5, fin, fout, seed=2)
+
+
+@pytest.mark.parametrize('kw', [dict(range_nodes=16, split_threshold=4, chunk_size=3), dict(range_nodes=1, split_threshold=1, chunk_size=1),
+                                dict(range_nodes=100000, split_threshold=100000)])
+def test_layer_invariant_to_blocking_and_chunking(kw):
+    ei, et = random_multigraph(120, 2500, 6, seed=11, hub_frac=0.5, dup_frac=0.3)
+    _layer_case(ei, et, 120, 6, 63, 16, seed=3, graph_kw=kw)
+    _layer_case(ei, et, 120, 6, 16, 11, seed=4, graph_kw=kw)
+
+
+def test_layer_simple_and_tensor_paths_agree_with_oracle():
+    ei, et, n, r = golden_graph('AIFB_sum_in_out')
+    a = _layer_case(ei, et, n, r, 63, 16, seed=5, force_simple=True)
+    b = _layer_case(ei, et, n, r, 63, 16, seed=5, force_simple=False)
+    assert rel_err(a, b.cpu()) < TOL
+
+
+@pytest.mark.parametrize('need', [(False, True, True, True), (True, False, False, False), (False, False, False, True),
+                                  (False, True, False, False), (True, False, True, False)])
+def test_layer_respects_requires_grad_flags(need):
+    """-e_freeze True / -w_grad False (main.py:84-87) switch whole backward passes off."""
+    ei, et = random_multigraph(64, 700, 5, seed=13, hub_frac=0.2)
+    _layer_case(ei, et, 64, 5, 63, 16, seed=6, need=need)
+
+
+@pytest.mark.parametrize('fin,fout', [(16, 11), (63, 16)])
+def test_layer_fused_relu_input(fin, fout):
+    ei, et = random_multigraph(150, 2000, 5, seed=17, hub_frac=0.3, dup_frac=0.1)
+    _layer_case(ei, et, 150, 5, fin, fout, seed=7, relu_in=True, graph_kw=dict(split_threshold=8, chunk_size=4))
+
+
+def test_isolated_nodes_unused_relation_slot_and_duplicates():
+    # node 5 isolated; relation 3 (the 2|rel| slot, modelTrainer.py:78) never used; duplicate edges
+    ei = torch.tensor([[0, 0, 0, 1, 2, 3, 3], [1, 1, 1, 2, 0, 4, 4]])
+    et = torch.tensor([0, 0, 0, 1, 2, 0, 0])
+    out = _layer_case(ei, et, 6, 4, 63, 16, seed=8)
+    assert torch.isfinite(out).all()
+
+
+def test_basis_decomposition_module():
+    ei, et = random_multigraph(80, 900, 6, seed=19)
+    torch.manual_seed(0)
+    ref = rgcn_oracle.RGCNConv(20, 12, 6, num_bases=3)
+    mine = RGCNConv(20, 12, 6, num_bases=3)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(DEV)
+    x = torch.randn(80, 20)
+    a = ref(x, ei, et)
+    b = mine(x.to(DEV), ei.to(DEV), et.to(DEV))
+    a.sum().backward()
+    b.sum().backward()
+    assert rel_err(b, a) < TOL
+    assert rel_err(mine.comp.grad, ref.comp.grad) < TOL and rel_err(mine.weight.grad, ref.weight.grad) < TOL
+
+
+def test_strided_views_and_graph_cache():
+    ei, et, n, r = golden_graph('MUTAG_bisim_k1')
+    assert not ei.is_contiguous()
+    d = Data(edge_index=ei)
+    d.edge_type = et
+    d = d.to(DEV)
+    from rgcn_b200.graph import _CACHE, clear_cache
+    clear_cache()
+    c1, c2 = RGCNConv(8, 8, r).to(DEV), RGCNConv(8, 4, r).to(DEV)
+    x = torch.randn(n, 8, device=DEV)
+    c2(c1(x, d.edge_index, d.edge_type), d.edge_index, d.edge_type)
+    assert len(_CACHE) == 1          # both layers share one build (model/layers.py:21,23)
+
+
+# ------------------------------------------------------------------ full models vs reference-caller goldens
+@pytest.mark.parametrize('name', ['TEST_complete', 'AIFB_sum_in', 'AIFB_sum_in_out', 'MUTAG_bisim_k1', 'AIFB_bisim_k3'])
+@pytest.mark.parametrize('fused', [False, True])
+def test_emb_layers_matches_reference_golden(name, fused):
+    ei, et, n, r = golden_graph(name)
+    g = load_golden(f'layers_{name}.npz')
+    emb, hid, c = g['emb'].shape[1], g['w1'].shape[2], g['w2'].shape[2]
+    model = Emb_Layers(r, hid, c, n, emb, 1)
+    with torch.no_grad():
+        model.embedding.weight.copy_(torch.from_numpy(g['emb']))
+        for conv, sfx in ((model.rgcn1, '1'), (model.rgcn2, '2')):
+            conv.weight.copy_(torch.from_numpy(g['w' + sfx]))
+            conv.root.copy_(torch.from_numpy(g['r' + sfx]))
+            conv.bias.copy_(torch.from_numpy(g['b' + sfx]))
+    model.fused = fused
+    model = model.to(DEV)
+    d = Data(edge_index=ei)
+    d.edge_type = et
+    d = d.to(DEV)
+    bce = str(g['loss_kind']) == 'bce'
+    out = model(d, torch.sigmoid if bce else (lambda t: t))
+    xt, yt = torch.from_numpy(g['x_train']).to(DEV), torch.from_numpy(g['y_train']).to(DEV)
+    loss = (bce_loss if bce else ce_loss)(out[xt], yt)
+    loss.backward()
+    want_out = torch.from_numpy(g['out'])
+    assert rel_err(out, want_out) < TOL
+    assert torch.equal(out.argmax(1).cpu(), want_out.argmax(1)) or \
+        float((out.argmax(1).cpu() != want_out.argmax(1)).float().mean()) == 0.0
+    assert abs(loss.item() - float(g['loss'])) < TOL * max(1.0, abs(float(g['loss'])))
+    for pname, key in (('embedding.weight', 'g_emb'), ('rgcn1.weight', 'g_w1'), ('rgcn1.root', 'g_r1'), ('rgcn1.bias', 'g_b1'),
+                       ('rgcn2.weight', 'g_w2'), ('rgcn2.root', 'g_r2'), ('rgcn2.bias', 'g_b2')):
+        got = dict(model.named_parameters())[pname].grad
+        assert rel_err(got, torch.from_numpy(g[key])) < TOL, (pname, rel_err(got, torch.from_numpy(g[key])))
+
+
+def test_transfer_heads_match_reference_golden():
+    ei, et, n, r = golden_graph('TEST_complete')
+    g = load_golden('heads_TEST.npz')
+    S, emb, hid, C = int(g['S']), int(g['emb']), int(g['hidden']), int(g['C'])
+    d = Data(edge_index=ei)
+    d.edge_type = et
+    d = d.to(DEV)
+    mlp = Emb_MLP_Layers(r, hid, C, n, emb, S)
+    mlp.load_embedding(torch.from_numpy(g['e_cat']), freeze=True)
+    mlp.load_state_dict({k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('mlp.')})
+    out = mlp.to(DEV)(d, torch.sigmoid)
+    assert rel_err(out, torch.from_numpy(g['out_mlp'])) < TOL
+    att = Emb_ATT_Layers(r, hid, C, n, emb, S)
+    att.load_embedding(torch.from_numpy(g['e_stack']), freeze=True)
+    att.load_state_dict({k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('att.')})
+    att.eval()
+    out = att.to(DEV)(d, torch.sigmoid)
+    assert rel_err(out, torch.from_numpy(g['out_att'])) < TOL
+
+
+# ------------------------------------------------------------------ K5 map gather: bit-exact
+@pytest.mark.parametrize('tag', ['TEST_attr', 'AIFB_attr', 'AIFB_bisim'])
+def test_map_gather_bit_exact(tag):
+    g = load_golden(f'mapgather_{tag}.npz')
+    s = int(g['num_sums'])
+    embs = [torch.from_numpy(g[f'emb{i}']).to(DEV) for i in range(s)]
+    idxs = [torch.from_numpy(g[f'idx{i}']).to(DEV) for i in range(s)]
+    fbs = [torch.from_numpy(g[f'fallback{i}']).to(DEV) for i in range(s)]
+    for mode, key in ((0, 'out_sum'), (1, 'out_concat'), (2, 'out_stack')):
+        got = map_gather(embs, idxs, fbs, mode).cpu()
+        assert torch.equal(got, torch.from_numpy(g[key])), key
+
+
+# ------------------------------------------------------------------ larger sizes: properties
+@pytest.fixture(scope='module')
+def am16():
+    ei, et, n, r = am_shape(scale=1 / 16)
+    return ei.to(DEV), et.to(DEV), n, r, RGCNGraph(ei.to(DEV), et.to(DEV), n, r)
+
+
+def test_am_shape_sixteenth_matches_oracle_forward(am16):
+    ei, et, n, r, g = am16
+    torch.manual_seed(0)
+    x = torch.randn(n, 63)
+    w = (torch.rand(r, 63, 16) - 0.5) * 0.3
+    root = (torch.rand(63, 16) - 0.5) * 0.3
+    bias = torch.rand(16)
+    with torch.no_grad():
+        ref = rgcn_oracle.rgcn_forward(x, ei.cpu(), et.cpu(), w, root, bias)
+        out = rgcn_layer(x.to(DEV), w.to(DEV), root.to(DEV), bias.to(DEV), g)
+    assert rel_err(out, ref) < TOL
+
+
+def test_am_shape_known_answer_constant_features(am16):
+    """x = ones  =>  every segment mean is ones  =>  out[i] = sum_{r present at i} colsum(W_r) + colsum(root) + bias."""
+    ei, et, n, r, g = am16
+    torch.manual_seed(1)
+    w = (torch.rand(r, 63, 16, device=DEV) - 0.5)
+    root = torch.rand(63, 16, device=DEV)
+    bias = torch.rand(16, device=DEV)
+    out = rgcn_layer(torch.ones(n, 63, device=DEV), w, root, bias, g)
+    pairs = torch.unique(ei[1] * r + et)                       # distinct (dst, rel)
+    want = torch.zeros(n, 16, device=DEV, dtype=torch.float64)
+    want.index_add_(0, pairs // r, w.sum(1).double()[pairs % r])
+    want += root.sum(0).double() + bias.double()
+    assert rel_err(out, want) < TOL
+
+
+def test_am_shape_linearity_and_backward_adjointness(am16):
+    """<gout, F(x)> == <F^T(gout), x> for the bias-free linear map x -> out (fwd vs dL/dx kernels), and
+    dL/dW is the matching adjoint in W — ties K1, K3 and K4 together at a size the oracle cannot reach."""
+    ei, et, n, r, g = am16
+    torch.manual_seed(2)
+    x = torch.randn(n, 63, device=DEV, requires_grad=True)
+    w = ((torch.rand(r, 63, 16, device=DEV) - 0.5) * 0.3).requires_grad_()
+    root = ((torch.rand(63, 16, device=DEV) - 0.5) * 0.3).requires_grad_()
+    gout = torch.randn(n, 16, device=DEV)
+    out = rgcn_layer(x, w, root, None, g)
+    out.backward(gout)
+    lhs = float((gout.double() * out.detach().double()).sum())
+    rhs_x = float((x.grad.double() * x.detach().double()).sum())
+    rhs_w = float((w.grad.double() * w.detach().double()).sum() + (root.grad.double() * root.detach().double()).sum())
+    assert abs(lhs - rhs_x) < 1e-5 * abs(lhs) + 1e-3
+    assert abs(lhs - rhs_w) < 1e-5 * abs(lhs) + 1e-3
+    out2 = rgcn_layer(2.0 * x.detach(), w.detach(), root.detach(), None, g)
+    assert rel_err(out2, 2.0 * out.detach().cpu()) < TOL
+
+
+def test_am_shape_tensor_and_generic_kernels_agree(am16):
+    ei, et, n, r, g = am16
+    torch.manual_seed(3)
+    x = torch.randn(n, 16, device=DEV, requires_grad=True)
+    w = ((torch.rand(r, 16, 11, device=DEV) - 0.5) * 0.3).requires_grad_()
+    root = torch.rand(16, 11, device=DEV, requires_grad=True)
+    bias = torch.rand(11, device=DEV, requires_grad=True)
+    gout = torch.randn(n, 11, device=DEV)
+    res = []
+    for simple in (False, True):
+        for t in (x, w, root, bias):
+            t.grad = None
+        out = rgcn_layer(x, w, root, bias, g, force_simple=simple)
+        out.backward(gout)
+        res.append([out.detach().cpu()] + [t.grad.cpu() for t in (x, w, root, bias)])
+    for a, b in zip(*res):
+        assert rel_err(a, b) < TOL
