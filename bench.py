@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 R-GCN engine (contract: see DESIGN.md section 6).
+
+Metric (BASELINE.json): R-GCN fwd+bwd directed edges/s on the synthetic AM-shape graph
+(N=1 666 764, 5 988 321 triples -> E=11 976 642 directed edges, 133 predicates -> R=267,
+63 -> 16 -> 11, fp32, all gradients).  One "step" = both layers forward + backward over the
+whole graph (inter-layer ReLU, root and bias included; loss/optimizer excluded).
+
+  python bench.py --gpus N --steps K --warmup W            # engine arm
+  python bench.py --impl reference ...                     # reference CPU path (oracle port) on host cores
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(REPO, 'scaling-rgcn-training_b200')
+for p in (REPO, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = 'rgcn_fwd_bwd_directed_edges_per_s_am_shape'
+UNIT = 'edges/s'
+EMB, HIDDEN, CLASSES = 63, 16, 11
+
+
+def algorithmic_bytes(n, e, fin, fout, need_w=True, need_x=True):
+    """SURVEY.md section 8(d) / BASELINE.md section 2 formula, per layer."""
+    fwd = e * (4 * fin + 8) + n * 4 * (fin + fout)
+    bwd = n * 4 * fout
+    if need_w:
+        bwd += e * (4 * fin + 8) + n * 4 * fin
+    if need_x:
+        bwd += e * (4 * fout + 8) + n * 4 * fin
+    return fwd, bwd
+
+
+def pass_bytes(n, e, fin, fout):
+    """Per-kernel split of the same formula: the dL/dW pass carries the read
+    of gout (N*4*Fout) because it runs first; the dL/dx pass does not count it again."""
+    return {
+        ('tile_fwd', fin, fout): e * (4 * fin + 8) + n * 4 * (fin + fout),
+        ('wgrad', fin, fout): n * 4 * fout + e * (4 * fin + 8) + n * 4 * fin,
+        ('tile_dx', fout, fin): e * (4 * fout + 8) + n * 4 * fin,
+    }
+
+
+def load_peaks():
+    path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def dist_setup(n_gpus: int):
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    return rank, world, local
+
+
+def time_steps(step_fn, steps: int, warmup: int, world: int, device):
+    """W untimed steps, then exactly K steps between barrier+synchronize, CUDA events, max over ranks."""
+    import torch.distributed as dist
+    for _ in range(warmup):
+        step_fn()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step_fn()
+    t1.record()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([t0.elapsed_time(t1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference's PyG loop path on host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_reference(steps: int, warmup: int, scale: float, threads: int):
+    sys.path.insert(0, os.path.join(REPO, 'oracle'))
+    import rgcn_oracle                                 # bench.py's cpu_baseline leg may execute oracle/
+    from rgcn_b200.synthetic import am_shape
+    torch.set_num_threads(threads)
+    ei, et, n, r = am_shape(scale=scale)
+    e = et.numel()
+    torch.manual_seed(0)
+    emb = torch.randn(n, EMB, requires_grad=True)
+    c1 = rgcn_oracle.RGCNConv(EMB, HIDDEN, r)
+    c2 = rgcn_oracle.RGCNConv(HIDDEN, CLASSES, r)
+    gout = torch.randn(n, CLASSES)
+    params = [emb] + list(c1.parameters()) + list(c2.parameters())
+
+    def step():
+        for p in params:
+            p.grad = None
+        out = c2(torch.relu(c1(emb, ei, et)), ei, et)
+        out.backward(gout)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    sample = (f'AM-shape at scale {scale:g} (N={n}, E={e}, R={r}), 63->16->11 fwd+bwd all grads, fp32, '
+              f'{steps} timed steps after {warmup} warm-up; the loop path keeps an N x Fin tensor per relation, '
+              f'full scale does not fit host RAM (SURVEY.md F11)')
+    return e / dt, dt * 1e3, n, e, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    val, ms, n, e, sample = cpu_reference(args.steps, args.warmup, args.ref_scale, threads)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'am_shape_full_graph_rgcn_63_16_11_all_grads', 'reference_sample_scale': args.ref_scale,
+                   'sample_nodes': n, 'sample_edges': e},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# engine arm
+# ----------------------------------------------------------------------------------------------
+def run_engine(args):
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device — the engine has no CPU path (use --impl reference for the CPU baseline)')
+    import __graft_entry__
+    __graft_entry__.build()
+    from rgcn_b200 import Data, Emb_Layers, RGCNGraph, _lib, rgcn_layer
+    from rgcn_b200.synthetic import am_shape, labelled_split
+    from rgcn_b200.trainer import ce_loss, identity, make_optimizer
+    rank, world, local = dist_setup(args.gpus)
+    device = torch.device('cuda', local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        from rgcn_b200 import partition
+        return partition.run_partitioned_bench(args, rank, world, device, METRIC, UNIT)
+
+    ei, et, n, r = am_shape(scale=args.scale)
+    e = et.numel()
+    t_setup = time.perf_counter()
+    data = Data(edge_index=ei)
+    data.edge_type = et
+    data = data.to(device)
+    graph = RGCNGraph(data.edge_index, data.edge_type, n, r)
+    torch.cuda.synchronize(device)
+    setup_ms = (time.perf_counter() - t_setup) * 1e3
+
+    torch.manual_seed(0)
+    model = Emb_Layers(r, HIDDEN, CLASSES, n, EMB, 1).to(device)
+    gout = torch.randn(n, CLASSES, device=device)
+    params = list(model.parameters())
+    c1, c2 = model.rgcn1, model.rgcn2
+
+    def layer_step():
+        for p in params:
+            p.grad = None
+        h = rgcn_layer(model.embedding.weight, c1.weight, c1.root, c1.bias, graph)
+        out = rgcn_layer(h, c2.weight, c2.root, c2.bias, graph, relu_in=True)   # F.relu fused into the load
+        out.backward(gout)
+
+    sampler = ClockSampler(local)
+    launches0 = None
+
+    def timed():
+        nonlocal launches0
+        layer_step()
+
+    for _ in range(args.warmup):
+        layer_step()
+    torch.cuda.synchronize(device)
+    _lib.profile_enable(True)
+    _lib.profile_collect()
+    launches0 = _lib.launch_count()
+    sampler.start()
+    total_ms = time_steps(layer_step, args.steps, 0, world, device)
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - launches0
+    recs = _lib.profile_collect()
+    _lib.profile_enable(False)
+    ms_per_step = total_ms / args.steps
+    value = e / (ms_per_step * 1e-3)
+
+    # dominant kernel and its roofline
+    peak, peak_src = load_peaks()
+    agg = {}
+    for name, dims, ms in recs:
+        agg.setdefault((name, dims[0], dims[1]), []).append(ms)
+    tot = {k: sum(v) for k, v in agg.items()}
+    pb = {}
+    for (fin, fout) in ((EMB, HIDDEN), (HIDDEN, CLASSES)):
+        pb.update(pass_bytes(n, e, fin, fout))
+    graded = {k: v for k, v in tot.items() if k in pb}
+    dom = max(graded, key=graded.get) if graded else None
+    roofline = None
+    if dom is not None:
+        avg_ms = statistics.mean(agg[dom])
+        ach = pb[dom] / (avg_ms * 1e-3) / 1e9
+        roofline = {'bound': 'hbm', 'kernel': f'{dom[0]}_{dom[1]}x{dom[2]}', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                    'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': pb[dom], 'avg_launch_ms': avg_ms,
+                    'share_of_step': tot[dom] / args.steps / ms_per_step}
+    f1, b1 = algorithmic_bytes(n, e, EMB, HIDDEN)
+    f2, b2 = algorithmic_bytes(n, e, HIDDEN, CLASSES)
+    step_bytes = f1 + b1 + f2 + b2
+    passes = {f'{k[0]}_{k[1]}x{k[2]}': {'avg_ms': statistics.mean(v), 'launches': len(v),
+                                        'gbps_algorithmic': (pb[k] / (statistics.mean(v) * 1e-3) / 1e9) if k in pb else None}
+              for k, v in sorted(agg.items())}
+
+    # end to end: the reference's Trainer.train iteration body through the public (drop-in) API,
+    # labelled batch copied from pinned host memory every step, loss read back every step
+    x_train_h, y_train_h = labelled_split(n, CLASSES)
+    x_train_h, y_train_h = x_train_h.pin_memory(), y_train_h.pin_memory()
+    opt = make_optimizer(model)
+    h2d = x_train_h.numel() * x_train_h.element_size() + y_train_h.numel() * y_train_h.element_size()
+
+    def e2e_step():
+        data.x_train = x_train_h.to(device, non_blocking=True)
+        data.y_train = y_train_h.to(device, non_blocking=True)
+        model.train()
+        opt.zero_grad()
+        out = model(data, identity)
+        loss = ce_loss(out[data.x_train], data.y_train.to(torch.float32))
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    e2e_ms = time_steps(e2e_step, args.steps, args.warmup, world, device) / args.steps if not args.no_e2e else float('nan')
+    e2e = {'value': e / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4,
+           'ms_per_step': e2e_ms,
+           'what': 'Trainer.train iteration body (modelTrainer.py:61-69) via Emb_Layers on the drop-in RGCNConv: '
+                   'pinned H2D of x_train/y_train, fwd, CE loss, bwd, Adam (incl. the [N,63] embedding), loss.item()'}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cval, cms, cn, ce_, sample = cpu_reference(3, 1, args.ref_scale, threads)
+        cpu = {'value': cval, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample, 'ms_per_step': cms}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'am_shape_full_graph_rgcn_63_16_11_all_grads', 'scale': args.scale, 'nodes': n,
+                   'directed_edges': e, 'triples_per_s': value / 2, 'relations': r, 'emb': EMB, 'hidden': HIDDEN,
+                   'classes': CLASSES, 'l2_policy': 'inputs larger than L2 (features 420 MB + CSR > 126 MB L2); no flush',
+                   'graph_build_ms_once': setup_ms, 'range_nodes': graph.query(_lib.Q_RANGE_NODES),
+                   'step_algorithmic_bytes': step_bytes, 'step_roofline_frac': step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                   'passes': passes},
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', choices=['engine', 'reference'], default='engine')
+    ap.add_argument('--scale', type=float, default=1.0, help='AM-shape scale (1.0 = the BASELINE.json config)')
+    ap.add_argument('--ref-scale', type=float, default=1 / 32, help='bounded sample for the CPU reference arm')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true', help='kernel-level timing only (tuning runs; not a bench line)')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RGCN_B200_ABI_VERSION 1
+#define RGCN_B200_ABI_VERSION 2
 
 typedef enum {
     RGCN_OK = 0,
@@ -51,7 +51,7 @@ enum {
     RGCN_Q_NUM_NODES = 0, RGCN_Q_NUM_EDGES = 1, RGCN_Q_NUM_RELATIONS = 2,
     RGCN_Q_NUM_SEGMENTS = 3, RGCN_Q_NUM_ENTRIES = 4, RGCN_Q_NUM_CHUNKS = 5,
     RGCN_Q_NUM_GROUPS = 6, RGCN_Q_NUM_BATCHES = 7, RGCN_Q_RANGE_NODES = 8,
-    RGCN_Q_DEVICE_BYTES = 9
+    RGCN_Q_DEVICE_BYTES = 9, RGCN_Q_NUM_OWNED = 10, RGCN_Q_OWN_LO = 11, RGCN_Q_NUM_ENTRIES0 = 12
 };
 
 /* rgcn_graph_export array ids (element type in brackets) */
@@ -81,6 +81,18 @@ int rgcn_graph_create(const int64_t* src, int64_t src_stride,
                       int64_t num_edges, int64_t num_nodes, int32_t num_relations,
                       int32_t range_nodes, int32_t split_threshold, int32_t chunk_size,
                       void* stream, rgcn_graph** out);
+/* Destination-partitioned variant (multi-GPU, one process per GPU): this graph owns the nodes
+ * [own_lo, own_hi).  Its forward structures hold the edges whose dst is owned, its transposed
+ * structure the edges whose src is owned; owner ids are local (id - own_lo), gathered rows keep
+ * GLOBAL ids, and the mean normalisers are those of the whole graph.  Layer calls then take x /
+ * gout_gather with all N rows (the caller all-gathers them) and produce the owned rows only. */
+int rgcn_graph_create_part(const int64_t* src, int64_t src_stride,
+                           const int64_t* dst, int64_t dst_stride,
+                           const int64_t* etype, int64_t etype_stride,
+                           int64_t num_edges, int64_t num_nodes, int32_t num_relations,
+                           int64_t own_lo, int64_t own_hi,
+                           int32_t range_nodes, int32_t split_threshold, int32_t chunk_size,
+                           void* stream, rgcn_graph** out);
 void rgcn_graph_destroy(rgcn_graph* g);
 int rgcn_graph_query(const rgcn_graph* g, int32_t brc, int32_t key, int64_t* out);
 int rgcn_graph_export(const rgcn_graph* g, int32_t brc, int32_t array, void* host_dst,
@@ -92,7 +104,8 @@ int64_t rgcn_layer_workspace_bytes(const rgcn_graph* g, int32_t fin, int32_t fou
 /* RGCNConv.forward (reference call sites model/layers.py:21,23):
  *   out[i] = sum_r mean_{e: type=r, dst=i} x[src_e] . W_r + x[i] . root + bias
  * weight [R, fin, fout] (basis form is expanded by the caller), root/bias nullable.
- * out is fully overwritten. */
+ * x has one row per node of the whole graph, out one row per OWNED node (all of them unless the
+ * graph was created with rgcn_graph_create_part); out is fully overwritten. */
 int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin,
                    const float* weight, const float* root, const float* bias,
                    float* out, int64_t ldo, int32_t fout, uint32_t flags,
@@ -101,10 +114,13 @@ int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin
 /* Autograd backward of the above (reference model/modelTrainer.py:66).  Any of
  * gx / gweight / groot / gbias may be null = not needed (-e_freeze / -w_grad False).
  * Non-null outputs are fully overwritten.  With RGCN_F_RELU_IN, x is the pre-activation and
- * gx is the gradient w.r.t. that pre-activation (ReLU mask applied). */
+ * gx is the gradient w.r.t. that pre-activation (ReLU mask applied).
+ * gout holds the rows of the OWNED nodes; gout_gather the rows of ALL nodes (null = same tensor,
+ * only valid for an unpartitioned graph).  gx / gweight / groot / gbias cover the owned nodes
+ * (partial sums in the partitioned case: the caller all-reduces the parameter gradients). */
 int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin,
                    const float* weight, const float* root,
-                   const float* gout, int64_t ldg, int32_t fout,
+                   const float* gout, int64_t ldg, const float* gout_gather, int64_t ldgg, int32_t fout,
                    float* gx, int64_t ldgx, float* gweight, float* groot, float* gbias,
                    uint32_t flags, void* workspace, int64_t workspace_bytes, void* stream);
 

@@ -26,16 +26,33 @@ BS = 16
 LAST_FLAG = np.uint32(0x80000000)
 
 
-def build_brc(own, gat, rel, n, r, nr, t, ch, w_entry=None):
+def edge_weights(dst, rel, n):
+    """w[e] = 1 / multiplicity of e's (relation, dst) pair over the WHOLE graph (float32 division)."""
+    key = np.asarray(rel, dtype=np.int64) * n + np.asarray(dst, dtype=np.int64)
+    _, inv, counts = np.unique(key, return_inverse=True, return_counts=True)
+    return (np.float32(1.0) / counts.astype(np.float32))[inv].astype(np.float32)
+
+
+def build_brc(own, gat, rel, n, r, nr, t, ch, w_edge=None, lo=0, hi=None):
+    """own/gat/rel: the graph's edges (global ids).  [lo,hi): owned node range (whole graph by
+    default).  Entries = edges whose owner end is owned (input order), then the owned self loops."""
     own = np.asarray(own, dtype=np.int64)
     gat = np.asarray(gat, dtype=np.int64)
     rel = np.asarray(rel, dtype=np.int64)
-    e = own.size
-    nr = int(min(max(nr, 1), max(n, 1)))
-    loops = np.arange(n, dtype=np.int64)
-    own2 = np.concatenate([own, loops])
-    gat2 = np.concatenate([gat, loops])
-    rel2 = np.concatenate([rel, np.full(n, r, dtype=np.int64)])
+    hi = n if hi is None else hi
+    if w_edge is None:
+        raise ValueError('w_edge required (edge_weights(dst, rel, n))')
+    sel = (own >= lo) & (own < hi)
+    n_gat = n
+    n_own = hi - lo
+    nr = int(min(max(nr, 1), max(n_own, 1)))
+    loops = np.arange(n_own, dtype=np.int64)
+    own2 = np.concatenate([own[sel] - lo, loops])
+    gat2 = np.concatenate([gat[sel], loops + lo])
+    rel2 = np.concatenate([rel[sel], np.full(n_own, r, dtype=np.int64)])
+    w_entry = np.concatenate([np.asarray(w_edge, dtype=np.float32)[sel], np.ones(n_own, dtype=np.float32)])
+    e = int(sel.sum())
+    n = n_own
     key = (own2 // nr) * ((r + 1) * nr) + rel2 * nr + own2 % nr
     perm = np.argsort(key, kind='stable')
     skey = key[perm]
@@ -51,9 +68,6 @@ def build_brc(own, gat, rel, n, r, nr, t, ch, w_entry=None):
     seg_range = seg_key // ((r + 1) * nr)
     seg_rel = (seg_key // nr) % (r + 1)
     seg_own = seg_range * nr + seg_key % nr
-    if w_entry is None:
-        w_entry = np.empty(e2, dtype=np.float32)
-        w_entry[perm] = (np.float32(1.0) / cnt.astype(np.float32))[seg_of]
     raw_idx = gat2[perm].astype(np.int32)
     raw_w = w_entry[perm].astype(np.float32)
     # chunking
@@ -76,7 +90,7 @@ def build_brc(own, gat, rel, n, r, nr, t, ch, w_entry=None):
                 c = chunk_base[si] + j
                 chunk_beg[c] = a + j * ch
                 chunk_end[c] = min(a + (j + 1) * ch, b)
-                e_idx[o + j] = n + c
+                e_idx[o + j] = n_gat + c
                 e_w[o + j] = 1.0
         else:
             e_idx[o:o + (b - a)] = raw_idx[a:b].astype(np.uint32)
@@ -110,10 +124,11 @@ def build_brc(own, gat, rel, n, r, nr, t, ch, w_entry=None):
                 num_groups=g, num_batches=nb, bat_seg0=bat_seg0, bat_info=bat_info)
 
 
-def build_graph(src, dst, rel, n, r, nr, t, ch):
+def build_graph(src, dst, rel, n, r, nr, t, ch, lo=0, hi=None):
     """Forward (owner = dst) and transposed (owner = src) BRCs as the engine builds them."""
-    fwd = build_brc(dst, src, rel, n, r, nr, t, ch)
-    bwd = build_brc(src, dst, rel, n, r, nr, t, ch, w_entry=fwd['w_entry'])
+    w = edge_weights(dst, rel, n)
+    fwd = build_brc(dst, src, rel, n, r, nr, t, ch, w_edge=w, lo=lo, hi=hi)
+    bwd = build_brc(src, dst, rel, n, r, nr, t, ch, w_edge=w, lo=lo, hi=hi)
     return fwd, bwd
 
 

@@ -39,7 +39,7 @@ int64_t fwd_ws(const rgcn_graph* g, int fin, int fout) {
     int64_t b = 0;
     b += ws_take((int64_t)(g->R + 1) * kp * np * 2, 4);                      // wfrag (hi,lo)
     b += ws_take((int64_t)g->brc[RGCN_BRC_FWD].num_chunks * kp, 4);          // chunk rows
-    b += ws_take((int64_t)g->N * np, 4);                                     // padded accumulate target
+    b += ws_take((int64_t)g->n_own * np, 4);                                 // padded accumulate target
     return b;
 }
 
@@ -50,7 +50,7 @@ int64_t bwd_ws(const rgcn_graph* g, int fin, int fout) {
     b += ws_take((int64_t)g->brc[RGCN_BRC_FWD_REL].num_chunks * kp, 4);      // chunk rows of x (dW pass)
     b += ws_take((int64_t)(g->R + 1) * kp * np * 2, 4);                      // W^T frags
     b += ws_take((int64_t)g->brc[RGCN_BRC_BWD].num_chunks * np, 4);          // chunk rows of gout (dx pass)
-    b += ws_take((int64_t)g->N * kp, 4);                                     // padded dx target
+    b += ws_take((int64_t)g->n_own * kp, 4);                                 // padded dx target
     return b;
 }
 
@@ -70,7 +70,7 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     const bool relu = (flags & RGCN_F_RELU_IN) != 0;
     const int kp = pad_dim(fin), np = pad_dim(fout);
     if ((flags & RGCN_F_FORCE_SIMPLE) || !kp || !np) {
-        RGCN_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)fout * 4, (size_t)g->N, st));
+        RGCN_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)fout * 4, (size_t)g->n_own, st));
         SimplePass p{};
         p.brc = &g->brc[RGCN_BRC_FWD];
         p.n_nodes = g->N;
@@ -84,7 +84,7 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     float4* wfrag = (float4*)ws.take<float>((int64_t)(g->R + 1) * kp * np * 2);
     float* aux = ws.take<float>((int64_t)g->brc[RGCN_BRC_FWD].num_chunks * kp);
     const bool direct = direct_target(out, ldo, fout);
-    float* target = direct ? out : ws.take<float>((int64_t)g->N * np);
+    float* target = direct ? out : ws.take<float>((int64_t)g->n_own * np);
     if (!ws.ok) return fail(RGCN_ERR_WORKSPACE, "rgcn_layer_fwd: workspace too small (see rgcn_layer_workspace_bytes)");
     const int64_t tld = direct ? ldo : np;
     const int tn = direct ? fout : np;
@@ -103,18 +103,27 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     p.kp = kp; p.np = np;
     p.relu_in = relu;
     if ((rc = launch_chunk_prepass(p, st))) return rc;
-    RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->N * tld * 4, st));
+    RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->n_own * tld * 4, st));
     if ((rc = launch_tile_pass(p, g->num_sms, st))) return rc;
-    if (!direct) return launch_copy_cols(target, tld, out, ldo, g->N, fout, st);
+    if (!direct) return launch_copy_cols(target, tld, out, ldo, g->n_own, fout, st);
     return 0;
 }
 
 extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, const float* weight,
-                              const float* root, const float* gout, int64_t ldg, int32_t fout, float* gx,
-                              int64_t ldgx, float* gweight, float* groot, float* gbias, uint32_t flags,
-                              void* workspace, int64_t workspace_bytes, void* stream) {
+                              const float* root, const float* gout, int64_t ldg, const float* gout_gather,
+                              int64_t ldgg, int32_t fout, float* gx, int64_t ldgx, float* gweight, float* groot,
+                              float* gbias, uint32_t flags, void* workspace, int64_t workspace_bytes, void* stream) {
     if (!g || !x || !weight || !gout || fin <= 0 || fout <= 0 || ldx < fin || ldg < fout || (gx && ldgx < fin))
         return fail(RGCN_ERR_INVALID_ARG, "rgcn_layer_bwd: bad argument");
+    if (!gout_gather) {
+        if (gx && g->n_own != g->N)
+            return fail(RGCN_ERR_INVALID_ARG, "rgcn_layer_bwd: a partitioned graph needs gout_gather (all nodes' rows) for dL/dx");
+        gout_gather = gout;
+        ldgg = ldg;
+    } else if (ldgg < fout) {
+        return fail(RGCN_ERR_INVALID_ARG, "rgcn_layer_bwd: bad argument");
+    }
+    const float* x_own = x + g->own_lo * ldx;   // rows of the owned nodes (ReLU mask)
     cudaStream_t st = (cudaStream_t)stream;
     const bool relu = (flags & RGCN_F_RELU_IN) != 0;
     const int kp = pad_dim(fin), np = pad_dim(fout);
@@ -135,15 +144,15 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
             if ((rc = launch_simple_wgrad(p, st))) return rc;
         }
         if (gx) {
-            RGCN_CUDA(cudaMemset2DAsync(gx, (size_t)ldgx * 4, 0, (size_t)fin * 4, (size_t)g->N, st));
+            RGCN_CUDA(cudaMemset2DAsync(gx, (size_t)ldgx * 4, 0, (size_t)fin * 4, (size_t)g->n_own, st));
             SimplePass p{};
             p.brc = &g->brc[RGCN_BRC_BWD];
             p.n_nodes = g->N; p.self_rel = g->R;
-            p.feat = gout; p.ldf = ldg; p.kin = fout;
+            p.feat = gout_gather; p.ldf = ldgg; p.kin = fout;
             p.weight = weight; p.root = root; p.bias = nullptr; p.transpose = true; p.w_rows = fin; p.w_cols = fout;
             p.out = gx; p.ldo = ldgx; p.nout = fin; p.relu_in = false;
             if ((rc = launch_simple_pass(p, st))) return rc;
-            if (relu && (rc = launch_relu_mask(gx, ldgx, x, ldx, g->N, fin, st))) return rc;
+            if (relu && (rc = launch_relu_mask(gx, ldgx, x_own, ldx, g->n_own, fin, st))) return rc;
         }
         return 0;
     }
@@ -152,7 +161,7 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     float4* wtfrag = (float4*)ws.take<float>((int64_t)(g->R + 1) * kp * np * 2);
     float* gaux = ws.take<float>((int64_t)g->brc[RGCN_BRC_BWD].num_chunks * np);
     const bool direct = gx && direct_target(gx, ldgx, fin);
-    float* target = gx ? (direct ? gx : ws.take<float>((int64_t)g->N * kp)) : nullptr;
+    float* target = gx ? (direct ? gx : ws.take<float>((int64_t)g->n_own * kp)) : nullptr;
     if (!ws.ok) return fail(RGCN_ERR_WORKSPACE, "rgcn_layer_bwd: workspace too small (see rgcn_layer_workspace_bytes)");
     if (need_w) {
         // chunk rows of x in the relation-major ordering, then dW / droot / dbias
@@ -178,7 +187,7 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
         TilePass p{};
         p.brc = &g->brc[RGCN_BRC_BWD];
         p.n_nodes = g->N; p.self_rel = g->R;
-        p.feat = gout; p.ldf = ldg; p.kin = fout;
+        p.feat = gout_gather; p.ldf = ldgg; p.kin = fout;
         p.aux = gaux;
         p.wfrag = wtfrag;
         p.bias = nullptr; p.nbias = 0;
@@ -187,10 +196,10 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
         p.relu_in = false;
         p.transposed = true;
         if ((rc = launch_chunk_prepass(p, st))) return rc;
-        RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->N * tld * 4, st));
+        RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->n_own * tld * 4, st));
         if ((rc = launch_tile_pass(p, g->num_sms, st))) return rc;
-        if (!direct && (rc = launch_copy_cols(target, tld, gx, ldgx, g->N, fin, st))) return rc;
-        if (relu && (rc = launch_relu_mask(gx, ldgx, x, ldx, g->N, fin, st))) return rc;
+        if (!direct && (rc = launch_copy_cols(target, tld, gx, ldgx, g->n_own, fin, st))) return rc;
+        if (relu && (rc = launch_relu_mask(gx, ldgx, x_own, ldx, g->n_own, fin, st))) return rc;
     }
     return 0;
 }

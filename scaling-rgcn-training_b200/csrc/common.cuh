@@ -11,6 +11,8 @@
 namespace rgcn {
 
 constexpr int BS = 16;                        // segments per batch (MMA M)
+constexpr int UNIT_BATCH_COST = 24;           // work-unit cost model: entries + 24 per batch
+constexpr int UNIT_MAX = 32768, UNIT_MIN_COST = 1024;
 constexpr uint32_t LAST_FLAG = 0x80000000u;   // bit 31 of e_idx: last entry of its segment
 constexpr uint32_t IDX_MASK = 0x7fffffffu;
 
@@ -55,6 +57,8 @@ struct Brc {
     int32_t* chunk_end = nullptr;  // [NC]
     int32_t* bat_seg0 = nullptr;   // [NB]
     int32_t* bat_info = nullptr;   // [NB] rel << 8 | nseg
+    int4* units = nullptr;         // [NU+1] equal-cost work units: (first batch, first segment, first entry, 0)
+    int32_t num_units = 0;
     int64_t bytes = 0;
     void release();
 };
@@ -62,14 +66,14 @@ struct Brc {
 }  // namespace rgcn
 
 struct rgcn_graph {
-    int64_t N = 0, E = 0;
+    int64_t N = 0, E = 0;      // global node / edge counts (gather rows are global ids)
+    int64_t own_lo = 0, n_own = 0;   // owned node range [own_lo, own_lo + n_own) (whole graph unless partitioned)
     int32_t R = 0;
     int32_t range_nodes = 0, split_threshold = 0, chunk_size = 0;
     int device = 0;
     int num_sms = 148;
     rgcn::Brc brc[3];
     bool rel_is_fwd = false;   // FWD_REL aliases FWD (graph fits one range)
-    float* w_entry = nullptr;  // [E+N] 1/cnt of the forward segment, by entry id
 };
 
 namespace rgcn {

@@ -24,7 +24,7 @@ const char* last_error_cstr() { return g_last_error.c_str(); }
 
 void Brc::release() {
     void* ptrs[] = {perm, seg_ptr0, seg_ptr, seg_own, seg_rel, e_idx, e_w, raw_idx, raw_w,
-                    chunk_beg, chunk_end, bat_seg0, bat_info};
+                    chunk_beg, chunk_end, bat_seg0, bat_info, units};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     *this = Brc();
@@ -53,28 +53,75 @@ struct Dev {   // scratch buffer freed at scope exit
 constexpr int TPB = 256;
 inline int blocks_for(int64_t n) { return (int)std::max<int64_t>(1, (n + TPB - 1) / TPB); }
 
-// entries [0,E): edges (validated) ; [E, E+N): self loops with relation R
-__global__ void k_entries(const int64_t* __restrict__ src, int64_t ss, const int64_t* __restrict__ dst, int64_t ds,
-                          const int64_t* __restrict__ et, int64_t es, int64_t E, int64_t N, int R,
-                          int32_t* __restrict__ src32, int32_t* __restrict__ dst32, int32_t* __restrict__ rel32,
-                          int* __restrict__ err) {
+// edges -> int32 (validated, global ids)
+__global__ void k_edges(const int64_t* __restrict__ src, int64_t ss, const int64_t* __restrict__ dst, int64_t ds,
+                        const int64_t* __restrict__ et, int64_t es, int64_t E, int64_t N, int R,
+                        int32_t* __restrict__ src32, int32_t* __restrict__ dst32, int32_t* __restrict__ rel32,
+                        int* __restrict__ err) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= E + N) return;
+    if (i >= E) return;
+    int64_t s = src[i * ss], d = dst[i * ds], r = et[i * es];
+    if (s < 0 || s >= N || d < 0 || d >= N || r < 0 || r >= R) {
+        atomicOr(err, 1);
+        s = d = 0;
+        r = 0;
+    }
+    src32[i] = (int32_t)s;
+    dst32[i] = (int32_t)d;
+    rel32[i] = (int32_t)r;
+}
+
+// per-edge mean normaliser 1/cnt(rel,dst): sort by rel*N+dst, run lengths, scatter back by edge id
+__global__ void k_wkeys(const int32_t* __restrict__ dst, const int32_t* __restrict__ rel, int64_t E, int64_t N,
+                        uint64_t* __restrict__ key, int32_t* __restrict__ eid) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= E) return;
+    key[i] = (uint64_t)rel[i] * (uint64_t)N + (uint64_t)dst[i];
+    eid[i] = (int32_t)i;
+}
+__global__ void k_run_starts(const int32_t* __restrict__ head, const int32_t* __restrict__ scan, int64_t n,
+                             int32_t* __restrict__ start) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n || !head[i]) return;
+    start[scan[i] - 1] = (int32_t)i;
+}
+__global__ void k_edge_weights(const int32_t* __restrict__ perm, const int32_t* __restrict__ scan,
+                               const int32_t* __restrict__ start, int64_t n, float* __restrict__ w_edge) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t s = scan[i] - 1;
+    w_edge[perm[i]] = 1.0f / (float)(start[s + 1] - start[s]);
+}
+
+// entry list of one BRC of the partition [lo,hi): edges whose owner end lies in the range (kept in
+// input order), then one self loop per owned node.  Owner ids local, gather ids global.
+__global__ void k_flag_owned(const int32_t* __restrict__ own_g, int64_t E, int32_t lo, int32_t hi,
+                             int32_t* __restrict__ flag) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= E) return;
+    flag[i] = (own_g[i] >= lo && own_g[i] < hi) ? 1 : 0;
+}
+__global__ void k_fill_entries(const int32_t* __restrict__ own_g, const int32_t* __restrict__ gat_g,
+                               const int32_t* __restrict__ rel_g, const float* __restrict__ w_edge,
+                               const int32_t* __restrict__ flag, const int32_t* __restrict__ pos, int64_t E, int64_t nsel,
+                               int32_t lo, int32_t hi, int R, int32_t* __restrict__ own, int32_t* __restrict__ gat,
+                               int32_t* __restrict__ rel, float* __restrict__ w) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < E) {
-        int64_t s = src[i * ss], d = dst[i * ds], r = et[i * es];
-        if (s < 0 || s >= N || d < 0 || d >= N || r < 0 || r >= R) {
-            atomicOr(err, 1);
-            s = d = 0;
-            r = 0;
+        if (flag[i]) {
+            int32_t o = pos[i];
+            own[o] = own_g[i] - lo;
+            gat[o] = gat_g[i];
+            rel[o] = rel_g[i];
+            w[o] = w_edge[i];
         }
-        src32[i] = (int32_t)s;
-        dst32[i] = (int32_t)d;
-        rel32[i] = (int32_t)r;
-    } else {
+    } else if (i < E + (hi - lo)) {
         int32_t v = (int32_t)(i - E);
-        src32[i] = v;
-        dst32[i] = v;
-        rel32[i] = R;
+        int64_t o = nsel + v;
+        own[o] = v;
+        gat[o] = lo + v;
+        rel[o] = R;
+        w[o] = 1.0f;
     }
 }
 
@@ -106,15 +153,6 @@ __global__ void k_seg_fill(const uint64_t* __restrict__ skey, const int32_t* __r
     seg_ptr0[s] = (int32_t)i;
     seg_rel[s] = (int32_t)(rem / NR);
     seg_own[s] = (int32_t)(rng * NR + rem % NR);
-}
-
-__global__ void k_weights(const int32_t* __restrict__ perm, const int32_t* __restrict__ scan,
-                          const int32_t* __restrict__ seg_ptr0, int64_t n2, float* __restrict__ w_entry) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n2) return;
-    int32_t s = scan[i] - 1;
-    int32_t cnt = seg_ptr0[s + 1] - seg_ptr0[s];
-    w_entry[perm[i]] = 1.0f / (float)cnt;
 }
 
 __global__ void k_raw(const int32_t* __restrict__ perm, const int32_t* __restrict__ gat,
@@ -203,6 +241,29 @@ __global__ void k_batch_fill(const int32_t* __restrict__ bat_base, const int32_t
 
 __global__ void k_set_i32(int32_t* p, int32_t v) { *p = v; }
 
+// Work units: cut the batch list into NU pieces of equal cost c(b) = first_entry(b) + 24 b
+// (entries + a per-batch overhead), so that warps taking units round-robin finish together.
+__global__ void k_units(const int32_t* __restrict__ bat_seg0, const int32_t* __restrict__ seg_ptr, int32_t NB,
+                        int32_t S, int32_t E3, int32_t NU, int4* __restrict__ units) {
+    int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (u > NU) return;
+    if (u == NU) {
+        units[u] = make_int4(NB, S, E3, 0);
+        return;
+    }
+    const int64_t total = (int64_t)E3 + (int64_t)UNIT_BATCH_COST * NB;
+    const int64_t target = total * u / NU;
+    int lo = 0, hi = NB;   // first batch with c(b) >= target
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        int64_t c = (int64_t)seg_ptr[bat_seg0[mid]] + (int64_t)UNIT_BATCH_COST * mid;
+        if (c >= target) hi = mid;
+        else lo = mid + 1;
+    }
+    if (lo >= NB) units[u] = make_int4(NB, S, E3, 0);
+    else units[u] = make_int4(lo, bat_seg0[lo], seg_ptr[bat_seg0[lo]], 0);
+}
+
 template <typename T>
 cudaError_t scan_inclusive(const T* in, T* out, int64_t n, cudaStream_t st) {
     size_t tmp_bytes = 0;
@@ -235,10 +296,11 @@ int bit_length(uint64_t v) {
     return std::max(b, 1);
 }
 
-// Build one BRC.  own/gat/rel: [E+N] int32 entry arrays.  w_entry: in/out ([E+N]); computed when
-// compute_w.
-int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, int64_t n2, int64_t N, int R, int NR, int T,
-              int CH, float* w_entry, bool compute_w, cudaStream_t st, Brc* out) {
+// Build one BRC from an entry list (owner local id, gather global id, relation, weight).
+// n_own owners (ranges of NR), chunk rows are numbered from n_gat (the gather row count).
+int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const float* w_entry, int64_t n2,
+              int64_t n_own, int64_t n_gat, int R, int NR, int T, int CH, cudaStream_t st, Brc* out) {
+    const int64_t N = n_own;
     Brc b;
     b.num_entries0 = n2;
     b.range_nodes = NR;
@@ -275,7 +337,6 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, int64_
     RGCN_CUDA(cudaMalloc(&b.seg_rel, std::max(S, 1) * 4));
     k_seg_fill<<<blocks_for(n2), TPB, 0, st>>>(skey.p, head.p, scan.p, n2, R, NR, b.seg_ptr0, b.seg_own, b.seg_rel);
     k_set_i32<<<1, 1, 0, st>>>(b.seg_ptr0 + S, (int32_t)n2);
-    if (compute_w) k_weights<<<blocks_for(n2), TPB, 0, st>>>(b.perm, scan.p, b.seg_ptr0, n2, w_entry);
     RGCN_CUDA(cudaMalloc(&b.raw_idx, std::max<int64_t>(n2, 1) * 4));
     RGCN_CUDA(cudaMalloc(&b.raw_w, std::max<int64_t>(n2, 1) * 4));
     k_raw<<<blocks_for(n2), TPB, 0, st>>>(b.perm, gat, w_entry, n2, b.raw_idx, b.raw_w);
@@ -299,7 +360,7 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, int64_
     RGCN_CUDA(cudaMalloc(&b.e_w, std::max(E3, 1) * 4));
     RGCN_CUDA(cudaMalloc(&b.chunk_beg, std::max(NC, 1) * 4));
     RGCN_CUDA(cudaMalloc(&b.chunk_end, std::max(NC, 1) * 4));
-    k_compact<<<blocks_for(n2), TPB, 0, st>>>(scan.p, b.seg_ptr0, b.seg_ptr, chunk_base.p, b.raw_idx, b.raw_w, n2, N, T,
+    k_compact<<<blocks_for(n2), TPB, 0, st>>>(scan.p, b.seg_ptr0, b.seg_ptr, chunk_base.p, b.raw_idx, b.raw_w, n2, n_gat, T,
                                               CH, b.e_idx, b.e_w, b.chunk_beg, b.chunk_end);
 
     // groups and batches
@@ -331,6 +392,13 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, int64_
     RGCN_CUDA(cudaMalloc(&b.bat_info, std::max(NB, 1) * 4));
     if (NB > 0)
         k_batch_fill<<<blocks_for(NB), TPB, 0, st>>>(bat_base.p, grp_seg.p, b.seg_rel, G, NB, b.bat_seg0, b.bat_info);
+    {
+        const int64_t total = (int64_t)E3 + (int64_t)UNIT_BATCH_COST * NB;
+        int64_t nu = std::min<int64_t>(UNIT_MAX, std::max<int64_t>(1, total / UNIT_MIN_COST));
+        b.num_units = (int32_t)nu;
+        RGCN_CUDA(cudaMalloc(&b.units, (size_t)(nu + 1) * sizeof(int4)));
+        k_units<<<blocks_for(nu + 1), TPB, 0, st>>>(b.bat_seg0, b.seg_ptr, NB, S, E3, (int32_t)nu, b.units);
+    }
     RGCN_CUDA(cudaStreamSynchronize(st));
     RGCN_CUDA(cudaGetLastError());
     b.bytes = n2 * 12 + (int64_t)S * 16 + (int64_t)E3 * 8 + (int64_t)NC * 8 + (int64_t)NB * 8;
@@ -352,18 +420,87 @@ extern "C" void rgcn_graph_destroy(rgcn_graph* g) {
         if (i == RGCN_BRC_FWD_REL && g->rel_is_fwd) continue;
         g->brc[i].release();
     }
-    if (g->w_entry) cudaFree(g->w_entry);
     delete g;
 }
 
-extern "C" int rgcn_graph_create(const int64_t* src, int64_t src_stride, const int64_t* dst, int64_t dst_stride,
-                                 const int64_t* etype, int64_t etype_stride, int64_t num_edges, int64_t num_nodes,
-                                 int32_t num_relations, int32_t range_nodes, int32_t split_threshold,
-                                 int32_t chunk_size, void* stream, rgcn_graph** out) {
+namespace {
+
+// w_edge[e] = 1 / |{e' : rel(e') = rel(e), dst(e') = dst(e)}|  over ALL edges of the graph
+int compute_edge_weights(const int32_t* dst32, const int32_t* rel32, int64_t E, int64_t N, int R, float* w_edge,
+                         cudaStream_t st) {
+    if (E == 0) return 0;
+    Dev<uint64_t> key, skey;
+    Dev<int32_t> eid, perm, head, scan, start;
+    RGCN_CUDA(key.alloc(E));
+    RGCN_CUDA(skey.alloc(E));
+    RGCN_CUDA(eid.alloc(E));
+    RGCN_CUDA(perm.alloc(E));
+    RGCN_CUDA(head.alloc(E));
+    RGCN_CUDA(scan.alloc(E));
+    k_wkeys<<<blocks_for(E), TPB, 0, st>>>(dst32, rel32, E, N, key.p, eid.p);
+    const int end_bit = std::min(64, bit_length((uint64_t)R * (uint64_t)N));
+    size_t tmp_bytes = 0;
+    RGCN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key.p, skey.p, eid.p, perm.p, (int)E, 0, end_bit, st));
+    Dev<char> tmp;
+    RGCN_CUDA(tmp.alloc(tmp_bytes));
+    RGCN_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key.p, skey.p, eid.p, perm.p, (int)E, 0, end_bit, st));
+    k_heads<<<blocks_for(E), TPB, 0, st>>>(skey.p, E, head.p);
+    RGCN_CUDA(scan_inclusive(head.p, scan.p, E, st));
+    int32_t S = 0;
+    RGCN_CUDA(cudaMemcpy(&S, scan.p + (E - 1), 4, cudaMemcpyDeviceToHost));
+    RGCN_CUDA(start.alloc((size_t)S + 1));
+    k_run_starts<<<blocks_for(E), TPB, 0, st>>>(head.p, scan.p, E, start.p);
+    k_set_i32<<<1, 1, 0, st>>>(start.p + S, (int32_t)E);
+    k_edge_weights<<<blocks_for(E), TPB, 0, st>>>(perm.p, scan.p, start.p, E, w_edge);
+    RGCN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// Entry list (owner-local, gather-global, rel, weight) of the edges whose owner end is in [lo,hi),
+// in input order, followed by the self loops of the owned nodes; then the BRC(s) over it.
+int build_side(const int32_t* own_g, const int32_t* gat_g, const int32_t* rel_g, const float* w_edge, int64_t E,
+               int64_t n_gat, int R, int64_t lo, int64_t hi, int NR, int T, int CH, cudaStream_t st, Brc* blocked,
+               Brc* relmajor) {
+    Dev<int32_t> flag, pos, own, gat, rel;
+    Dev<float> w;
+    RGCN_CUDA(flag.alloc(E + 1));
+    RGCN_CUDA(pos.alloc(E + 1));
+    int32_t nsel = 0;
+    if (E > 0) {
+        RGCN_CUDA(cudaMemsetAsync(flag.p, 0, (size_t)(E + 1) * 4, st));
+        k_flag_owned<<<blocks_for(E), TPB, 0, st>>>(own_g, E, (int32_t)lo, (int32_t)hi, flag.p);
+        RGCN_CUDA(scan_exclusive(flag.p, pos.p, E + 1, st));
+        RGCN_CUDA(cudaMemcpy(&nsel, pos.p + E, 4, cudaMemcpyDeviceToHost));
+    }
+    const int64_t n_own = hi - lo;
+    const int64_t n2 = (int64_t)nsel + n_own;
+    RGCN_CUDA(own.alloc(n2));
+    RGCN_CUDA(gat.alloc(n2));
+    RGCN_CUDA(rel.alloc(n2));
+    RGCN_CUDA(w.alloc(n2));
+    k_fill_entries<<<blocks_for(E + n_own), TPB, 0, st>>>(own_g, gat_g, rel_g, w_edge, flag.p, pos.p, E, nsel,
+                                                          (int32_t)lo, (int32_t)hi, R, own.p, gat.p, rel.p, w.p);
+    int rc;
+    if ((rc = build_brc(own.p, gat.p, rel.p, w.p, n2, n_own, n_gat, R, NR, T, CH, st, blocked))) return rc;
+    if (relmajor && (rc = build_brc(own.p, gat.p, rel.p, w.p, n2, n_own, n_gat, R, (int)std::max<int64_t>(n_own, 1), T,
+                                    CH, st, relmajor)))
+        return rc;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int rgcn_graph_create_part(const int64_t* src, int64_t src_stride, const int64_t* dst, int64_t dst_stride,
+                                      const int64_t* etype, int64_t etype_stride, int64_t num_edges,
+                                      int64_t num_nodes, int32_t num_relations, int64_t own_lo, int64_t own_hi,
+                                      int32_t range_nodes, int32_t split_threshold, int32_t chunk_size, void* stream,
+                                      rgcn_graph** out) {
     if (!out) return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_create: out is null");
     *out = nullptr;
     if (num_edges < 0 || num_nodes <= 0 || num_relations <= 0)
         return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_create: need num_edges >= 0, num_nodes > 0, num_relations > 0");
+    if (own_lo < 0 || own_hi > num_nodes || own_lo >= own_hi)
+        return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_create: need 0 <= own_lo < own_hi <= num_nodes");
     if (num_edges > 0 && (!src || !dst || !etype))
         return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_create: null edge tensor");
     if (num_edges + num_nodes >= (int64_t)0x7fffffff - 65536 || num_relations >= (1 << 22))
@@ -378,17 +515,20 @@ extern "C" int rgcn_graph_create(const int64_t* src, int64_t src_stride, const i
     g->N = num_nodes;
     g->E = num_edges;
     g->R = num_relations;
+    g->own_lo = own_lo;
+    g->n_own = own_hi - own_lo;
     cudaGetDevice(&g->device);
     cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, g->device);
     g->split_threshold = split_threshold > 0 ? split_threshold : 256;
     g->chunk_size = chunk_size > 0 ? chunk_size : 256;
     int64_t nr = range_nodes > 0 ? range_nodes : 4096;
     // small graphs: one range (pure relation-major); large: blocked so accumulate targets stay L2-hot
-    if (nr >= num_nodes) nr = num_nodes;
+    if (nr >= g->n_own) nr = g->n_own;
     g->range_nodes = (int32_t)nr;
 
-    int64_t n2 = num_edges + num_nodes;
+    const int64_t E = num_edges;
     Dev<int32_t> src32, dst32, rel32;
+    Dev<float> w_edge;
     Dev<int> err;
     int rc = 0;
     auto bail = [&](int code) {
@@ -401,40 +541,47 @@ extern "C" int rgcn_graph_create(const int64_t* src, int64_t src_stride, const i
         if (_e != cudaSuccess)                                                                     \
             return bail(fail((int)_e, std::string(#call) + ": " + cudaGetErrorString(_e)));        \
     } while (0)
-    RGCN_CUDA_G(src32.alloc(n2));
-    RGCN_CUDA_G(dst32.alloc(n2));
-    RGCN_CUDA_G(rel32.alloc(n2));
+    RGCN_CUDA_G(src32.alloc(E));
+    RGCN_CUDA_G(dst32.alloc(E));
+    RGCN_CUDA_G(rel32.alloc(E));
+    RGCN_CUDA_G(w_edge.alloc(E));
     RGCN_CUDA_G(err.alloc(1));
     RGCN_CUDA_G(cudaMemsetAsync(err.p, 0, sizeof(int), st));
-    k_entries<<<blocks_for(n2), TPB, 0, st>>>(src, src_stride, dst, dst_stride, etype, etype_stride, num_edges,
-                                              num_nodes, num_relations, src32.p, dst32.p, rel32.p, err.p);
+    if (E > 0)
+        k_edges<<<blocks_for(E), TPB, 0, st>>>(src, src_stride, dst, dst_stride, etype, etype_stride, E, num_nodes,
+                                               num_relations, src32.p, dst32.p, rel32.p, err.p);
     int herr = 0;
     RGCN_CUDA_G(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     RGCN_CUDA_G(cudaStreamSynchronize(st));
     if (herr)
         return bail(fail(RGCN_ERR_INDEX_RANGE,
                          "rgcn_graph_create: edge_index outside [0,num_nodes) or edge_type outside [0,num_relations)"));
-    RGCN_CUDA_G(cudaMalloc(&g->w_entry, std::max<int64_t>(n2, 1) * 4));
+    if ((rc = compute_edge_weights(dst32.p, rel32.p, E, num_nodes, num_relations, w_edge.p, st))) return bail(rc);
     const int T = g->split_threshold, CH = g->chunk_size;
-    // forward: owner = dst, gather = src ; defines the per-(relation,dst) mean weights
-    if ((rc = build_brc(dst32.p, src32.p, rel32.p, n2, num_nodes, num_relations, (int)nr, T, CH, g->w_entry, true, st,
-                        &g->brc[RGCN_BRC_FWD])))
+    const bool one_range = nr >= g->n_own;
+    // forward: owner = dst, gather = src (+ the same entries in pure relation-major order for dL/dW)
+    if ((rc = build_side(dst32.p, src32.p, rel32.p, w_edge.p, E, num_nodes, num_relations, own_lo, own_hi, (int)nr, T,
+                         CH, st, &g->brc[RGCN_BRC_FWD], one_range ? nullptr : &g->brc[RGCN_BRC_FWD_REL])))
         return bail(rc);
-    // transposed: owner = src, gather = dst, same per-entry weights
-    if ((rc = build_brc(src32.p, dst32.p, rel32.p, n2, num_nodes, num_relations, (int)nr, T, CH, g->w_entry, false, st,
-                        &g->brc[RGCN_BRC_BWD])))
-        return bail(rc);
-    if (nr >= num_nodes) {
+    if (one_range) {
         g->brc[RGCN_BRC_FWD_REL] = g->brc[RGCN_BRC_FWD];
         g->rel_is_fwd = true;
-    } else {
-        if ((rc = build_brc(dst32.p, src32.p, rel32.p, n2, num_nodes, num_relations, (int)num_nodes, T, CH, g->w_entry,
-                            false, st, &g->brc[RGCN_BRC_FWD_REL])))
-            return bail(rc);
     }
+    // transposed: owner = src, gather = dst, same per-edge weights
+    if ((rc = build_side(src32.p, dst32.p, rel32.p, w_edge.p, E, num_nodes, num_relations, own_lo, own_hi, (int)nr, T,
+                         CH, st, &g->brc[RGCN_BRC_BWD], nullptr)))
+        return bail(rc);
 #undef RGCN_CUDA_G
     *out = g;
     return 0;
+}
+
+extern "C" int rgcn_graph_create(const int64_t* src, int64_t src_stride, const int64_t* dst, int64_t dst_stride,
+                                 const int64_t* etype, int64_t etype_stride, int64_t num_edges, int64_t num_nodes,
+                                 int32_t num_relations, int32_t range_nodes, int32_t split_threshold,
+                                 int32_t chunk_size, void* stream, rgcn_graph** out) {
+    return rgcn_graph_create_part(src, src_stride, dst, dst_stride, etype, etype_stride, num_edges, num_nodes,
+                                  num_relations, 0, num_nodes, range_nodes, split_threshold, chunk_size, stream, out);
 }
 
 extern "C" int rgcn_graph_query(const rgcn_graph* g, int32_t brc, int32_t key, int64_t* out) {
@@ -450,8 +597,11 @@ extern "C" int rgcn_graph_query(const rgcn_graph* g, int32_t brc, int32_t key, i
         case RGCN_Q_NUM_GROUPS: *out = b.num_groups; break;
         case RGCN_Q_NUM_BATCHES: *out = b.num_batches; break;
         case RGCN_Q_RANGE_NODES: *out = b.range_nodes; break;
+        case RGCN_Q_NUM_OWNED: *out = g->n_own; break;
+        case RGCN_Q_OWN_LO: *out = g->own_lo; break;
+        case RGCN_Q_NUM_ENTRIES0: *out = b.num_entries0; break;
         case RGCN_Q_DEVICE_BYTES:
-            *out = g->brc[0].bytes + g->brc[1].bytes + (g->rel_is_fwd ? 0 : g->brc[2].bytes) + (g->E + g->N) * 4;
+            *out = g->brc[0].bytes + g->brc[1].bytes + (g->rel_is_fwd ? 0 : g->brc[2].bytes);
             break;
         default: return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_query: unknown key");
     }

@@ -15,6 +15,7 @@
 // The self loop (root) is relation R of the same structure; bias rides on it.
 // Long segments were cut into chunk rows at build time; a pre-pass reduces those first.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -32,9 +33,16 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+// weights: round-to-nearest split, done once per call in k_wprep
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
     hi = to_tf32(x);
     lo = to_tf32(x - __uint_as_float(hi));
+}
+// activations (inner loops): hi = x with the 13 low mantissa bits cleared, lo = x - hi (exact).
+// mma .tf32 reads only the upper 19 bits of each operand, so lo needs no further rounding.
+__device__ __forceinline__ void split_fast(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                          uint32_t b0, uint32_t b1) {
@@ -43,89 +51,175 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+// 4-byte async copy global -> shared; src_bytes = 0 zero-fills (rows without an owner)
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, int src_bytes) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void red_add_v4(float* p, float x, float y, float z, float w) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 
-// Weighted sum of gathered rows over entries [ebeg,eend).  Lane l owns columns l and l+32.
-// FLAGGED: entries carry LAST_FLAG; at each flag the running sums go to H[cs*ldh + col], cs++.
-// !FLAGGED: a single sum is returned in (acc0, acc1).
-template <int KP, bool FLAGGED>
-__device__ __forceinline__ void gather_rows(const uint32_t* __restrict__ idx_arr, const float* __restrict__ w_arr,
-                                            int ebeg, int eend, const float* __restrict__ feat, int64_t ldf, int kin,
-                                            const float* __restrict__ aux, int64_t n_nodes, bool relu,
-                                            float* __restrict__ H, int ldh, int lane, float& acc0, float& acc1) {
-    acc0 = 0.f;
-    acc1 = 0.f;
-    int cs = 0;
-    const bool c0 = lane < kin;
-    const bool c1 = (KP > 32) && (lane + 32 < kin);
-    for (int base = ebeg; base < eend; base += 32) {
-        const int m = min(32, eend - base);
-        uint32_t my_idx = 0;
-        float my_w = 0.f;
-        if (lane < m) {
-            my_idx = idx_arr[base + lane];
-            my_w = w_arr[base + lane];
+// ---- streaming gather ---------------------------------------------------------------------------
+// A warp walks a CONTIGUOUS run of entries (its batches are consecutive segments, and entries are
+// stored in segment order).  Entries are taken 32 at a time (one coalesced index/weight load,
+// prefetched one block ahead), rows 8 at a time: 16 broadcasts, then 16 independent row loads
+// issued back to back (lane l reads columns l and l+32), then 8 weighted accumulations.
+// Slots past the end of the run carry index 0 / weight 0: they load row 0 and change nothing,
+// so the inner loops carry only the two per-lane column predicates.
+constexpr int RING = 32;   // smem ring of finished segment rows per warp (>= 16 + 8)
+
+struct LanePtrs {   // per-lane base pointers (lane's column folded in) and column predicates
+    const float* f0;
+    const float* a0;
+    uint32_t ldf, n_rows;
+    bool c0, c1;
+};
+template <int KP>
+__device__ __forceinline__ LanePtrs lane_ptrs(const float* feat, int64_t ldf, int kin, const float* aux,
+                                              int64_t n_rows, int lane) {
+    LanePtrs q;
+    q.f0 = feat + lane;
+    q.a0 = (aux ? aux : feat) + lane;
+    q.ldf = (uint32_t)ldf;
+    q.n_rows = (uint32_t)n_rows;
+    q.c0 = lane < kin;
+    q.c1 = (KP > 32) && (lane + 32 < kin);
+    return q;
+}
+
+template <int KP, bool RELU>
+struct RowGroup {
+    float v0[GATHER_U], v1[GATHER_U], w[GATHER_U];
+    uint32_t raw[GATHER_U];
+    // CH: the block contains chunk rows (index >= n_rows) -> per-entry select; rare
+    template <bool CH>
+    __device__ __forceinline__ void load(uint32_t blk_idx, float blk_w, int j0, const LanePtrs& q) {
+#pragma unroll
+        for (int u = 0; u < GATHER_U; ++u) {
+            raw[u] = __shfl_sync(FULL, blk_idx, j0 + u);
+            w[u] = __shfl_sync(FULL, blk_w, j0 + u);
         }
-        for (int j0 = 0; j0 < m; j0 += GATHER_U) {
-            float v0[GATHER_U], v1[GATHER_U];
+        const float* p0[GATHER_U];
 #pragma unroll
-            for (int u = 0; u < GATHER_U; ++u) {
-                v0[u] = 0.f;
-                v1[u] = 0.f;
-                if (j0 + u < m) {
-                    const uint32_t raw = __shfl_sync(FULL, my_idx, j0 + u);
-                    const int64_t row = (int64_t)(raw & IDX_MASK);
-                    const float* rp = row < n_nodes ? feat + row * ldf : aux + (row - n_nodes) * KP;
-                    if (c0) v0[u] = __ldg(rp + lane);
-                    if (KP > 32) {
-                        if (c1) v1[u] = __ldg(rp + lane + 32);
-                    }
-                }
+        for (int u = 0; u < GATHER_U; ++u) {
+            const uint32_t row = raw[u] & IDX_MASK;
+            if (CH && row >= q.n_rows) p0[u] = q.a0 + (uint64_t)(row - q.n_rows) * KP;
+            else p0[u] = q.f0 + (uint64_t)row * q.ldf;
+        }
+#pragma unroll
+        for (int u = 0; u < GATHER_U; ++u) {
+            v0[u] = 0.f;
+            v1[u] = 0.f;
+            if (q.c0) v0[u] = __ldg(p0[u]);
+            if (KP > 32) {
+                if (q.c1) v1[u] = __ldg(p0[u] + 32);
             }
+        }
+        if (RELU) {
 #pragma unroll
             for (int u = 0; u < GATHER_U; ++u) {
-                if (j0 + u < m) {
-                    const uint32_t raw = __shfl_sync(FULL, my_idx, j0 + u);
-                    const float w = __shfl_sync(FULL, my_w, j0 + u);
-                    float x0 = v0[u], x1 = v1[u];
-                    if (relu && (int64_t)(raw & IDX_MASK) < n_nodes) {
-                        x0 = fmaxf(x0, 0.f);
-                        x1 = fmaxf(x1, 0.f);
-                    }
-                    acc0 = fmaf(w, x0, acc0);
-                    acc1 = fmaf(w, x1, acc1);
-                    if (FLAGGED && (raw & LAST_FLAG)) {
-                        if (lane < KP) H[cs * ldh + lane] = acc0;
-                        if (KP > 32) H[cs * ldh + lane + 32] = acc1;
-                        acc0 = 0.f;
-                        acc1 = 0.f;
-                        ++cs;
-                    }
+                if (!CH || (raw[u] & IDX_MASK) < q.n_rows) {   // chunk rows are sums of rectified rows already
+                    v0[u] = fmaxf(v0[u], 0.f);
+                    v1[u] = fmaxf(v1[u], 0.f);
                 }
             }
         }
     }
-}
+    __device__ __forceinline__ void load_any(uint32_t blk_idx, float blk_w, int j0, const LanePtrs& q, bool has_chunk) {
+        if (has_chunk) load<true>(blk_idx, blk_w, j0, q);
+        else load<false>(blk_idx, blk_w, j0, q);
+    }
+};
+
+// Entry stream of one warp: block prefetch + the ring of finished segment rows.
+template <int KP, int LDH>
+struct Stream {
+    uint32_t nxt_idx, blk_idx;
+    float nxt_w, blk_w;
+    int ring_w;
+    float acc0, acc1;
+    bool has_chunk;
+    __device__ __forceinline__ void start(const uint32_t* e_idx, const float* e_w, int E0, int E1, int lane) {
+        nxt_idx = 0;
+        nxt_w = 0.f;
+        if (E0 + lane < E1) {
+            nxt_idx = e_idx[E0 + lane];
+            nxt_w = e_w[E0 + lane];
+        }
+        ring_w = 0;
+        acc0 = acc1 = 0.f;
+    }
+    __device__ __forceinline__ void next_block(const uint32_t* e_idx, const float* e_w, int pos, int E1, int lane,
+                                               uint32_t n_rows) {
+        blk_idx = nxt_idx;
+        blk_w = nxt_w;
+        nxt_idx = 0;
+        nxt_w = 0.f;
+        if (pos + 32 + lane < E1) {
+            nxt_idx = e_idx[pos + 32 + lane];
+            nxt_w = e_w[pos + 32 + lane];
+        }
+        has_chunk = __any_sync(FULL, (blk_idx & IDX_MASK) >= n_rows);
+    }
+    // branch-free: the running sums are stored on every entry and kept or cleared by the LAST flag
+    template <bool RELU>
+    __device__ __forceinline__ void consume(const RowGroup<KP, RELU>& rg, float* H, int lane) {
+#pragma unroll
+        for (int u = 0; u < GATHER_U; ++u) {
+            acc0 = fmaf(rg.w[u], rg.v0[u], acc0);
+            acc1 = fmaf(rg.w[u], rg.v1[u], acc1);
+            float* hr = H + (ring_w & (RING - 1)) * LDH;
+            if (KP >= 32 || lane < KP) hr[lane] = acc0;
+            if (KP > 32) hr[lane + 32] = acc1;
+            const uint32_t last = rg.raw[u] >> 31;
+            ring_w += (int)last;
+            acc0 = last ? 0.f : acc0;
+            acc1 = last ? 0.f : acc1;
+        }
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // chunk pre-pass: aux[c] = sum_{k in chunk c} raw_w[k] * feat[raw_idx[k]]   (one warp per chunk)
 // ---------------------------------------------------------------------------------------------
-template <int KP>
+template <int KP, bool RELU>
 __global__ void __launch_bounds__(256) k_chunk_sum(const int32_t* __restrict__ raw_idx, const float* __restrict__ raw_w,
                                                    const int32_t* __restrict__ chunk_beg,
                                                    const int32_t* __restrict__ chunk_end, int num_chunks,
                                                    const float* __restrict__ feat, int64_t ldf, int kin,
-                                                   int64_t n_nodes, int relu, float* __restrict__ aux) {
+                                                   int64_t n_rows, float* __restrict__ aux) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= num_chunks) return;
-    float a0, a1;
-    gather_rows<KP, false>(reinterpret_cast<const uint32_t*>(raw_idx), raw_w, chunk_beg[c], chunk_end[c], feat, ldf,
-                           kin, nullptr, n_nodes, relu != 0, nullptr, 0, lane, a0, a1);
-    if (lane < KP) aux[(int64_t)c * KP + lane] = a0;
-    if (KP > 32) aux[(int64_t)c * KP + lane + 32] = a1;
+    const LanePtrs q = lane_ptrs<KP>(feat, ldf, kin, nullptr, n_rows, lane);
+    const int e0 = chunk_beg[c], e1 = chunk_end[c];
+    float acc0 = 0.f, acc1 = 0.f;
+    for (int pos = e0; pos < e1; pos += 32) {
+        uint32_t bi = 0;
+        float bw = 0.f;
+        if (pos + lane < e1) {
+            bi = (uint32_t)raw_idx[pos + lane];
+            bw = raw_w[pos + lane];
+        }
+        const int m = min(32, e1 - pos);
+        for (int j0 = 0; j0 < m; j0 += GATHER_U) {
+            RowGroup<KP, RELU> rg;
+            rg.template load<false>(bi, bw, j0, q);
+#pragma unroll
+            for (int u = 0; u < GATHER_U; ++u) {
+                acc0 = fmaf(rg.w[u], rg.v0[u], acc0);
+                acc1 = fmaf(rg.w[u], rg.v1[u], acc1);
+            }
+        }
+    }
+    if (lane < KP) aux[(int64_t)c * KP + lane] = acc0;
+    if (KP > 32) aux[(int64_t)c * KP + lane + 32] = acc1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -179,6 +273,9 @@ struct TileArgs {
     const int32_t* bat_seg0;
     const int32_t* bat_info;
     int num_batches;
+    int num_entries;
+    const int4* units;
+    int num_units;
     const float* feat;
     int64_t ldf;
     int kin;
@@ -194,100 +291,126 @@ struct TileArgs {
     int relu_in;
 };
 
-template <int KT, int NT>
-__global__ void __launch_bounds__(TILE_WARPS * 32) k_tile(const TileArgs a) {
+template <int KT, int NT, bool RELU, bool BREG>
+__global__ void __launch_bounds__(TILE_WARPS * 32, BREG ? 1 : (NT <= 2 ? 3 : 2)) k_tile(const TileArgs a) {
     constexpr int KP = KT * 8, LDH = KP + 4;
-    constexpr bool BREG = (KT * NT <= 16);
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* H = smem + warp * (BS * LDH);
+    float* H = smem + warp * (RING * LDH);
     const int g = lane >> 2, t = lane & 3;
-    const int64_t gw = (int64_t)blockIdx.x * TILE_WARPS + warp;
-    const int64_t nw = (int64_t)gridDim.x * TILE_WARPS;
-    const int per = (int)((a.num_batches + nw - 1) / nw);
-    const int b_begin = (int)min((int64_t)a.num_batches, gw * per);
-    const int b_end = (int)min((int64_t)a.num_batches, gw * per + per);
+    const int gw = blockIdx.x * TILE_WARPS + warp;
+    const int nw = gridDim.x * TILE_WARPS;
+    const uint32_t* __restrict__ e_idx = a.e_idx;
+    const float* __restrict__ e_w = a.e_w;
+    const LanePtrs q = lane_ptrs<KP>(a.feat, a.ldf, a.kin, a.aux, a.n_nodes, lane);
     float4 bfrag[BREG ? KT * NT : 1];
     int cur_rel = -1;
-    for (int b = b_begin; b < b_end; ++b) {
-        const int seg0 = a.bat_seg0[b];
-        const int info = a.bat_info[b];
-        const int nseg = info & 0xff, rel = info >> 8;
-        const float4* wf = a.wfrag + (int64_t)rel * (KT * NT * 32) + lane;
-        if constexpr (BREG) {
-            if (rel != cur_rel) {
+
+    for (int unit = gw; unit < a.num_units; unit += nw) {   // equal-cost units, round-robin over warps
+        const int4 u0 = a.units[unit], u1 = a.units[unit + 1];
+        int b = u0.x;
+        const int b_end = u1.x;
+        if (b >= b_end) continue;
+        int seg0 = u0.y;
+        const int E0 = u0.z, E1 = u1.z;
+        int info = a.bat_info[b];
+        int nseg = info & 0xff, rel = info >> 8;
+        int my_own = lane < nseg ? a.seg_own[seg0 + lane] : -1;
+        int info_n = b + 1 < b_end ? a.bat_info[b + 1] : 0;
+        int own_n = (b + 1 < b_end && lane < (info_n & 0xff)) ? a.seg_own[seg0 + nseg + lane] : -1;
+        int ring_base = 0;
+        Stream<KP, LDH> sm;
+        sm.start(e_idx, e_w, E0, E1, lane);
+        for (int pos = E0; pos < E1; pos += 32) {
+            sm.next_block(e_idx, e_w, pos, E1, lane, q.n_rows);
+            const int m = min(32, E1 - pos);
+            for (int j0 = 0; j0 < m; j0 += GATHER_U) {
+                RowGroup<KP, RELU> rg;
+                rg.load_any(sm.blk_idx, sm.blk_w, j0, q, sm.has_chunk);
+                sm.consume(rg, H, lane);
+                // drain every batch whose rows are all in the ring
+                while (b < b_end && sm.ring_w - ring_base >= nseg) {
+                    __syncwarp();
+                    const float4* wf = a.wfrag + (int64_t)rel * (KT * NT * 32) + lane;
+                    if constexpr (BREG) {
+                        if (rel != cur_rel) {
 #pragma unroll
-                for (int i = 0; i < KT * NT; ++i) bfrag[i] = __ldg(wf + i * 32);
-                cur_rel = rel;
-            }
-        }
-        const int my_own = lane < nseg ? a.seg_own[seg0 + lane] : -1;
-        const int my_ptr = lane <= nseg ? a.seg_ptr[seg0 + lane] : 0;
-        const int ebeg = __shfl_sync(FULL, my_ptr, 0), eend = __shfl_sync(FULL, my_ptr, nseg);
-        if (nseg < BS) {
-            for (int r = nseg; r < BS; ++r) {
-                if (lane < KP) H[r * LDH + lane] = 0.f;
-                if (KP > 32) H[r * LDH + lane + 32] = 0.f;
-            }
-        }
-        float u0, u1;
-        gather_rows<KP, true>(a.e_idx, a.e_w, ebeg, eend, a.feat, a.ldf, a.kin, a.aux, a.n_nodes, a.relu_in != 0, H, LDH,
-                              lane, u0, u1);
-        __syncwarp();
-        float d[NT][4];
+                            for (int i = 0; i < KT * NT; ++i) bfrag[i] = __ldg(wf + i * 32);
+                            cur_rel = rel;
+                        }
+                    }
+                    const float* h_lo = H + ((ring_base + g) & (RING - 1)) * LDH;
+                    const float* h_hi = H + ((ring_base + g + 8) & (RING - 1)) * LDH;
+                    float d[NT][4];
 #pragma unroll
-        for (int n = 0; n < NT; ++n) d[n][0] = d[n][1] = d[n][2] = d[n][3] = 0.f;
+                    for (int n = 0; n < NT; ++n) d[n][0] = d[n][1] = d[n][2] = d[n][3] = 0.f;
 #pragma unroll
-        for (int kt = 0; kt < KT; ++kt) {
-            uint32_t ah[4], al[4];
-            split_tf32(H[g * LDH + 8 * kt + t], ah[0], al[0]);
-            split_tf32(H[(g + 8) * LDH + 8 * kt + t], ah[1], al[1]);
-            split_tf32(H[g * LDH + 8 * kt + t + 4], ah[2], al[2]);
-            split_tf32(H[(g + 8) * LDH + 8 * kt + t + 4], ah[3], al[3]);
+                    for (int kt = 0; kt < KT; ++kt) {
+                        uint32_t ah[4], al[4];
+                        split_fast(h_lo[8 * kt + t], ah[0], al[0]);
+                        split_fast(h_hi[8 * kt + t], ah[1], al[1]);
+                        split_fast(h_lo[8 * kt + t + 4], ah[2], al[2]);
+                        split_fast(h_hi[8 * kt + t + 4], ah[3], al[3]);
 #pragma unroll
-            for (int n = 0; n < NT; ++n) {
-                float4 bf;
-                if constexpr (BREG) bf = bfrag[kt * NT + n];
-                else bf = __ldg(wf + (kt * NT + n) * 32);
-                const uint32_t bh0 = __float_as_uint(bf.x), bh1 = __float_as_uint(bf.y);
-                const uint32_t bl0 = __float_as_uint(bf.z), bl1 = __float_as_uint(bf.w);
-                mma_tf32(d[n], al[0], al[1], al[2], al[3], bh0, bh1);
-                mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
-                mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
-            }
-        }
-        if (rel == a.self_rel && a.bias != nullptr) {
+                        for (int n = 0; n < NT; ++n) {
+                            float4 bf;
+                            if constexpr (BREG) bf = bfrag[kt * NT + n];
+                            else bf = __ldg(wf + (kt * NT + n) * 32);
+                            const uint32_t bh0 = __float_as_uint(bf.x), bh1 = __float_as_uint(bf.y);
+                            const uint32_t bl0 = __float_as_uint(bf.z), bl1 = __float_as_uint(bf.w);
+                            mma_tf32(d[n], al[0], al[1], al[2], al[3], bh0, bh1);
+                            mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+                            mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+                        }
+                    }
+                    if (rel == a.self_rel && a.bias != nullptr) {
 #pragma unroll
-            for (int n = 0; n < NT; ++n) {
-                const int col = 8 * n + 2 * t;
-                const float bx = col < a.nbias ? a.bias[col] : 0.f;
-                const float by = col + 1 < a.nbias ? a.bias[col + 1] : 0.f;
-                d[n][0] += bx;
-                d[n][1] += by;
-                d[n][2] += bx;
-                d[n][3] += by;
-            }
-        }
-        const int own_lo = __shfl_sync(FULL, my_own, g), own_hi = __shfl_sync(FULL, my_own, g + 8);
-        const bool odd = (t & 1) != 0;
+                        for (int n = 0; n < NT; ++n) {
+                            const int col = 8 * n + 2 * t;
+                            const float bx = col < a.nbias ? a.bias[col] : 0.f;
+                            const float by = col + 1 < a.nbias ? a.bias[col + 1] : 0.f;
+                            d[n][0] += bx;
+                            d[n][1] += by;
+                            d[n][2] += bx;
+                            d[n][3] += by;
+                        }
+                    }
+                    // rows past nseg belong to later batches: their owners read -1 and are skipped
+                    const int own_lo = __shfl_sync(FULL, my_own, g), own_hi = __shfl_sync(FULL, my_own, g + 8);
+                    const bool odd = (t & 1) != 0;
 #pragma unroll
-        for (int j = 0; j < NT / 2; ++j) {
-            const int col = odd ? 8 * (2 * j + 1) + 2 * (t - 1) : 8 * (2 * j) + 2 * t;
+                    for (int j = 0; j < NT / 2; ++j) {
+                        const int col = odd ? 8 * (2 * j + 1) + 2 * (t - 1) : 8 * (2 * j) + 2 * t;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {   // h = 0: row g ; h = 1: row g + 8
-                const float e0 = d[2 * j][2 * h], e1 = d[2 * j][2 * h + 1];
-                const float f0 = d[2 * j + 1][2 * h], f1 = d[2 * j + 1][2 * h + 1];
-                const float rx = __shfl_xor_sync(FULL, odd ? e0 : f0, 1);
-                const float ry = __shfl_xor_sync(FULL, odd ? e1 : f1, 1);
-                const int own = h ? own_hi : own_lo;
-                if (own >= 0 && col < a.nout) {
-                    float* p = a.out + (int64_t)own * a.ldo + col;
-                    if (odd) red_add_v4(p, rx, ry, f0, f1);
-                    else red_add_v4(p, e0, e1, rx, ry);
+                        for (int h = 0; h < 2; ++h) {   // h = 0: row g ; h = 1: row g + 8
+                            const float e0 = d[2 * j][2 * h], e1 = d[2 * j][2 * h + 1];
+                            const float f0 = d[2 * j + 1][2 * h], f1 = d[2 * j + 1][2 * h + 1];
+                            const float rx = __shfl_xor_sync(FULL, odd ? e0 : f0, 1);
+                            const float ry = __shfl_xor_sync(FULL, odd ? e1 : f1, 1);
+                            const int own = h ? own_hi : own_lo;
+                            if (own >= 0 && col < a.nout) {
+                                float* p = a.out + (int64_t)own * a.ldo + col;
+                                if (odd) red_add_v4(p, rx, ry, f0, f1);
+                                else red_add_v4(p, e0, e1, rx, ry);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    // next batch: metadata was prefetched one batch ago
+                    ring_base += nseg;
+                    seg0 += nseg;
+                    ++b;
+                    info = info_n;
+                    nseg = info & 0xff;
+                    rel = info >> 8;
+                    my_own = own_n;
+                    if (b < b_end) {
+                        info_n = b + 1 < b_end ? a.bat_info[b + 1] : 0;
+                        own_n = (b + 1 < b_end && lane < (info_n & 0xff)) ? a.seg_own[seg0 + nseg + lane] : -1;
+                    }
                 }
             }
         }
-        __syncwarp();
     }
 }
 
@@ -305,6 +428,9 @@ struct WGradArgs {
     const int32_t* bat_seg0;
     const int32_t* bat_info;
     int num_batches;
+    int num_entries;
+    const int4* units;
+    int num_units;
     const float* feat;
     int64_t ldf;
     int kin;
@@ -320,20 +446,26 @@ struct WGradArgs {
     int relu_in;
 };
 
-template <int KT, int NT>
-__global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const WGradArgs a) {
+template <int KT, int NT, bool RELU>
+__global__ void __launch_bounds__(WG_WARPS * 32, (KT * NT <= 16) ? 4 : ((KT * NT <= 32) ? 2 : 1)) k_wgrad(const WGradArgs a) {
     constexpr int KP = KT * 8, NP = NT * 8, MT = KP / 16;
     constexpr int LDH = KP + 8, LDG = NP + 8;
+    constexpr int GR = BS * NP / 32;   // registers holding a batch's 16 gout rows
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* H = smem + warp * (BS * (LDH + LDG));
-    float* G = H + BS * LDH;
+    float* H = smem + warp * (RING * LDH + 2 * BS * LDG);
+    float* Gbuf = H + RING * LDH;   // two buffers of 16 gout rows, filled by cp.async one batch ahead
     const int g = lane >> 2, t = lane & 3;
-    const int64_t gw = (int64_t)blockIdx.x * WG_WARPS + warp;
-    const int64_t nw = (int64_t)gridDim.x * WG_WARPS;
-    const int per = (int)((a.num_batches + nw - 1) / nw);
-    const int b_begin = (int)min((int64_t)a.num_batches, gw * per);
-    const int b_end = (int)min((int64_t)a.num_batches, gw * per + per);
+    const int gw = blockIdx.x * WG_WARPS + warp;
+    const int nw = gridDim.x * WG_WARPS;
+    // ring rows are the K dimension here: anything ever read must be finite
+    for (int i = lane; i < RING * LDH; i += 32) H[i] = 0.f;
+    __syncwarp();
+    const uint32_t* __restrict__ e_idx = a.e_idx;
+    const float* __restrict__ e_w = a.e_w;
+    const float* __restrict__ gout = a.gout;
+    const LanePtrs q = lane_ptrs<KP>(a.feat, a.ldf, a.kin, a.aux, a.n_nodes, lane);
+
     float d[MT][NT][4];
     float bsum[(NP + 31) / 32];
 #pragma unroll
@@ -359,79 +491,114 @@ __global__ void __launch_bounds__(WG_WARPS * 32) k_wgrad(const WGradArgs a) {
                 }
             }
     };
+    // the 16 gout rows of a batch, requested (async, straight into shared memory) one batch ahead
+    auto fetch_g = [&](float* dstbuf, int own) {
+#pragma unroll
+        for (int i = 0; i < GR; ++i) {
+            const int e = i * 32 + lane;
+            const int row = e / NP, col = e % NP;
+            const int o = __shfl_sync(FULL, own, row);
+            const bool ok = o >= 0 && col < a.nout;
+            cp_async4(dstbuf + row * LDG + col, ok ? gout + (int64_t)o * a.ldg + col : gout, ok ? 4 : 0);
+        }
+        cp_async_commit();
+    };
 
-    for (int b = b_begin; b < b_end; ++b) {
-        const int seg0 = a.bat_seg0[b];
-        const int info = a.bat_info[b];
-        const int nseg = info & 0xff, rel = info >> 8;
-        if (rel != cur_rel) {
-            if (cur_rel >= 0) flush(cur_rel);
-            cur_rel = rel;
-        }
-        if (rel != a.self_rel && a.gweight == nullptr) continue;
-        if (rel == a.self_rel && a.groot == nullptr && a.gbias == nullptr) continue;
-        const int my_own = lane < nseg ? a.seg_own[seg0 + lane] : -1;
-        const int my_ptr = lane <= nseg ? a.seg_ptr[seg0 + lane] : 0;
-        const int ebeg = __shfl_sync(FULL, my_ptr, 0), eend = __shfl_sync(FULL, my_ptr, nseg);
-        if (nseg < BS) {
-            for (int r = nseg; r < BS; ++r) {
-                if (lane < KP) H[r * LDH + lane] = 0.f;
-                if (KP > 32) H[r * LDH + lane + 32] = 0.f;
-            }
-        }
-        // G rows: gout[owner]
-#pragma unroll 8
-        for (int r = 0; r < BS; ++r) {
-            const int own = __shfl_sync(FULL, my_own, r);
-            float x0 = 0.f, x1 = 0.f;
-            if (own >= 0) {
-                const float* gp = a.gout + (int64_t)own * a.ldg;
-                if (lane < a.nout) x0 = __ldg(gp + lane);
-                if (NP > 32 && lane + 32 < a.nout) x1 = __ldg(gp + lane + 32);
-            }
-            if (lane < NP) G[r * LDG + lane] = x0;
-            if (NP > 32) G[r * LDG + lane + 32] = x1;
-        }
-        float u0, u1;
-        gather_rows<KP, true>(a.e_idx, a.e_w, ebeg, eend, a.feat, a.ldf, a.kin, a.aux, a.n_nodes, a.relu_in != 0, H, LDH,
-                              lane, u0, u1);
+    for (int unit = gw; unit < a.num_units; unit += nw) {
+        const int4 u0 = a.units[unit], u1 = a.units[unit + 1];
+        int b = u0.x;
+        const int b_end = u1.x;
+        if (b >= b_end) continue;
+        int seg0 = u0.y;
+        const int E0 = u0.z, E1 = u1.z;
+        int info = a.bat_info[b];
+        int nseg = info & 0xff, rel = info >> 8;
+        int my_own = lane < nseg ? a.seg_own[seg0 + lane] : -1;
+        int info_n = b + 1 < b_end ? a.bat_info[b + 1] : 0;
+        int own_n = (b + 1 < b_end && lane < (info_n & 0xff)) ? a.seg_own[seg0 + nseg + lane] : -1;
+        int par = 0;
+        cp_async_wait<0>();   // nothing of the previous unit may still be landing in the G buffers
         __syncwarp();
-        if (rel == a.self_rel) {
+        fetch_g(Gbuf, my_own);
+        fetch_g(Gbuf + BS * LDG, own_n);
+        int ring_base = 0;
+        Stream<KP, LDH> sm;
+        sm.start(e_idx, e_w, E0, E1, lane);
+        for (int pos = E0; pos < E1; pos += 32) {
+            sm.next_block(e_idx, e_w, pos, E1, lane, q.n_rows);
+            const int m_blk = min(32, E1 - pos);
+            for (int j0 = 0; j0 < m_blk; j0 += GATHER_U) {
+                RowGroup<KP, RELU> rg;
+                rg.load_any(sm.blk_idx, sm.blk_w, j0, q, sm.has_chunk);
+                sm.consume(rg, H, lane);
+                while (b < b_end && sm.ring_w - ring_base >= nseg) {
+                    if (rel != cur_rel) {
+                        if (cur_rel >= 0) flush(cur_rel);
+                        cur_rel = rel;
+                    }
+                    const bool wanted =
+                        rel == a.self_rel ? (a.groot != nullptr || a.gbias != nullptr) : a.gweight != nullptr;
+                    cp_async_wait<1>();   // this batch's rows have landed; the next batch's may still fly
+                    __syncwarp();
+                    const float* G = Gbuf + par * (BS * LDG);
+                    if (wanted) {
+                        if (rel == a.self_rel) {
 #pragma unroll
-            for (int i = 0; i < (NP + 31) / 32; ++i) {
-                const int c = lane + 32 * i;
-                if (c < NP) {
-                    float s = 0.f;
+                            for (int i = 0; i < (NP + 31) / 32; ++i) {
+                                const int c = lane + 32 * i;
+                                if (c < NP) {
+                                    float sacc = 0.f;
 #pragma unroll
-                    for (int r = 0; r < BS; ++r) s += G[r * LDG + c];
-                    bsum[i] += s;
+                                    for (int r = 0; r < BS; ++r) sacc += G[r * LDG + c];
+                                    bsum[i] += sacc;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+                            for (int n = 0; n < NT; ++n) {
+                                split_fast(G[(8 * ks + t) * LDG + 8 * n + g], bh[n][0], bl[n][0]);
+                                split_fast(G[(8 * ks + t + 4) * LDG + 8 * n + g], bh[n][1], bl[n][1]);
+                            }
+                            const float* r0 = H + ((ring_base + 8 * ks + t) & (RING - 1)) * LDH;
+                            const float* r1 = H + ((ring_base + 8 * ks + t + 4) & (RING - 1)) * LDH;
+#pragma unroll
+                            for (int m = 0; m < MT; ++m) {
+                                uint32_t ah[4], al[4];
+                                split_fast(r0[16 * m + g], ah[0], al[0]);
+                                split_fast(r0[16 * m + g + 8], ah[1], al[1]);
+                                split_fast(r1[16 * m + g], ah[2], al[2]);
+                                split_fast(r1[16 * m + g + 8], ah[3], al[3]);
+#pragma unroll
+                                for (int n = 0; n < NT; ++n) {
+                                    mma_tf32(d[m][n], al[0], al[1], al[2], al[3], bh[n][0], bh[n][1]);
+                                    mma_tf32(d[m][n], ah[0], ah[1], ah[2], ah[3], bl[n][0], bl[n][1]);
+                                    mma_tf32(d[m][n], ah[0], ah[1], ah[2], ah[3], bh[n][0], bh[n][1]);
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    ring_base += nseg;
+                    seg0 += nseg;
+                    ++b;
+                    info = info_n;
+                    nseg = info & 0xff;
+                    rel = info >> 8;
+                    my_own = own_n;
+                    info_n = 0;
+                    own_n = -1;
+                    if (b + 1 < b_end) {
+                        info_n = a.bat_info[b + 1];
+                        own_n = lane < (info_n & 0xff) ? a.seg_own[seg0 + nseg + lane] : -1;
+                    }
+                    fetch_g(Gbuf + par * (BS * LDG), own_n);   // refill the buffer just consumed (zeros past the end)
+                    par ^= 1;
                 }
             }
         }
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            uint32_t bh[NT][2], bl[NT][2];
-#pragma unroll
-            for (int n = 0; n < NT; ++n) {
-                split_tf32(G[(8 * ks + t) * LDG + 8 * n + g], bh[n][0], bl[n][0]);
-                split_tf32(G[(8 * ks + t + 4) * LDG + 8 * n + g], bh[n][1], bl[n][1]);
-            }
-#pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                uint32_t ah[4], al[4];
-                split_tf32(H[(8 * ks + t) * LDH + 16 * m + g], ah[0], al[0]);
-                split_tf32(H[(8 * ks + t) * LDH + 16 * m + g + 8], ah[1], al[1]);
-                split_tf32(H[(8 * ks + t + 4) * LDH + 16 * m + g], ah[2], al[2]);
-                split_tf32(H[(8 * ks + t + 4) * LDH + 16 * m + g + 8], ah[3], al[3]);
-#pragma unroll
-                for (int n = 0; n < NT; ++n) {
-                    mma_tf32(d[m][n], al[0], al[1], al[2], al[3], bh[n][0], bh[n][1]);
-                    mma_tf32(d[m][n], ah[0], ah[1], ah[2], ah[3], bl[n][0], bl[n][1]);
-                    mma_tf32(d[m][n], ah[0], ah[1], ah[2], ah[3], bh[n][0], bh[n][1]);
-                }
-            }
-        }
-        __syncwarp();
     }
     if (cur_rel >= 0) flush(cur_rel);
     if (a.gbias) {
@@ -461,42 +628,75 @@ __global__ void k_relu_mask(float* __restrict__ gr, int64_t ldg, const float* __
     if (!(pre[r * ldp + c] > 0.f)) gr[r * ldg + c] = 0.f;
 }
 
-template <int KT, int NT>
-int run_tile(const TileArgs& a, int num_sms, cudaStream_t st) {
+template <int KT, int NT, bool RELU, bool BREG>
+int run_tile_v(const TileArgs& a, int num_sms, cudaStream_t st) {
     constexpr int LDH = KT * 8 + 4;
-    const size_t smem = (size_t)TILE_WARPS * BS * LDH * sizeof(float);
+    const size_t smem = (size_t)TILE_WARPS * RING * LDH * sizeof(float);
     static bool configured = false;
+    auto kern = k_tile<KT, NT, RELU, BREG>;
     if (!configured) {
-        RGCN_CUDA(cudaFuncSetAttribute(k_tile<KT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     int per_sm = 1;
-    RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile<KT, NT>, TILE_WARPS * 32, smem));
+    RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILE_WARPS * 32, smem));
     per_sm = std::max(per_sm, 1);
-    int64_t want = ((int64_t)a.num_batches + TILE_WARPS - 1) / TILE_WARPS;
+    // a few batches per warp at least, so the streaming prefetch has something to stream
+    int64_t want = ((int64_t)a.num_units + TILE_WARPS - 1) / TILE_WARPS;
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms * per_sm));
-    k_tile<KT, NT><<<grid, TILE_WARPS * 32, smem, st>>>(a);
+    kern<<<grid, TILE_WARPS * 32, smem, st>>>(a);
+    RGCN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+bool breg_enabled() {   // RGCN_B200_BREG=1 keeps the B fragments of the current relation in registers
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RGCN_B200_BREG");
+        v = (e && e[0] == '1') ? 1 : 0;   // default off: the extra 64 registers cost more warps than they save loads
+    }
+    return v == 1;
+}
+
+template <int KT, int NT>
+int run_tile(const TileArgs& a, int num_sms, cudaStream_t st) {
+    const bool breg = (KT * NT <= 16) && breg_enabled();
+    if (a.relu_in) {
+        if constexpr (KT * NT <= 16) {
+            if (breg) return run_tile_v<KT, NT, true, true>(a, num_sms, st);
+        }
+        return run_tile_v<KT, NT, true, false>(a, num_sms, st);
+    }
+    if constexpr (KT * NT <= 16) {
+        if (breg) return run_tile_v<KT, NT, false, true>(a, num_sms, st);
+    }
+    return run_tile_v<KT, NT, false, false>(a, num_sms, st);
+}
+
+template <int KT, int NT, bool RELU>
+int run_wgrad_v(const WGradArgs& a, int num_sms, cudaStream_t st) {
+    constexpr int LDH = KT * 8 + 8, LDG = NT * 8 + 8;
+    const size_t smem = (size_t)WG_WARPS * (RING * LDH + 2 * BS * LDG) * sizeof(float);
+    static bool configured = false;
+    auto kern = k_wgrad<KT, NT, RELU>;
+    if (!configured) {
+        RGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int per_sm = 1;
+    RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WG_WARPS * 32, smem));
+    per_sm = std::max(per_sm, 1);
+    int64_t want = ((int64_t)a.num_units + WG_WARPS - 1) / WG_WARPS;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms * per_sm));
+    kern<<<grid, WG_WARPS * 32, smem, st>>>(a);
     RGCN_CUDA(cudaGetLastError());
     return 0;
 }
 
 template <int KT, int NT>
 int run_wgrad(const WGradArgs& a, int num_sms, cudaStream_t st) {
-    constexpr int LDH = KT * 8 + 8, LDG = NT * 8 + 8;
-    const size_t smem = (size_t)WG_WARPS * BS * (LDH + LDG) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        RGCN_CUDA(cudaFuncSetAttribute(k_wgrad<KT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    int per_sm = 1;
-    RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wgrad<KT, NT>, WG_WARPS * 32, smem));
-    per_sm = std::max(per_sm, 1);
-    int64_t want = ((int64_t)a.num_batches + WG_WARPS - 1) / WG_WARPS;
-    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms * per_sm));
-    k_wgrad<KT, NT><<<grid, WG_WARPS * 32, smem, st>>>(a);
-    RGCN_CUDA(cudaGetLastError());
-    return 0;
+    if (a.relu_in) return run_wgrad_v<KT, NT, true>(a, num_sms, st);
+    return run_wgrad_v<KT, NT, false>(a, num_sms, st);
 }
 
 #define RGCN_DISPATCH_KN(FN, kp, np, ...)                                        \
@@ -524,27 +724,29 @@ int pad_dim(int f) {
     return 0;
 }
 
+namespace {
+template <int KP>
+void run_chunk(const Brc& b, const TilePass& p, int grid, int wpb, cudaStream_t st) {
+    if (p.relu_in)
+        k_chunk_sum<KP, true><<<grid, wpb * 32, 0, st>>>(b.raw_idx, b.raw_w, b.chunk_beg, b.chunk_end, b.num_chunks, p.feat,
+                                                         p.ldf, p.kin, p.n_nodes, p.aux);
+    else
+        k_chunk_sum<KP, false><<<grid, wpb * 32, 0, st>>>(b.raw_idx, b.raw_w, b.chunk_beg, b.chunk_end, b.num_chunks, p.feat,
+                                                          p.ldf, p.kin, p.n_nodes, p.aux);
+}
+}  // namespace
+
 int launch_chunk_prepass(const TilePass& p, cudaStream_t st) {
     const Brc& b = *p.brc;
     if (b.num_chunks == 0) return 0;
     const int wpb = 8;
     const int grid = (b.num_chunks + wpb - 1) / wpb;
-    const int relu = p.relu_in ? 1 : 0;
     ProfScope prof(TAG_PREPASS, p.kin, b.num_chunks, st);
     note_launch(1);
     switch (p.kp) {
-        case 16:
-            k_chunk_sum<16><<<grid, wpb * 32, 0, st>>>(b.raw_idx, b.raw_w, b.chunk_beg, b.chunk_end, b.num_chunks,
-                                                       p.feat, p.ldf, p.kin, p.n_nodes, relu, p.aux);
-            break;
-        case 32:
-            k_chunk_sum<32><<<grid, wpb * 32, 0, st>>>(b.raw_idx, b.raw_w, b.chunk_beg, b.chunk_end, b.num_chunks,
-                                                       p.feat, p.ldf, p.kin, p.n_nodes, relu, p.aux);
-            break;
-        case 64:
-            k_chunk_sum<64><<<grid, wpb * 32, 0, st>>>(b.raw_idx, b.raw_w, b.chunk_beg, b.chunk_end, b.num_chunks,
-                                                       p.feat, p.ldf, p.kin, p.n_nodes, relu, p.aux);
-            break;
+        case 16: run_chunk<16>(b, p, grid, wpb, st); break;
+        case 32: run_chunk<32>(b, p, grid, wpb, st); break;
+        case 64: run_chunk<64>(b, p, grid, wpb, st); break;
         default: return fail(RGCN_ERR_UNSUPPORTED, "chunk pre-pass: unsupported padded width");
     }
     RGCN_CUDA(cudaGetLastError());
@@ -574,6 +776,9 @@ int launch_tile_pass(const TilePass& p, int num_sms, cudaStream_t st) {
     a.bat_seg0 = b.bat_seg0;
     a.bat_info = b.bat_info;
     a.num_batches = b.num_batches;
+    a.num_entries = (int)b.num_entries;
+    a.units = b.units;
+    a.num_units = b.num_units;
     a.feat = p.feat;
     a.ldf = p.ldf;
     a.kin = p.kin;
@@ -603,6 +808,9 @@ int launch_wgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st) {
     a.bat_seg0 = b.bat_seg0;
     a.bat_info = b.bat_info;
     a.num_batches = b.num_batches;
+    a.num_entries = (int)b.num_entries;
+    a.units = b.units;
+    a.num_units = b.num_units;
     a.feat = p.feat;
     a.ldf = p.ldf;
     a.kin = p.kin;

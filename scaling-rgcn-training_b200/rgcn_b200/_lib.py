@@ -14,14 +14,14 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'librgcn_b200.so')
 
 # every symbol include/rgcn_b200.h declares
 EXPORTS = (
-    'rgcn_last_error', 'rgcn_abi_version', 'rgcn_graph_create', 'rgcn_graph_destroy', 'rgcn_graph_query',
+    'rgcn_last_error', 'rgcn_abi_version', 'rgcn_graph_create', 'rgcn_graph_create_part', 'rgcn_graph_destroy', 'rgcn_graph_query',
     'rgcn_graph_export', 'rgcn_layer_workspace_bytes', 'rgcn_layer_fwd', 'rgcn_layer_bwd', 'rgcn_map_gather',
     'rgcn_kernel_launch_count', 'rgcn_profile_enable', 'rgcn_profile_collect',
 )
 
 BRC_FWD, BRC_BWD, BRC_FWD_REL = 0, 1, 2
 Q_NUM_NODES, Q_NUM_EDGES, Q_NUM_RELATIONS, Q_NUM_SEGMENTS, Q_NUM_ENTRIES, Q_NUM_CHUNKS, Q_NUM_GROUPS, \
-    Q_NUM_BATCHES, Q_RANGE_NODES, Q_DEVICE_BYTES = range(10)
+    Q_NUM_BATCHES, Q_RANGE_NODES, Q_DEVICE_BYTES, Q_NUM_OWNED, Q_OWN_LO, Q_NUM_ENTRIES0 = range(13)
 A_PERM, A_SEG_PTR, A_SEG_OWN, A_SEG_REL, A_SEG_PTR0, A_E_IDX, A_E_W, A_RAW_IDX, A_RAW_W, A_CHUNK_BEG, \
     A_CHUNK_END, A_BAT_SEG0, A_BAT_INFO = range(13)
 F_RELU_IN, F_FORCE_SIMPLE = 1, 2
@@ -48,6 +48,9 @@ def load():
     lib.rgcn_abi_version.restype = C.c_int
     lib.rgcn_graph_create.restype = C.c_int
     lib.rgcn_graph_create.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i32, i32, i32, i32, vp, C.POINTER(vp)]
+    lib.rgcn_graph_create_part.restype = C.c_int
+    lib.rgcn_graph_create_part.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i32, i64, i64, i32, i32, i32, vp,
+                                           C.POINTER(vp)]
     lib.rgcn_graph_destroy.restype = None
     lib.rgcn_graph_destroy.argtypes = [vp]
     lib.rgcn_graph_query.restype = C.c_int
@@ -59,7 +62,7 @@ def load():
     lib.rgcn_layer_fwd.restype = C.c_int
     lib.rgcn_layer_fwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, i64, i32, u32, vp, i64, vp]
     lib.rgcn_layer_bwd.restype = C.c_int
-    lib.rgcn_layer_bwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, i64, i32, vp, i64, vp, vp, vp, u32, vp, i64, vp]
+    lib.rgcn_layer_bwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, i64, vp, i64, i32, vp, i64, vp, vp, vp, u32, vp, i64, vp]
     lib.rgcn_map_gather.restype = C.c_int
     lib.rgcn_map_gather.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i32, i64, i32, i32, vp, vp]
     lib.rgcn_kernel_launch_count.restype = i64

@@ -39,13 +39,19 @@ class _RGCNLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x: Tensor, weight: Tensor, root: Optional[Tensor], bias: Optional[Tensor],
-                graph: RGCNGraph, flags: int) -> Tensor:
+                graph: RGCNGraph, flags: int, comm=None) -> Tensor:
+        # comm (partitioned graphs only): object with all_gather_rows(t) -> [N, F] and
+        # all_reduce_sum_(list of tensors); x then holds the OWNED rows and is all-gathered here.
         lib = _lib.load()
         if not x.is_cuda:
             raise _lib.EngineError('RGCNConv: input is not a CUDA tensor; the B200 engine has no CPU path')
         if x.dtype != torch.float32 or weight.dtype != torch.float32:
             raise TypeError('RGCNConv: fp32 features and parameters expected')
-        if x.dim() != 2 or x.size(0) != graph.num_nodes:
+        if comm is not None:
+            if x.dim() != 2 or x.size(0) != graph.num_owned:
+                raise ValueError(f'RGCNConv (partitioned): x must hold the {graph.num_owned} owned rows')
+            x = comm.all_gather_rows(x.contiguous())
+        if x.dim() != 2 or x.size(0) < graph.num_nodes or (comm is None and x.size(0) != graph.num_nodes):
             raise ValueError(f'RGCNConv: x must be [num_nodes={graph.num_nodes}, in_channels]')
         x = x if x.stride(1) == 1 or x.size(1) == 1 else x.contiguous()
         weight = weight.contiguous()
@@ -55,7 +61,7 @@ class _RGCNLayerFn(torch.autograd.Function):
         r, fin_w, fout = weight.shape
         if fin_w != fin or r != graph.num_relations:
             raise ValueError('RGCNConv: weight shape does not match input / num_relations')
-        out = torch.empty((n, fout), dtype=torch.float32, device=x.device)
+        out = torch.empty((graph.num_owned, fout), dtype=torch.float32, device=x.device)
         ws_bytes = graph.workspace_bytes(fin, fout, False)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         with torch.cuda.device(x.device):
@@ -63,7 +69,7 @@ class _RGCNLayerFn(torch.autograd.Function):
                                     _ptr(bias_c), out.data_ptr(), out.stride(0), fout, flags, ws.data_ptr(), ws_bytes,
                                     _stream(x.device))
         _lib.check(rc, 'rgcn_layer_fwd')
-        ctx.graph, ctx.flags = graph, flags
+        ctx.graph, ctx.flags, ctx.comm = graph, flags, comm
         ctx.has_root, ctx.has_bias = root is not None, bias is not None
         ctx.save_for_backward(x, weight, root_c if root_c is not None else x.new_empty(0))
         return out
@@ -81,7 +87,9 @@ class _RGCNLayerFn(torch.autograd.Function):
         n, fin = x.shape
         fout = weight.size(2)
         dev = x.device
-        gx = torch.empty((n, fin), dtype=torch.float32, device=dev) if need_x else None
+        comm = ctx.comm
+        gout_all = comm.all_gather_rows(gout) if (comm is not None and need_x) else None
+        gx = torch.empty((graph.num_owned, fin), dtype=torch.float32, device=dev) if need_x else None
         gw = torch.empty_like(weight) if need_w else None
         groot = torch.empty((fin, fout), dtype=torch.float32, device=dev) if need_root else None
         gbias = torch.empty((fout,), dtype=torch.float32, device=dev) if need_bias else None
@@ -90,16 +98,22 @@ class _RGCNLayerFn(torch.autograd.Function):
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             with torch.cuda.device(dev):
                 rc = lib.rgcn_layer_bwd(graph.handle, x.data_ptr(), x.stride(0), fin, weight.data_ptr(), _ptr(root),
-                                        gout.data_ptr(), gout.stride(0), fout, _ptr(gx), fin, _ptr(gw), _ptr(groot),
-                                        _ptr(gbias), ctx.flags, ws.data_ptr(), ws_bytes, _stream(dev))
+                                        gout.data_ptr(), gout.stride(0), _ptr(gout_all),
+                                        gout_all.stride(0) if gout_all is not None else 0, fout, _ptr(gx), fin,
+                                        _ptr(gw), _ptr(groot), _ptr(gbias), ctx.flags, ws.data_ptr(), ws_bytes,
+                                        _stream(dev))
             _lib.check(rc, 'rgcn_layer_bwd')
-        return gx, gw, groot, gbias, None, None
+            if comm is not None:
+                comm.all_reduce_sum_([t for t in (gw, groot, gbias) if t is not None])
+        return gx, gw, groot, gbias, None, None, None
 
 
 def rgcn_layer(x: Tensor, weight: Tensor, root: Optional[Tensor], bias: Optional[Tensor], graph: RGCNGraph,
-               relu_in: bool = False, force_simple: bool = False) -> Tensor:
+               relu_in: bool = False, force_simple: bool = False, comm=None) -> Tensor:
     flags = (_lib.F_RELU_IN if relu_in else 0) | (_lib.F_FORCE_SIMPLE if force_simple else 0)
-    return _RGCNLayerFn.apply(x, weight, root, bias, graph, flags)
+    if comm is None and graph.num_owned != graph.num_nodes:
+        raise ValueError('rgcn_layer: a partitioned graph needs comm= (see rgcn_b200.partition)')
+    return _RGCNLayerFn.apply(x, weight, root, bias, graph, flags, comm)
 
 
 class RGCNConv(nn.Module):

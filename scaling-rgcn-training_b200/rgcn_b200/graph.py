@@ -23,7 +23,7 @@ def _env_int(name: str, default: int) -> int:
 
 class RGCNGraph:
     def __init__(self, edge_index: torch.Tensor, edge_type: torch.Tensor, num_nodes: int, num_relations: int,
-                 range_nodes: int = 0, split_threshold: int = 0, chunk_size: int = 0) -> None:
+                 range_nodes: int = 0, split_threshold: int = 0, chunk_size: int = 0, own_range=None) -> None:
         lib = _lib.load()
         if edge_index.dtype != torch.int64 or edge_type.dtype != torch.int64:
             raise TypeError('edge_index and edge_type must be int64 (as graphs/graph.py:65 builds them)')
@@ -35,6 +35,9 @@ class RGCNGraph:
                                    '(move the Data object with .to("cuda") first)')
         self.device = edge_index.device
         self.num_nodes, self.num_relations, self.num_edges = int(num_nodes), int(num_relations), edge_type.numel()
+        # own_range = (lo, hi): destination-partitioned graph of one rank; default = the whole graph
+        self.own_lo, self.own_hi = (0, self.num_nodes) if own_range is None else (int(own_range[0]), int(own_range[1]))
+        self.num_owned = self.own_hi - self.own_lo
         range_nodes = range_nodes or _env_int('RGCN_B200_RANGE_NODES', 0)
         split_threshold = split_threshold or _env_int('RGCN_B200_SPLIT', 0)
         chunk_size = chunk_size or _env_int('RGCN_B200_CHUNK', 0)
@@ -42,11 +45,12 @@ class RGCNGraph:
         src, dst = edge_index[0], edge_index[1]          # strided views are passed as they are
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
-            rc = lib.rgcn_graph_create(src.data_ptr(), src.stride(0) if src.numel() else 1,
-                                       dst.data_ptr(), dst.stride(0) if dst.numel() else 1,
-                                       edge_type.data_ptr(), edge_type.stride(0) if edge_type.numel() else 1,
-                                       self.num_edges, self.num_nodes, self.num_relations,
-                                       range_nodes, split_threshold, chunk_size, stream, C.byref(handle))
+            rc = lib.rgcn_graph_create_part(src.data_ptr(), src.stride(0) if src.numel() else 1,
+                                            dst.data_ptr(), dst.stride(0) if dst.numel() else 1,
+                                            edge_type.data_ptr(), edge_type.stride(0) if edge_type.numel() else 1,
+                                            self.num_edges, self.num_nodes, self.num_relations, self.own_lo,
+                                            self.own_hi, range_nodes, split_threshold, chunk_size, stream,
+                                            C.byref(handle))
         _lib.check(rc, 'rgcn_graph_create')
         self._h = handle
         self._finalizer = weakref.finalize(self, lib.rgcn_graph_destroy, handle)
@@ -62,8 +66,8 @@ class RGCNGraph:
 
     def export(self, array: int, brc: int = _lib.BRC_FWD) -> np.ndarray:
         n = {
-            _lib.A_PERM: self.num_edges + self.num_nodes, _lib.A_RAW_IDX: self.num_edges + self.num_nodes,
-            _lib.A_RAW_W: self.num_edges + self.num_nodes,
+            _lib.A_PERM: self.query(_lib.Q_NUM_ENTRIES0, brc), _lib.A_RAW_IDX: self.query(_lib.Q_NUM_ENTRIES0, brc),
+            _lib.A_RAW_W: self.query(_lib.Q_NUM_ENTRIES0, brc),
             _lib.A_SEG_PTR: self.query(_lib.Q_NUM_SEGMENTS, brc) + 1, _lib.A_SEG_PTR0: self.query(_lib.Q_NUM_SEGMENTS, brc) + 1,
             _lib.A_SEG_OWN: self.query(_lib.Q_NUM_SEGMENTS, brc), _lib.A_SEG_REL: self.query(_lib.Q_NUM_SEGMENTS, brc),
             _lib.A_E_IDX: self.query(_lib.Q_NUM_ENTRIES, brc), _lib.A_E_W: self.query(_lib.Q_NUM_ENTRIES, brc),

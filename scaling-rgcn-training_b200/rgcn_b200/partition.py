@@ -1,0 +1,163 @@
+"""Destination-partitioned full-graph R-GCN over the GPUs of one node (one process per GPU,
+``torch.distributed``; BASELINE.json configs 4/5).
+
+The reference is single-process (model/modelTrainer.py:16); this is the engine's multi-GPU mode
+for the same layer arithmetic.  Owner-computes in BOTH directions, so the only data-path
+collectives are all-gathers of the gather-side rows and one all-reduce of parameter gradients:
+
+  rank p owns nodes [p*chunk, (p+1)*chunk)  (chunk = ceil(N / P): equal ranges make the
+  all-gathered tensor directly indexable by global node id)
+  forward   x_all  = all_gather(x_owned)        ->  out_owned  (edges whose dst is owned)
+  backward  g_all  = all_gather(gout_owned)     ->  gx_owned   (edges whose src is owned)
+            dW, droot, dbias partial over owned dst  ->  all_reduce(sum)
+The embedding rows, activations and their gradients stay sharded; weights are replicated.
+"""
+from __future__ import annotations
+
+import json
+import os
+import statistics
+import time
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor, nn
+
+
+def plan_ranges(num_nodes: int, world: int) -> Tuple[int, List[Tuple[int, int]]]:
+    """Equal contiguous node ranges; trailing ranks may own fewer (never zero) nodes."""
+    if world < 1 or num_nodes < world:
+        raise ValueError('plan_ranges: need 1 <= world <= num_nodes')
+    chunk = -(-num_nodes // world)
+    ranges = [(min(p * chunk, num_nodes), min((p + 1) * chunk, num_nodes)) for p in range(world)]
+    if any(lo >= hi for lo, hi in ranges):
+        raise ValueError(f'plan_ranges: {world} ranks leave an empty range for {num_nodes} nodes')
+    return chunk, ranges
+
+
+class RowComm:
+    """The two collectives of the partitioned layer, over any torch.distributed backend
+    (nccl on the GPUs; gloo in the CPU tests of this host logic)."""
+
+    def __init__(self, num_nodes: int, group=None) -> None:
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.num_nodes = num_nodes
+        self.chunk, self.ranges = plan_ranges(num_nodes, self.world)
+        self.lo, self.hi = self.ranges[self.rank]
+        self.bytes_gathered = 0
+
+    def all_gather_rows(self, t: Tensor) -> Tensor:
+        """[n_owned, F] on every rank -> [world*chunk, F]; row i is node i for i < num_nodes."""
+        n_own, f = t.shape
+        if n_own != self.hi - self.lo:
+            raise ValueError('all_gather_rows: wrong number of owned rows')
+        if n_own != self.chunk:        # last rank(s): pad to the common chunk
+            pad = t.new_zeros((self.chunk, f))
+            pad[:n_own] = t
+            t = pad
+        out = t.new_empty((self.world * self.chunk, f))
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        self.bytes_gathered += out.numel() * out.element_size()
+        return out
+
+    def all_reduce_sum_(self, tensors: List[Tensor]) -> None:
+        """One flat all-reduce for the (small) parameter gradients."""
+        tensors = [t for t in tensors if t is not None]
+        if not tensors or self.world == 1:
+            return
+        flat = torch.cat([t.reshape(-1) for t in tensors])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        off = 0
+        for t in tensors:
+            t.copy_(flat[off:off + t.numel()].view_as(t))
+            off += t.numel()
+
+
+class PartitionedRGCN(nn.Module):
+    """2-layer R-GCN (Emb_Layers arithmetic, reference model/layers.py:20-25) on a partitioned
+    graph: sharded embedding rows, replicated layer weights, fused inter-layer ReLU."""
+
+    def __init__(self, graph, comm: RowComm, num_relations: int, hidden_l: int, num_labels: int, emb_dim: int,
+                 seed: int = 0) -> None:
+        super().__init__()
+        from .conv import RGCNConv
+        self.graph, self.comm = graph, comm
+        gen = torch.Generator().manual_seed(seed)          # same replicated weights on every rank
+        full = torch.randn(comm.num_nodes, emb_dim, generator=gen)
+        self.embedding = nn.Parameter(full[comm.lo:comm.hi].clone())
+        torch.manual_seed(seed)
+        self.rgcn1 = RGCNConv(emb_dim, hidden_l, num_relations)
+        self.rgcn2 = RGCNConv(hidden_l, num_labels, num_relations)
+        for conv in (self.rgcn1, self.rgcn2):
+            nn.init.kaiming_uniform_(conv.weight, mode='fan_in')
+
+    def forward(self) -> Tensor:
+        from .conv import rgcn_layer
+        c1, c2 = self.rgcn1, self.rgcn2
+        h = rgcn_layer(self.embedding, c1.weight, c1.root, c1.bias, self.graph, comm=self.comm)
+        return rgcn_layer(h, c2.weight, c2.root, c2.bias, self.graph, relu_in=True, comm=self.comm)
+
+
+def run_partitioned_bench(args, rank: int, world: int, device, metric: str, unit: str) -> None:
+    """bench.py --gpus N (N > 1): strong scaling of the AM-shape fwd+bwd step."""
+    from . import _lib
+    from .graph import RGCNGraph
+    from .synthetic import am_shape
+    import bench as B                                        # helpers of the single-GPU arm
+    ei, et, n, r = am_shape(scale=args.scale)                # every rank derives the same graph (seed 0)
+    e = et.numel()
+    comm = RowComm(n)
+    t0 = time.perf_counter()
+    ei_d, et_d = ei.to(device), et.to(device)
+    graph = RGCNGraph(ei_d, et_d, n, r, own_range=(comm.lo, comm.hi))
+    del ei_d, et_d
+    torch.cuda.synchronize(device)
+    setup_ms = (time.perf_counter() - t0) * 1e3
+    model = PartitionedRGCN(graph, comm, r, B.HIDDEN, B.CLASSES, B.EMB).to(device)
+    gen = torch.Generator().manual_seed(1)
+    gout = torch.randn(n, B.CLASSES, generator=gen)[comm.lo:comm.hi].to(device)
+    params = list(model.parameters())
+
+    def step():
+        for p in params:
+            p.grad = None
+        model().backward(gout)
+
+    sampler = B.ClockSampler(device.index)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize(device)
+    comm.bytes_gathered = 0
+    launches0 = _lib.launch_count()
+    if rank == 0:
+        sampler.start()
+    total_ms = B.time_steps(step, args.steps, 0, world, device)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.launch_count() - launches0
+    ms = total_ms / args.steps
+    value = e / (ms * 1e-3)
+    own_edges = torch.tensor([graph.query(_lib.Q_NUM_ENTRIES0, _lib.BRC_FWD) - graph.num_owned], device=device,
+                             dtype=torch.float64)
+    mx = own_edges.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        line = {
+            'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': 'am_shape_full_graph_rgcn_63_16_11_all_grads', 'scale': args.scale, 'nodes': n,
+                       'directed_edges': e, 'relations': r, 'partition': f'dst-partitioned x{world}, equal node ranges',
+                       'collectives': 'per layer: all_gather(x) fwd, all_gather(gout) bwd; one all_reduce of dW/droot/dbias',
+                       'all_gather_bytes_per_step_per_rank': comm.bytes_gathered // max(args.steps, 1),
+                       'max_rank_in_edges': int(mx.item()), 'mean_rank_in_edges': e / world,
+                       'graph_build_ms_once': setup_ms,
+                       'l2_policy': 'inputs larger than L2; no flush'},
+            'clocks': clocks, 'gpu_launches': int(launches),
+            'e2e': None, 'roofline': None, 'cpu_baseline': None,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

@@ -50,7 +50,7 @@ def test_graph_build_bit_exact(name, nr, t, ch):
     fwd, bwd = csr_oracle.build_graph(src, dst, rel, n, r, nr_eff, t_eff, ch_eff)
     _check_brc(g, _lib.BRC_FWD, fwd)
     _check_brc(g, _lib.BRC_BWD, bwd)
-    fwd_rel = csr_oracle.build_brc(dst, src, rel, n, r, n, t_eff, ch_eff, w_entry=fwd['w_entry'])
+    fwd_rel = csr_oracle.build_brc(dst, src, rel, n, r, n, t_eff, ch_eff, w_edge=csr_oracle.edge_weights(dst, rel, n))
     _check_brc(g, _lib.BRC_FWD_REL, fwd_rel)
 
 
@@ -330,5 +330,69 @@ def test_am_shape_tensor_and_generic_kernels_agree(am16):
         out = rgcn_layer(x, w, root, bias, g, force_simple=simple)
         out.backward(gout)
         res.append([out.detach().cpu()] + [t.grad.cpu() for t in (x, w, root, bias)])
-    for a, b in zip(*res):
-        assert rel_err(a, b) < TOL
+    # out and dL/dx at the parity tolerance; the parameter gradients of the GENERIC path are sums of
+    # ~1e5-1e6 fp32 atomic adds into single floats (round-off ~1e-5 of the result), so that side is
+    # the loose one here — the tensor path itself is checked against the oracle elsewhere
+    for i, (a, b) in enumerate(zip(*res)):
+        assert rel_err(a, b) < (TOL if i < 2 else 1e-4), i
+
+
+# ------------------------------------------------------------------ destination-partitioned graphs (1 GPU emulation)
+class _LocalComm:
+    """Stands in for rgcn_b200.partition.RowComm on one GPU: the 'other ranks' rows come from a
+    table filled by running the ranks one after another (no concurrent waiting kernels)."""
+
+    def __init__(self, chunk, world):
+        self.chunk, self.world, self.table, self.reduced = chunk, world, {}, []
+
+    def set_full(self, key_rows, full):
+        self.table[key_rows] = full
+
+    def all_gather_rows(self, t):
+        full = self.table[t.size(1)]
+        out = full.new_zeros((self.world * self.chunk, full.size(1)))
+        out[:full.size(0)] = full
+        return out
+
+    def all_reduce_sum_(self, tensors):
+        self.reduced.append([t.clone() for t in tensors])
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_partitioned_graph_matches_unpartitioned(world):
+    from rgcn_b200.partition import plan_ranges
+    ei, et, n, r = golden_graph('AIFB_bisim_k3')
+    eid, etd = ei.to(DEV), et.to(DEV)
+    chunk, ranges = plan_ranges(n, world)
+    torch.manual_seed(0)
+    x = torch.randn(n, 63, device=DEV)
+    w = ((torch.rand(r, 63, 16, device=DEV) - 0.5) * 0.3)
+    root = ((torch.rand(63, 16, device=DEV) - 0.5) * 0.3)
+    bias = torch.rand(16, device=DEV)
+    gout = torch.randn(n, 16, device=DEV)
+    g_full = RGCNGraph(eid, etd, n, r)
+    leaves = [t.clone().requires_grad_() for t in (x, w, root, bias)]
+    ref = rgcn_layer(*leaves, g_full)
+    ref.backward(gout)
+    outs, gxs, gws, groots, gbiases = [], [], 0, 0, 0
+    for lo, hi in ranges:
+        # bit-exact structure of this rank's partition
+        g = RGCNGraph(eid, etd, n, r, own_range=(lo, hi), range_nodes=64, split_threshold=8, chunk_size=4)
+        fwd, bwd = csr_oracle.build_graph(ei[0].numpy(), ei[1].numpy(), et.numpy(), n, r, 64, 8, 4, lo=lo, hi=hi)
+        _check_brc(g, _lib.BRC_FWD, fwd)
+        _check_brc(g, _lib.BRC_BWD, bwd)
+        comm = _LocalComm(chunk, world)
+        comm.set_full(63, x)
+        comm.set_full(16, gout)
+        lv = [x[lo:hi].clone().requires_grad_()] + [t.clone().requires_grad_() for t in (w, root, bias)]
+        out = rgcn_layer(*lv, g, comm=comm)
+        out.backward(gout[lo:hi])
+        outs.append(out.detach())
+        gxs.append(lv[0].grad)
+        gw, gr, gb = comm.reduced[0]
+        gws, groots, gbiases = gws + gw, groots + gr, gbiases + gb
+    assert rel_err(torch.cat(outs), ref.detach().cpu()) < TOL
+    assert rel_err(torch.cat(gxs), leaves[0].grad.cpu()) < TOL
+    assert rel_err(gws, leaves[1].grad.cpu()) < TOL
+    assert rel_err(groots, leaves[2].grad.cpu()) < TOL
+    assert rel_err(gbiases, leaves[3].grad.cpu()) < TOL

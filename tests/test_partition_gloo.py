@@ -1,0 +1,77 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: range planning, padded row
+all-gather with global indexing, flat gradient all-reduce, and the owner-computes algebra of the
+partitioned layer (local compute supplied by the ORACLE here — the engine itself has no CPU path)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ORACLE, PKG, REPO, golden_graph
+
+
+def test_plan_ranges():
+    from rgcn_b200.partition import plan_ranges
+    chunk, r = plan_ranges(10, 3)
+    assert chunk == 4 and r == [(0, 4), (4, 8), (8, 10)]
+    chunk, r = plan_ranges(1666764, 8)
+    assert r[0][0] == 0 and r[-1][1] == 1666764 and all(b - a <= chunk for a, b in r)
+    with pytest.raises(ValueError):
+        plan_ranges(5, 4)          # ceil(5/4)=2 -> 4th range empty
+    with pytest.raises(ValueError):
+        plan_ranges(3, 8)
+
+
+def _worker(rank, world, port, ret):
+    for p in (REPO, PKG, ORACLE):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import numpy as np
+        import rgcn_oracle
+        from rgcn_b200.partition import RowComm
+        sys.path.insert(0, os.path.join(REPO, 'tests'))
+        ei, et, n, r = golden_graph('MUTAG_bisim_k1')          # N=66 -> ranges of 33
+        n_odd = n - 1                                          # uneven last range exercises the padding
+        comm = RowComm(n_odd)
+        lo, hi = comm.lo, comm.hi
+        torch.manual_seed(0)
+        keep = (ei[0] < n_odd) & (ei[1] < n_odd)
+        ei, et = ei[:, keep], et[keep]
+        x = torch.randn(n_odd, 5)
+        w = torch.randn(r, 5, 3) * 0.2
+        root = torch.randn(5, 3) * 0.2
+        bias = torch.randn(3) * 0.1
+        gout = torch.randn(n_odd, 3)
+        # all-gather: rows land at their global index
+        x_all = comm.all_gather_rows(x[lo:hi].clone())
+        assert x_all.shape == (comm.world * comm.chunk, 5) and torch.equal(x_all[:n_odd], x)
+        # owner-computes forward: every rank needs only the edges whose dst it owns
+        ref = rgcn_oracle.rgcn_forward(x, ei, et, w, root, bias)
+        mine_dst = (ei[1] >= lo) & (ei[1] < hi)
+        out_full = rgcn_oracle.rgcn_forward(x_all[:n_odd], ei[:, mine_dst], et[mine_dst], w, root, bias)
+        assert torch.allclose(out_full[lo:hi], ref[lo:hi], atol=1e-6)
+        # parameter gradients: partial sums over owned dst, one flat all-reduce
+        leaves = [t.clone().requires_grad_() for t in (x, w, root, bias)]
+        rgcn_oracle.rgcn_forward(*[leaves[0], ei, et] + leaves[1:]).backward(gout)
+        part = [t.clone().requires_grad_() for t in (w, root, bias)]
+        o = rgcn_oracle.rgcn_forward(x, ei[:, mine_dst], et[mine_dst], *part)
+        o[lo:hi].backward(gout[lo:hi])
+        grads = [p.grad.clone() for p in part]
+        comm.all_reduce_sum_(grads)
+        for a, b in zip(grads, leaves[1:]):
+            assert torch.allclose(a, b.grad, atol=1e-5), 'all-reduced parameter gradients'
+        ret[rank] = 'ok'
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_comm_world2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, 29611, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: 'ok', 1: 'ok'}
