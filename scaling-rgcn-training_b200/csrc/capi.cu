@@ -69,7 +69,9 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     cudaStream_t st = (cudaStream_t)stream;
     const bool relu = (flags & RGCN_F_RELU_IN) != 0;
     const int kp = pad_dim(fin), np = pad_dim(fout);
-    if ((flags & RGCN_F_FORCE_SIMPLE) || !kp || !np) {
+    // tile kernels address gathered rows with 32-bit element offsets
+    const bool big = (uint64_t)g->N * (uint64_t)ldx >= (1ull << 32);
+    if ((flags & RGCN_F_FORCE_SIMPLE) || !kp || !np || big) {
         RGCN_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)fout * 4, (size_t)g->n_own, st));
         SimplePass p{};
         p.brc = &g->brc[RGCN_BRC_FWD];
@@ -127,7 +129,9 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     cudaStream_t st = (cudaStream_t)stream;
     const bool relu = (flags & RGCN_F_RELU_IN) != 0;
     const int kp = pad_dim(fin), np = pad_dim(fout);
-    const bool simple = (flags & RGCN_F_FORCE_SIMPLE) || !kp || !np;
+    const bool big = (uint64_t)g->N * (uint64_t)ldx >= (1ull << 32) ||
+                     (uint64_t)g->N * (uint64_t)(gout_gather ? ldgg : ldg) >= (1ull << 32);
+    const bool simple = (flags & RGCN_F_FORCE_SIMPLE) || !kp || !np || big;
     const bool need_w = gweight || groot || gbias;
     int rc;
     if (gweight) RGCN_CUDA(cudaMemsetAsync(gweight, 0, (size_t)g->R * fin * fout * 4, st));

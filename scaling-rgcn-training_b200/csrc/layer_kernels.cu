@@ -74,51 +74,50 @@ __device__ __forceinline__ void red_add_v4(float* p, float x, float y, float z, 
 // so the inner loops carry only the two per-lane column predicates.
 constexpr int RING = 32;   // smem ring of finished segment rows per warp (>= 16 + 8)
 
-struct LanePtrs {   // per-lane base pointers (lane's column folded in) and column predicates
-    const float* f0;
-    const float* a0;
+struct LanePtrs {   // what a lane needs to address its columns of a gathered row
+    const float* feat;   // feature matrix (row r at feat + r * ldf)
+    const float* aux;    // chunk rows (row r - n_rows at aux + (r - n_rows) * KP)
     uint32_t ldf, n_rows;
-    bool c0, c1;
+    uint32_t col;        // this lane's first column (clamped to the logical width)
+    bool c1;             // lane also owns column lane + 32
 };
 template <int KP>
 __device__ __forceinline__ LanePtrs lane_ptrs(const float* feat, int64_t ldf, int kin, const float* aux,
                                               int64_t n_rows, int lane) {
     LanePtrs q;
-    q.f0 = feat + lane;
-    q.a0 = (aux ? aux : feat) + lane;
+    q.feat = feat;
+    q.aux = aux ? aux : feat;
     q.ldf = (uint32_t)ldf;
     q.n_rows = (uint32_t)n_rows;
-    q.c0 = lane < kin;
-    q.c1 = (KP > 32) && (lane + 32 < kin);
+    q.col = (uint32_t)min(lane, kin - 1);   // lanes past the width re-read the last column; their
+    q.c1 = (KP > 32) && (lane + 32 < kin);  // sums land in pad columns that meet zero rows of B
     return q;
 }
 
 template <int KP, bool RELU>
 struct RowGroup {
-    float v0[GATHER_U], v1[GATHER_U], w[GATHER_U];
+    float v0[GATHER_U], v1[GATHER_U];
     uint32_t raw[GATHER_U];
-    // CH: the block contains chunk rows (index >= n_rows) -> per-entry select; rare
+    // CH: the block contains chunk rows (index >= n_rows) -> per-entry select; rare.
+    // Element offsets are 32-bit (the host checks rows * ld < 2^32): one IMAD + one LEA pair per
+    // entry, shared by both column halves (the second half is an immediate +128 B).
     template <bool CH>
-    __device__ __forceinline__ void load(uint32_t blk_idx, float blk_w, int j0, const LanePtrs& q) {
+    __device__ __forceinline__ void load(uint32_t blk_idx, int j0, const LanePtrs& q) {
 #pragma unroll
-        for (int u = 0; u < GATHER_U; ++u) {
-            raw[u] = __shfl_sync(FULL, blk_idx, j0 + u);
-            w[u] = __shfl_sync(FULL, blk_w, j0 + u);
-        }
-        const float* p0[GATHER_U];
+        for (int u = 0; u < GATHER_U; ++u) raw[u] = __shfl_sync(FULL, blk_idx, j0 + u);
+        const float* p[GATHER_U];
 #pragma unroll
         for (int u = 0; u < GATHER_U; ++u) {
             const uint32_t row = raw[u] & IDX_MASK;
-            if (CH && row >= q.n_rows) p0[u] = q.a0 + (uint64_t)(row - q.n_rows) * KP;
-            else p0[u] = q.f0 + (uint64_t)row * q.ldf;
+            if (CH && row >= q.n_rows) p[u] = q.aux + ((row - q.n_rows) * (uint32_t)KP + q.col);
+            else p[u] = q.feat + (row * q.ldf + q.col);
         }
 #pragma unroll
         for (int u = 0; u < GATHER_U; ++u) {
-            v0[u] = 0.f;
+            v0[u] = __ldg(p[u]);
             v1[u] = 0.f;
-            if (q.c0) v0[u] = __ldg(p0[u]);
             if (KP > 32) {
-                if (q.c1) v1[u] = __ldg(p0[u] + 32);
+                if (q.c1) v1[u] = __ldg(p[u] + 32);
             }
         }
         if (RELU) {
@@ -131,9 +130,9 @@ struct RowGroup {
             }
         }
     }
-    __device__ __forceinline__ void load_any(uint32_t blk_idx, float blk_w, int j0, const LanePtrs& q, bool has_chunk) {
-        if (has_chunk) load<true>(blk_idx, blk_w, j0, q);
-        else load<false>(blk_idx, blk_w, j0, q);
+    __device__ __forceinline__ void load_any(uint32_t blk_idx, int j0, const LanePtrs& q, bool has_chunk) {
+        if (has_chunk) load<true>(blk_idx, j0, q);
+        else load<false>(blk_idx, j0, q);
     }
 };
 
@@ -169,14 +168,17 @@ struct Stream {
     }
     // branch-free: the running sums are stored on every entry and kept or cleared by the LAST flag
     template <bool RELU>
-    __device__ __forceinline__ void consume(const RowGroup<KP, RELU>& rg, float* H, int lane) {
+    __device__ __forceinline__ void consume(const RowGroup<KP, RELU>& rg, float wreg, int j0, float* Hlane, int lane) {
+        float w[GATHER_U];
+#pragma unroll
+        for (int u = 0; u < GATHER_U; ++u) w[u] = __shfl_sync(FULL, wreg, j0 + u);
 #pragma unroll
         for (int u = 0; u < GATHER_U; ++u) {
-            acc0 = fmaf(rg.w[u], rg.v0[u], acc0);
-            acc1 = fmaf(rg.w[u], rg.v1[u], acc1);
-            float* hr = H + (ring_w & (RING - 1)) * LDH;
-            if (KP >= 32 || lane < KP) hr[lane] = acc0;
-            if (KP > 32) hr[lane + 32] = acc1;
+            acc0 = fmaf(w[u], rg.v0[u], acc0);
+            acc1 = fmaf(w[u], rg.v1[u], acc1);
+            float* hr = Hlane + (ring_w & (RING - 1)) * LDH;   // Hlane = ring base + lane
+            if (KP >= 32 || lane < KP) hr[0] = acc0;
+            if (KP > 32) hr[32] = acc1;
             const uint32_t last = rg.raw[u] >> 31;
             ring_w += (int)last;
             acc0 = last ? 0.f : acc0;
@@ -210,16 +212,18 @@ __global__ void __launch_bounds__(256) k_chunk_sum(const int32_t* __restrict__ r
         const int m = min(32, e1 - pos);
         for (int j0 = 0; j0 < m; j0 += GATHER_U) {
             RowGroup<KP, RELU> rg;
-            rg.template load<false>(bi, bw, j0, q);
+            rg.template load<false>(bi, j0, q);
 #pragma unroll
             for (int u = 0; u < GATHER_U; ++u) {
-                acc0 = fmaf(rg.w[u], rg.v0[u], acc0);
-                acc1 = fmaf(rg.w[u], rg.v1[u], acc1);
+                const float w = __shfl_sync(FULL, bw, j0 + u);
+                acc0 = fmaf(w, rg.v0[u], acc0);
+                acc1 = fmaf(w, rg.v1[u], acc1);
             }
         }
     }
-    if (lane < KP) aux[(int64_t)c * KP + lane] = acc0;
-    if (KP > 32) aux[(int64_t)c * KP + lane + 32] = acc1;
+    if (lane < min(KP, kin)) aux[(int64_t)c * KP + lane] = acc0;   // pad columns stay zero
+    else if (lane < KP) aux[(int64_t)c * KP + lane] = 0.f;
+    if (KP > 32) aux[(int64_t)c * KP + lane + 32] = acc1;          // v1 is zero past the width
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -292,8 +296,9 @@ struct TileArgs {
 };
 
 template <int KT, int NT, bool RELU, bool BREG>
-__global__ void __launch_bounds__(TILE_WARPS * 32, BREG ? 1 : (NT <= 2 ? 3 : 2)) k_tile(const TileArgs a) {
+__global__ void __launch_bounds__(TILE_WARPS * 32, BREG ? 1 : ((KT == 8 || NT > 2) ? 2 : 3)) k_tile(const TileArgs a) {
     constexpr int KP = KT * 8, LDH = KP + 4;
+    constexpr bool PIPE = (KT == 8);   // wide rows: double-buffered groups (more bytes in flight per warp)
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* H = smem + warp * (RING * LDH);
@@ -321,93 +326,128 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, BREG ? 1 : (NT <= 2 ? 3 : 2))
         int ring_base = 0;
         Stream<KP, LDH> sm;
         sm.start(e_idx, e_w, E0, E1, lane);
-        for (int pos = E0; pos < E1; pos += 32) {
-            sm.next_block(e_idx, e_w, pos, E1, lane, q.n_rows);
-            const int m = min(32, E1 - pos);
-            for (int j0 = 0; j0 < m; j0 += GATHER_U) {
-                RowGroup<KP, RELU> rg;
-                rg.load_any(sm.blk_idx, sm.blk_w, j0, q, sm.has_chunk);
-                sm.consume(rg, H, lane);
-                // drain every batch whose rows are all in the ring
-                while (b < b_end && sm.ring_w - ring_base >= nseg) {
-                    __syncwarp();
-                    const float4* wf = a.wfrag + (int64_t)rel * (KT * NT * 32) + lane;
-                    if constexpr (BREG) {
-                        if (rel != cur_rel) {
+        sm.next_block(e_idx, e_w, E0, E1, lane, q.n_rows);
+        // drain every batch whose rows are all in the ring
+        auto drain = [&]() {
+        while (b < b_end && sm.ring_w - ring_base >= nseg) {
+            __syncwarp();
+            const float4* wf = a.wfrag + (int64_t)rel * (KT * NT * 32) + lane;
+            if constexpr (BREG) {
+                if (rel != cur_rel) {
 #pragma unroll
-                            for (int i = 0; i < KT * NT; ++i) bfrag[i] = __ldg(wf + i * 32);
-                            cur_rel = rel;
-                        }
+                    for (int i = 0; i < KT * NT; ++i) bfrag[i] = __ldg(wf + i * 32);
+                    cur_rel = rel;
+                }
+            }
+            const float* h_lo = H + ((ring_base + g) & (RING - 1)) * LDH;
+            const float* h_hi = H + ((ring_base + g + 8) & (RING - 1)) * LDH;
+            float d[NT][4];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) d[n][0] = d[n][1] = d[n][2] = d[n][3] = 0.f;
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) {
+                uint32_t ah[4], al[4];
+                split_fast(h_lo[8 * kt + t], ah[0], al[0]);
+                split_fast(h_hi[8 * kt + t], ah[1], al[1]);
+                split_fast(h_lo[8 * kt + t + 4], ah[2], al[2]);
+                split_fast(h_hi[8 * kt + t + 4], ah[3], al[3]);
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    float4 bf;
+                    if constexpr (BREG) bf = bfrag[kt * NT + n];
+                    else bf = __ldg(wf + (kt * NT + n) * 32);
+                    const uint32_t bh0 = __float_as_uint(bf.x), bh1 = __float_as_uint(bf.y);
+                    const uint32_t bl0 = __float_as_uint(bf.z), bl1 = __float_as_uint(bf.w);
+                    mma_tf32(d[n], al[0], al[1], al[2], al[3], bh0, bh1);
+                    mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+                    mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+                }
+            }
+            if (rel == a.self_rel && a.bias != nullptr) {
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    const int col = 8 * n + 2 * t;
+                    const float bx = col < a.nbias ? a.bias[col] : 0.f;
+                    const float by = col + 1 < a.nbias ? a.bias[col + 1] : 0.f;
+                    d[n][0] += bx;
+                    d[n][1] += by;
+                    d[n][2] += bx;
+                    d[n][3] += by;
+                }
+            }
+            // rows past nseg belong to later batches: their owners read -1 and are skipped
+            const int own_lo = __shfl_sync(FULL, my_own, g), own_hi = __shfl_sync(FULL, my_own, g + 8);
+            const bool odd = (t & 1) != 0;
+#pragma unroll
+            for (int j = 0; j < NT / 2; ++j) {
+                const int col = odd ? 8 * (2 * j + 1) + 2 * (t - 1) : 8 * (2 * j) + 2 * t;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {   // h = 0: row g ; h = 1: row g + 8
+                    const float e0 = d[2 * j][2 * h], e1 = d[2 * j][2 * h + 1];
+                    const float f0 = d[2 * j + 1][2 * h], f1 = d[2 * j + 1][2 * h + 1];
+                    const float rx = __shfl_xor_sync(FULL, odd ? e0 : f0, 1);
+                    const float ry = __shfl_xor_sync(FULL, odd ? e1 : f1, 1);
+                    const int own = h ? own_hi : own_lo;
+                    if (own >= 0 && col < a.nout) {
+                        float* p = a.out + (int64_t)own * a.ldo + col;
+                        if (odd) red_add_v4(p, rx, ry, f0, f1);
+                        else red_add_v4(p, e0, e1, rx, ry);
                     }
-                    const float* h_lo = H + ((ring_base + g) & (RING - 1)) * LDH;
-                    const float* h_hi = H + ((ring_base + g + 8) & (RING - 1)) * LDH;
-                    float d[NT][4];
-#pragma unroll
-                    for (int n = 0; n < NT; ++n) d[n][0] = d[n][1] = d[n][2] = d[n][3] = 0.f;
-#pragma unroll
-                    for (int kt = 0; kt < KT; ++kt) {
-                        uint32_t ah[4], al[4];
-                        split_fast(h_lo[8 * kt + t], ah[0], al[0]);
-                        split_fast(h_hi[8 * kt + t], ah[1], al[1]);
-                        split_fast(h_lo[8 * kt + t + 4], ah[2], al[2]);
-                        split_fast(h_hi[8 * kt + t + 4], ah[3], al[3]);
-#pragma unroll
-                        for (int n = 0; n < NT; ++n) {
-                            float4 bf;
-                            if constexpr (BREG) bf = bfrag[kt * NT + n];
-                            else bf = __ldg(wf + (kt * NT + n) * 32);
-                            const uint32_t bh0 = __float_as_uint(bf.x), bh1 = __float_as_uint(bf.y);
-                            const uint32_t bl0 = __float_as_uint(bf.z), bl1 = __float_as_uint(bf.w);
-                            mma_tf32(d[n], al[0], al[1], al[2], al[3], bh0, bh1);
-                            mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
-                            mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
-                        }
+                }
+            }
+            __syncwarp();
+            // next batch: metadata was prefetched one batch ago
+            ring_base += nseg;
+            seg0 += nseg;
+            ++b;
+            info = info_n;
+            nseg = info & 0xff;
+            rel = info >> 8;
+            my_own = own_n;
+            if (b < b_end) {
+                info_n = b + 1 < b_end ? a.bat_info[b + 1] : 0;
+                own_n = (b + 1 < b_end && lane < (info_n & 0xff)) ? a.seg_own[seg0 + nseg + lane] : -1;
+            }
+        }
+        };
+        // Software pipeline over groups of 8 entries: the loads of group k+1 are in flight while
+        // group k is accumulated and its finished batches go through the tensor pipe.
+        if constexpr (PIPE) {
+            RowGroup<KP, RELU> A, B;
+            A.load_any(sm.blk_idx, 0, q, sm.has_chunk);
+            for (int pos = E0; pos < E1; pos += 32) {
+                const int m = min(32, E1 - pos);
+    #pragma unroll 1
+                for (int h = 0; h < 2; ++h) {   // two (A, B) group pairs per 32-entry block
+                    const int ja = 16 * h, jb = ja + 8;
+                    if (jb < m) B.load_any(sm.blk_idx, jb, q, sm.has_chunk);
+                    if (ja < m) {
+                        sm.consume(A, sm.blk_w, ja, H + lane, lane);
+                        drain();
                     }
-                    if (rel == a.self_rel && a.bias != nullptr) {
-#pragma unroll
-                        for (int n = 0; n < NT; ++n) {
-                            const int col = 8 * n + 2 * t;
-                            const float bx = col < a.nbias ? a.bias[col] : 0.f;
-                            const float by = col + 1 < a.nbias ? a.bias[col + 1] : 0.f;
-                            d[n][0] += bx;
-                            d[n][1] += by;
-                            d[n][2] += bx;
-                            d[n][3] += by;
-                        }
+                    const float w_cur = sm.blk_w;
+                    if (h == 0) {
+                        if (16 < m) A.load_any(sm.blk_idx, 16, q, sm.has_chunk);
+                    } else if (pos + 32 < E1) {
+                        sm.next_block(e_idx, e_w, pos + 32, E1, lane, q.n_rows);
+                        A.load_any(sm.blk_idx, 0, q, sm.has_chunk);
                     }
-                    // rows past nseg belong to later batches: their owners read -1 and are skipped
-                    const int own_lo = __shfl_sync(FULL, my_own, g), own_hi = __shfl_sync(FULL, my_own, g + 8);
-                    const bool odd = (t & 1) != 0;
-#pragma unroll
-                    for (int j = 0; j < NT / 2; ++j) {
-                        const int col = odd ? 8 * (2 * j + 1) + 2 * (t - 1) : 8 * (2 * j) + 2 * t;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {   // h = 0: row g ; h = 1: row g + 8
-                            const float e0 = d[2 * j][2 * h], e1 = d[2 * j][2 * h + 1];
-                            const float f0 = d[2 * j + 1][2 * h], f1 = d[2 * j + 1][2 * h + 1];
-                            const float rx = __shfl_xor_sync(FULL, odd ? e0 : f0, 1);
-                            const float ry = __shfl_xor_sync(FULL, odd ? e1 : f1, 1);
-                            const int own = h ? own_hi : own_lo;
-                            if (own >= 0 && col < a.nout) {
-                                float* p = a.out + (int64_t)own * a.ldo + col;
-                                if (odd) red_add_v4(p, rx, ry, f0, f1);
-                                else red_add_v4(p, e0, e1, rx, ry);
-                            }
-                        }
+                    if (jb < m) {
+                        sm.consume(B, w_cur, jb, H + lane, lane);
+                        drain();
                     }
-                    __syncwarp();
-                    // next batch: metadata was prefetched one batch ago
-                    ring_base += nseg;
-                    seg0 += nseg;
-                    ++b;
-                    info = info_n;
-                    nseg = info & 0xff;
-                    rel = info >> 8;
-                    my_own = own_n;
-                    if (b < b_end) {
-                        info_n = b + 1 < b_end ? a.bat_info[b + 1] : 0;
-                        own_n = (b + 1 < b_end && lane < (info_n & 0xff)) ? a.seg_own[seg0 + nseg + lane] : -1;
-                    }
+                }
+            }
+
+        } else {
+            for (int pos = E0; pos < E1; pos += 32) {
+                if (pos > E0) sm.next_block(e_idx, e_w, pos, E1, lane, q.n_rows);
+                const int m = min(32, E1 - pos);
+                for (int j0 = 0; j0 < m; j0 += GATHER_U) {
+                    RowGroup<KP, RELU> rg;
+                    rg.load_any(sm.blk_idx, j0, q, sm.has_chunk);
+                    sm.consume(rg, sm.blk_w, j0, H + lane, lane);
+                    drain();
                 }
             }
         }
@@ -524,79 +564,83 @@ __global__ void __launch_bounds__(WG_WARPS * 32, (KT * NT <= 16) ? 4 : ((KT * NT
         int ring_base = 0;
         Stream<KP, LDH> sm;
         sm.start(e_idx, e_w, E0, E1, lane);
-        for (int pos = E0; pos < E1; pos += 32) {
-            sm.next_block(e_idx, e_w, pos, E1, lane, q.n_rows);
-            const int m_blk = min(32, E1 - pos);
-            for (int j0 = 0; j0 < m_blk; j0 += GATHER_U) {
-                RowGroup<KP, RELU> rg;
-                rg.load_any(sm.blk_idx, sm.blk_w, j0, q, sm.has_chunk);
-                sm.consume(rg, H, lane);
-                while (b < b_end && sm.ring_w - ring_base >= nseg) {
-                    if (rel != cur_rel) {
-                        if (cur_rel >= 0) flush(cur_rel);
-                        cur_rel = rel;
-                    }
-                    const bool wanted =
-                        rel == a.self_rel ? (a.groot != nullptr || a.gbias != nullptr) : a.gweight != nullptr;
-                    cp_async_wait<1>();   // this batch's rows have landed; the next batch's may still fly
-                    __syncwarp();
-                    const float* G = Gbuf + par * (BS * LDG);
-                    if (wanted) {
-                        if (rel == a.self_rel) {
+        sm.next_block(e_idx, e_w, E0, E1, lane, q.n_rows);
+        auto drain = [&]() {
+        while (b < b_end && sm.ring_w - ring_base >= nseg) {
+            if (rel != cur_rel) {
+                if (cur_rel >= 0) flush(cur_rel);
+                cur_rel = rel;
+            }
+            const bool wanted =
+                rel == a.self_rel ? (a.groot != nullptr || a.gbias != nullptr) : a.gweight != nullptr;
+            cp_async_wait<1>();   // this batch's rows have landed; the next batch's may still fly
+            __syncwarp();
+            const float* G = Gbuf + par * (BS * LDG);
+            if (wanted) {
+                if (rel == a.self_rel) {
 #pragma unroll
-                            for (int i = 0; i < (NP + 31) / 32; ++i) {
-                                const int c = lane + 32 * i;
-                                if (c < NP) {
-                                    float sacc = 0.f;
+                    for (int i = 0; i < (NP + 31) / 32; ++i) {
+                        const int c = lane + 32 * i;
+                        if (c < NP) {
+                            float sacc = 0.f;
 #pragma unroll
-                                    for (int r = 0; r < BS; ++r) sacc += G[r * LDG + c];
-                                    bsum[i] += sacc;
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            uint32_t bh[NT][2], bl[NT][2];
-#pragma unroll
-                            for (int n = 0; n < NT; ++n) {
-                                split_fast(G[(8 * ks + t) * LDG + 8 * n + g], bh[n][0], bl[n][0]);
-                                split_fast(G[(8 * ks + t + 4) * LDG + 8 * n + g], bh[n][1], bl[n][1]);
-                            }
-                            const float* r0 = H + ((ring_base + 8 * ks + t) & (RING - 1)) * LDH;
-                            const float* r1 = H + ((ring_base + 8 * ks + t + 4) & (RING - 1)) * LDH;
-#pragma unroll
-                            for (int m = 0; m < MT; ++m) {
-                                uint32_t ah[4], al[4];
-                                split_fast(r0[16 * m + g], ah[0], al[0]);
-                                split_fast(r0[16 * m + g + 8], ah[1], al[1]);
-                                split_fast(r1[16 * m + g], ah[2], al[2]);
-                                split_fast(r1[16 * m + g + 8], ah[3], al[3]);
-#pragma unroll
-                                for (int n = 0; n < NT; ++n) {
-                                    mma_tf32(d[m][n], al[0], al[1], al[2], al[3], bh[n][0], bh[n][1]);
-                                    mma_tf32(d[m][n], ah[0], ah[1], ah[2], ah[3], bl[n][0], bl[n][1]);
-                                    mma_tf32(d[m][n], ah[0], ah[1], ah[2], ah[3], bh[n][0], bh[n][1]);
-                                }
-                            }
+                            for (int r = 0; r < BS; ++r) sacc += G[r * LDG + c];
+                            bsum[i] += sacc;
                         }
                     }
-                    __syncwarp();
-                    ring_base += nseg;
-                    seg0 += nseg;
-                    ++b;
-                    info = info_n;
-                    nseg = info & 0xff;
-                    rel = info >> 8;
-                    my_own = own_n;
-                    info_n = 0;
-                    own_n = -1;
-                    if (b + 1 < b_end) {
-                        info_n = a.bat_info[b + 1];
-                        own_n = lane < (info_n & 0xff) ? a.seg_own[seg0 + nseg + lane] : -1;
-                    }
-                    fetch_g(Gbuf + par * (BS * LDG), own_n);   // refill the buffer just consumed (zeros past the end)
-                    par ^= 1;
                 }
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) {
+                        split_fast(G[(8 * ks + t) * LDG + 8 * n + g], bh[n][0], bl[n][0]);
+                        split_fast(G[(8 * ks + t + 4) * LDG + 8 * n + g], bh[n][1], bl[n][1]);
+                    }
+                    const float* r0 = H + ((ring_base + 8 * ks + t) & (RING - 1)) * LDH;
+                    const float* r1 = H + ((ring_base + 8 * ks + t + 4) & (RING - 1)) * LDH;
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        uint32_t ah[4], al[4];
+                        split_fast(r0[16 * m + g], ah[0], al[0]);
+                        split_fast(r0[16 * m + g + 8], ah[1], al[1]);
+                        split_fast(r1[16 * m + g], ah[2], al[2]);
+                        split_fast(r1[16 * m + g + 8], ah[3], al[3]);
+#pragma unroll
+                        for (int n = 0; n < NT; ++n) {
+                            mma_tf32(d[m][n], al[0], al[1], al[2], al[3], bh[n][0], bh[n][1]);
+                            mma_tf32(d[m][n], ah[0], ah[1], ah[2], ah[3], bl[n][0], bl[n][1]);
+                            mma_tf32(d[m][n], ah[0], ah[1], ah[2], ah[3], bh[n][0], bh[n][1]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            ring_base += nseg;
+            seg0 += nseg;
+            ++b;
+            info = info_n;
+            nseg = info & 0xff;
+            rel = info >> 8;
+            my_own = own_n;
+            info_n = 0;
+            own_n = -1;
+            if (b + 1 < b_end) {
+                info_n = a.bat_info[b + 1];
+                own_n = lane < (info_n & 0xff) ? a.seg_own[seg0 + nseg + lane] : -1;
+            }
+            fetch_g(Gbuf + par * (BS * LDG), own_n);   // refill the buffer just consumed (zeros past the end)
+            par ^= 1;
+        }
+        };
+        for (int pos = E0; pos < E1; pos += 32) {
+            if (pos > E0) sm.next_block(e_idx, e_w, pos, E1, lane, q.n_rows);
+            const int m = min(32, E1 - pos);
+            for (int j0 = 0; j0 < m; j0 += GATHER_U) {
+                RowGroup<KP, RELU> rg;
+                rg.load_any(sm.blk_idx, j0, q, sm.has_chunk);
+                sm.consume(rg, sm.blk_w, j0, H + lane, lane);
+                drain();
             }
         }
     }
@@ -610,13 +654,17 @@ __global__ void __launch_bounds__(WG_WARPS * 32, (KT * NT <= 16) ? 4 : ((KT * NT
     }
 }
 
-__global__ void k_copy_cols(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int64_t n,
-                            int cols) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n * cols) return;
-    const int64_t r = i / cols;
-    const int c = (int)(i % cols);
-    dst[r * ldd + c] = src[r * lds + c];
+// dst[r][0:cols] = src[r][0:cols]  (one warp per row: both sides coalesced)
+__global__ void __launch_bounds__(256) k_copy_cols(const float* __restrict__ src, int64_t lds, float* __restrict__ dst,
+                                                   int64_t ldd, int64_t n, int cols) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * 8;
+    for (int64_t r = wid; r < n; r += nw) {
+        const float* sp = src + r * lds;
+        float* dp = dst + r * ldd;
+        for (int c = lane; c < cols; c += 32) dp[c] = __ldg(sp + c);
+    }
 }
 
 __global__ void k_relu_mask(float* __restrict__ gr, int64_t ldg, const float* __restrict__ pre, int64_t ldp, int64_t n,
@@ -834,7 +882,7 @@ int launch_copy_cols(const float* src, int64_t lds, float* dst, int64_t ldd, int
     if (total == 0) return 0;
     ProfScope prof(TAG_COPY, cols, 0, st);
     note_launch(1);
-    k_copy_cols<<<(int)((total + 255) / 256), 256, 0, st>>>(src, lds, dst, ldd, n, cols);
+    k_copy_cols<<<(int)std::min<int64_t>((n + 7) / 8, 148 * 16), 256, 0, st>>>(src, lds, dst, ldd, n, cols);
     RGCN_CUDA(cudaGetLastError());
     return 0;
 }
