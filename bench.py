@@ -57,6 +57,16 @@ def pass_bytes(n, e, fin, fout):
     }
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    path = os.path.join(REPO, 'profiles', 'ncu_traffic.json')
+    try:
+        return json.load(open(path)).get(kernel)
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(REPO, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -277,8 +287,9 @@ def run_engine(args):
     if dom is not None:
         avg_ms = statistics.mean(agg[dom])
         ach = pb[dom] / (avg_ms * 1e-3) / 1e9
-        roofline = {'bound': 'hbm', 'kernel': f'{dom[0]}_{dom[1]}x{dom[2]}', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-                    'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+        kname = f'{dom[0]}_{dom[1]}x{dom[2]}'
+        roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                    'frac': ach / peak, 'traffic': ncu_traffic(kname) if args.scale == 1.0 else None, 'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': pb[dom], 'avg_launch_ms': avg_ms,
                     'share_of_step': tot[dom] / args.steps / ms_per_step}
     f1, b1 = algorithmic_bytes(n, e, EMB, HIDDEN)
@@ -336,7 +347,7 @@ def run_engine(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', choices=['engine', 'reference'], default='engine')
     ap.add_argument('--scale', type=float, default=1.0, help='AM-shape scale (1.0 = the BASELINE.json config)')

@@ -21,3 +21,10 @@ for v in "$@"; do
     nr1k) run nr1k RGCN_B200_RANGE_NODES=1024;;
   esac
 done
+for v in "$@"; do
+  case $v in
+    dbg1) run dbg1 RGCN_B200_DBG=1;;
+    dbg2) run dbg2 RGCN_B200_DBG=2;;
+    dbg3) run dbg3 RGCN_B200_DBG=3;;
+  esac
+done
