@@ -51,7 +51,8 @@ enum {
     RGCN_Q_NUM_NODES = 0, RGCN_Q_NUM_EDGES = 1, RGCN_Q_NUM_RELATIONS = 2,
     RGCN_Q_NUM_SEGMENTS = 3, RGCN_Q_NUM_ENTRIES = 4, RGCN_Q_NUM_CHUNKS = 5,
     RGCN_Q_NUM_GROUPS = 6, RGCN_Q_NUM_BATCHES = 7, RGCN_Q_RANGE_NODES = 8,
-    RGCN_Q_DEVICE_BYTES = 9, RGCN_Q_NUM_OWNED = 10, RGCN_Q_OWN_LO = 11, RGCN_Q_NUM_ENTRIES0 = 12
+    RGCN_Q_DEVICE_BYTES = 9, RGCN_Q_NUM_OWNED = 10, RGCN_Q_OWN_LO = 11, RGCN_Q_NUM_ENTRIES0 = 12,
+    RGCN_Q_NUM_TILES = 13
 };
 
 /* rgcn_graph_export array ids (element type in brackets) */
@@ -60,7 +61,8 @@ enum {
     RGCN_A_SEG_REL = 3 /*i32[S]*/, RGCN_A_SEG_PTR0 = 4 /*i32[S+1] before chunking; diff = multiplicity*/, RGCN_A_E_IDX = 5 /*u32[E3]*/,
     RGCN_A_E_W = 6 /*f32[E3]*/, RGCN_A_RAW_IDX = 7 /*i32[E+N]*/, RGCN_A_RAW_W = 8 /*f32[E+N]*/,
     RGCN_A_CHUNK_BEG = 9 /*i32[NC]*/, RGCN_A_CHUNK_END = 10 /*i32[NC]*/,
-    RGCN_A_BAT_SEG0 = 11 /*i32[NB]*/, RGCN_A_BAT_INFO = 12 /*i32[NB]*/
+    RGCN_A_BAT_SEG0 = 11 /*i32[NB]*/, RGCN_A_BAT_INFO = 12 /*i32[NB]*/,
+    RGCN_A_E_OWN = 13 /*i32[E3]*/, RGCN_A_TILE_E0 = 14 /*i32[NT]*/, RGCN_A_TILE_INFO = 15 /*i32[NT]*/
 };
 
 /* layer flags */

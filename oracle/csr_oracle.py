@@ -117,7 +117,16 @@ def build_brc(own, gat, rel, n, r, nr, t, ch, w_edge=None, lo=0, hi=None):
             bat_seg0[b] = s0
             bat_info[b] = (int(grp_rel[gi]) << 8) | int(ns)
             b += 1
-    return dict(perm=perm.astype(np.int32), num_seg=s, seg_ptr=seg_ptr.astype(np.int32),
+    # per-entry owner and entry tiles (<= 16 consecutive entries of one (range, relation) group)
+    e_own = np.repeat(seg_own, out_cnt).astype(np.int32)
+    tile_e0, tile_info = [], []
+    for gi in range(g):
+        a, bnd = int(seg_ptr[grp_seg[gi]]), int(seg_ptr[grp_seg[gi + 1]])
+        for e0 in range(a, bnd, 16):
+            tile_e0.append(e0)
+            tile_info.append((int(grp_rel[gi]) << 8) | min(16, bnd - e0))
+    return dict(e_own=e_own, tile_e0=np.asarray(tile_e0, dtype=np.int32), tile_info=np.asarray(tile_info, dtype=np.int32),
+                num_tiles=len(tile_e0), perm=perm.astype(np.int32), num_seg=s, seg_ptr=seg_ptr.astype(np.int32),
                 seg_own=seg_own.astype(np.int32), seg_rel=seg_rel.astype(np.int32), cnt=cnt.astype(np.int32),
                 e_idx=e_idx, e_w=e_w, raw_idx=raw_idx, raw_w=raw_w, w_entry=w_entry,
                 chunk_beg=chunk_beg, chunk_end=chunk_end, num_chunks=nc,

@@ -29,6 +29,19 @@ struct WsCarver {
 
 inline int64_t ws_take(int64_t count, int64_t elem) { return align_up(std::max<int64_t>(count, 1) * elem, 256); }
 
+// Which kernel family gathers a pass whose gathered rows are padded to `kp` columns:
+// RGCN_B200_ETILE=1 / 0 forces the entry-tile / staged kernels, default = entry tiles for rows of
+// up to 32 columns, staged (coalesced 128-byte row loads through shared memory) for wider rows.
+bool etile_choice(int kp) {
+    static int mode = -2;
+    if (mode == -2) {
+        const char* e = getenv("RGCN_B200_ETILE");
+        mode = e ? (e[0] == '0' ? 0 : 1) : -1;
+    }
+    if (mode >= 0) return mode == 1;
+    return kp <= 32;
+}
+
 bool direct_target(const void* p, int64_t ld, int width) {
     return ld == width && width % 4 == 0 && ((uintptr_t)p & 15) == 0;
 }
@@ -91,7 +104,11 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     const int64_t tld = direct ? ldo : np;
     const int tn = direct ? fout : np;
     int rc;
-    WPrep wp{weight, root, g->R, fin, fout, kp, np, false, wfrag};
+    // wide rows that are not 16-byte addressable (Fin = 63) go through the staged kernels; everything
+    // else is gathered straight into MMA fragments
+    const bool et = etile_choice(kp);
+    const bool v4 = et && etile_vec4_ok(x, ldx, fin, aux);
+    WPrep wp{weight, root, g->R, fin, fout, kp, np, false, v4, wfrag};
     if ((rc = launch_wprep(wp, st))) return rc;
     TilePass p{};
     p.brc = &g->brc[RGCN_BRC_FWD];
@@ -104,9 +121,10 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     p.out = target; p.ldo = tld; p.nout = tn;
     p.kp = kp; p.np = np;
     p.relu_in = relu;
+    p.vec4 = v4;
     if ((rc = launch_chunk_prepass(p, st))) return rc;
     RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->n_own * tld * 4, st));
-    if ((rc = launch_tile_pass(p, g->num_sms, st))) return rc;
+    if ((rc = et ? launch_etile_pass(p, g->num_sms, st) : launch_tile_pass(p, g->num_sms, st))) return rc;
     if (!direct) return launch_copy_cols(target, tld, out, ldo, g->n_own, fout, st);
     return 0;
 }
@@ -181,11 +199,13 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
         p.gout = gout; p.ldg = ldg; p.nout = fout;
         p.gweight = gweight; p.groot = groot; p.gbias = gbias;
         p.kp = kp; p.np = np; p.relu_in = relu;
-        if ((rc = launch_wgrad_pass(p, g->num_sms, st))) return rc;
+        if ((rc = etile_choice(kp) ? launch_ewgrad_pass(p, g->num_sms, st) : launch_wgrad_pass(p, g->num_sms, st))) return rc;
     }
     if (gx) {
         // dx: transposed structure, gathers gout rows (width fout), B = W^T : [np x kp]
-        WPrep wp{weight, root, g->R, fin, fout, np, kp, true, wtfrag};
+        const bool et = etile_choice(np);
+        const bool v4 = et && etile_vec4_ok(gout_gather, ldgg, fout, gaux);
+        WPrep wp{weight, root, g->R, fin, fout, np, kp, true, v4, wtfrag};
         if ((rc = launch_wprep(wp, st))) return rc;
         const int64_t tld = direct ? ldgx : kp;
         TilePass p{};
@@ -199,9 +219,10 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
         p.kp = np; p.np = kp;
         p.relu_in = false;
         p.transposed = true;
+        p.vec4 = v4;
         if ((rc = launch_chunk_prepass(p, st))) return rc;
         RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->n_own * tld * 4, st));
-        if ((rc = launch_tile_pass(p, g->num_sms, st))) return rc;
+        if ((rc = et ? launch_etile_pass(p, g->num_sms, st) : launch_tile_pass(p, g->num_sms, st))) return rc;
         if (!direct && (rc = launch_copy_cols(target, tld, gx, ldgx, g->n_own, fin, st))) return rc;
         if (relu && (rc = launch_relu_mask(gx, ldgx, x_own, ldx, g->n_own, fin, st))) return rc;
     }

@@ -13,6 +13,7 @@ namespace rgcn {
 constexpr int BS = 16;                        // segments per batch (MMA M)
 constexpr int UNIT_BATCH_COST = 24;           // work-unit cost model: entries + 24 per batch
 constexpr int UNIT_MAX = 32768, UNIT_MIN_COST = 1024;
+constexpr int ET = 16;                        // entries per entry tile (MMA M of the entry-tile kernels)
 constexpr uint32_t LAST_FLAG = 0x80000000u;   // bit 31 of e_idx: last entry of its segment
 constexpr uint32_t IDX_MASK = 0x7fffffffu;
 
@@ -59,6 +60,10 @@ struct Brc {
     int32_t* bat_info = nullptr;   // [NB] rel << 8 | nseg
     int4* units = nullptr;         // [NU+1] equal-cost work units: (first batch, first segment, first entry, 0)
     int32_t num_units = 0;
+    int32_t* e_own = nullptr;      // [E3] owner row of every entry
+    int32_t* tile_e0 = nullptr;    // [NT] entry tiles: <= 16 consecutive entries of one (range, relation) group
+    int32_t* tile_info = nullptr;  // [NT] rel << 8 | count
+    int32_t num_tiles = 0;
     int64_t bytes = 0;
     void release();
 };
@@ -99,6 +104,7 @@ struct TilePass {
     int kp, np;
     bool relu_in;
     bool transposed;                                // dL/dx pass (profiling tag only)
+    bool vec4;                                      // entry-tile kernel: 16-byte row loads, wfrag prepared with perm
 };
 int launch_chunk_prepass(const TilePass& p, cudaStream_t st);
 int launch_tile_pass(const TilePass& p, int num_sms, cudaStream_t st);
@@ -109,6 +115,7 @@ struct WPrep {
     int R, fin, fout;
     int kp, np;            // padded dims of the pass (kp x np B-operand)
     bool transpose;        // B[k][n] = W[n][k]
+    bool perm;             // K order of the vector-load entry-tile kernel (see etile_kernels.cu)
     float4* wfrag;
 };
 int launch_wprep(const WPrep& p, cudaStream_t st);
@@ -127,6 +134,11 @@ struct WGradPass {
     bool relu_in;
 };
 int launch_wgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st);
+// entry-tile variants (etile_kernels.cu): rows gathered straight into MMA fragments
+bool etile_enabled();
+bool etile_vec4_ok(const float* feat, int64_t ldf, int kin, const float* aux);
+int launch_etile_pass(const TilePass& p, int num_sms, cudaStream_t st);
+int launch_ewgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st);
 
 int launch_copy_cols(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t n, int cols, cudaStream_t st);
 int launch_relu_mask(float* g, int64_t ldg, const float* pre, int64_t ldp, int64_t n, int cols, cudaStream_t st);

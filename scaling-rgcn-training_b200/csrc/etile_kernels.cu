@@ -1,0 +1,485 @@
+// etile_kernels.cu — entry-tile kernels: the layer's forward / dL/dx (k_etile) and dL/dW (k_ewgrad)
+// with the gathered rows loaded STRAIGHT INTO tensor-core fragments.
+//
+// A tile is <= 16 consecutive entries (edges, self loops or chunk rows) of one relation.  With the
+// entries as the M dimension of mma.m16n8k8, lane (g, t) of a warp owns entries g and g+8 and the
+// K positions t, t+4 of every 8-column step — so its A fragment is exactly
+//     x[src(g)][8k+t], x[src(g+8)][8k+t], x[src(g)][8k+t+4], x[src(g+8)][8k+t+4]
+// i.e. four plain 4-byte loads off two row pointers with immediate offsets; one load instruction
+// covers 8 rows x 16 B (sector pairs shared by the t / t+4 halves).  No shared memory staging, no
+// per-entry accumulate chain, no segment bookkeeping in the kernel: the per-(relation, dst) mean
+// is the sum of the entries' 1/cnt-weighted rows, and the sum happens in the scatter
+// (REDG.ADD.F32x4 per entry row).  dL/dW needs no segments at all:
+//     dW_rel = sum_entries (w_e x[src_e])^T (x) gout[owner_e]   =  A^T . B over 16-entry K slices
+// with A^T fragments again direct loads (lane (g,t): entries t, t+4; feature rows 16m+g, +8).
+//
+// Per 16 entries (63 -> 16): 32 row loads, 32 fmul, 64 split ops, 48 HMMA (3xTF32), 16 B-fragment
+// loads, 4 vector atomics — about half the instructions of the staged version and no
+// dependent chains longer than the MMA accumulate.
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "device_utils.cuh"
+
+namespace rgcn {
+namespace {
+
+using namespace dev;
+
+constexpr int EW = 8;    // warps per CTA
+constexpr int UT = 16;   // tiles per work unit (round-robin over warps)
+
+struct ETileArgs {
+    const uint32_t* e_idx;
+    const float* e_w;
+    const int32_t* e_own;
+    const int32_t* tile_e0;
+    const int32_t* tile_info;
+    int num_tiles;
+    const float* feat;
+    int64_t ldf;
+    int kin;
+    const float* aux;
+    int64_t n_rows;
+    const float4* wfrag;
+    const float* bias;
+    int nbias;
+    int self_rel;
+    float* out;
+    int64_t ldo;
+    int nout;
+    // dL/dW only
+    const float* gout;
+    int64_t ldg;
+    float* gweight;
+    float* groot;
+    float* gbias;
+};
+
+__device__ __forceinline__ float4 ldg128_hint(const float4* p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+// round-to-nearest split (unbiased): used for ONE operand when both are activations, so that the
+// dropped lo*lo term has no systematic sign over long sums
+__device__ __forceinline__ void split_rn(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+struct RowRef {   // one gathered row of a lane
+    const float* p;   // row pointer + lane's k offset
+    float w;
+    int own;
+    bool real;        // a feature row (ReLU applies), not a chunk row
+};
+
+template <int KP>
+__device__ __forceinline__ RowRef make_ref(const ETileArgs& a, int e, bool valid, int koff, uint64_t pol_s) {
+    RowRef r;
+    uint32_t idx = 0;
+    r.w = 0.f;
+    r.own = -1;
+    if (valid) {
+        idx = ldg_stream_u32(a.e_idx + e, pol_s) & IDX_MASK;
+        r.w = ldg_stream_f32(a.e_w + e, pol_s);
+        r.own = ldg_stream_s32(a.e_own + e, pol_s);
+    }
+    r.real = idx < (uint32_t)a.n_rows;
+    r.p = (r.real ? a.feat + (uint64_t)idx * (uint32_t)a.ldf : a.aux + (uint64_t)(idx - (uint32_t)a.n_rows) * KP) + koff;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward / dL/dx :  out[owner_e] += (w_e * x[src_e]) . B_rel   for the 16 entries of a tile
+// ---------------------------------------------------------------------------------------------
+// V4: rows are 16-byte addressable -> one LDG.128 per row per 16 columns.  Lane (g,t) then holds
+// columns 16j+4t..+3, which serve K slots (t, t+4) of steps 2j and 2j+1; the B fragments are
+// prepared with the matching row permutation (k_wprep perm).  K is a contraction index, so any
+// consistent permutation is exact.
+template <int KT, int NT, bool RELU, bool V4>
+__global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(const ETileArgs a) {
+    constexpr int KP = KT * 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int gw = blockIdx.x * EW + warp, nw = gridDim.x * EW;
+    const uint64_t pol_s = policy_evict_first();
+    const uint64_t pol_f =
+        (uint64_t)a.n_rows * (uint64_t)a.ldf * 4ull <= (112ull << 20) ? policy_evict_last() : policy_evict_normal();
+    const int num_units = (a.num_tiles + UT - 1) / UT;
+    for (int unit = gw; unit < num_units; unit += nw) {
+        const int t0 = unit * UT, t1 = min(a.num_tiles, t0 + UT);
+        int e0 = a.tile_e0[t0], info = a.tile_info[t0];
+        constexpr int KOFF = V4 ? 4 : 1;   // lane's column offset inside a row: 4t (vector) or t
+        RowRef rg = make_ref<KP>(a, e0 + g, g < (info & 0xff), KOFF * t, pol_s);
+        RowRef rh = make_ref<KP>(a, e0 + g + 8, g + 8 < (info & 0xff), KOFF * t, pol_s);
+        for (int ti = t0; ti < t1; ++ti) {
+            const int rel = info >> 8;
+            // A fragments: raw loads first (all independent), arithmetic afterwards
+            float av[KT][4];
+            if constexpr (V4) {
+#pragma unroll
+                for (int j = 0; j < KT / 2; ++j) {
+                    float4 vg = make_float4(0.f, 0.f, 0.f, 0.f), vh = vg;
+                    if (16 * j + 4 * t < a.kin) {
+                        vg = ldg128_hint(reinterpret_cast<const float4*>(rg.p + 16 * j), pol_f);
+                        vh = ldg128_hint(reinterpret_cast<const float4*>(rh.p + 16 * j), pol_f);
+                    }
+                    av[2 * j][0] = vg.x;       // step 2j  : slot t   <- col 16j+4t
+                    av[2 * j][2] = vg.y;       //            slot t+4 <- col 16j+4t+1
+                    av[2 * j + 1][0] = vg.z;   // step 2j+1: slot t   <- col 16j+4t+2
+                    av[2 * j + 1][2] = vg.w;   //            slot t+4 <- col 16j+4t+3
+                    av[2 * j][1] = vh.x;
+                    av[2 * j][3] = vh.y;
+                    av[2 * j + 1][1] = vh.z;
+                    av[2 * j + 1][3] = vh.w;
+                }
+            } else {
+#pragma unroll
+                for (int kt = 0; kt < KT; ++kt) {
+                    const bool c_lo = 8 * kt + t < a.kin, c_hi = 8 * kt + 4 + t < a.kin;
+                    av[kt][0] = c_lo ? ldg_hint(rg.p + 8 * kt, pol_f) : 0.f;
+                    av[kt][1] = c_lo ? ldg_hint(rh.p + 8 * kt, pol_f) : 0.f;
+                    av[kt][2] = c_hi ? ldg_hint(rg.p + 8 * kt + 4, pol_f) : 0.f;
+                    av[kt][3] = c_hi ? ldg_hint(rh.p + 8 * kt + 4, pol_f) : 0.f;
+                }
+            }
+            const RowRef cg = rg, ch = rh;
+            if (ti + 1 < t1) {   // next tile's indices are in flight while this tile computes
+                e0 = a.tile_e0[ti + 1];
+                info = a.tile_info[ti + 1];
+                rg = make_ref<KP>(a, e0 + g, g < (info & 0xff), KOFF * t, pol_s);
+                rh = make_ref<KP>(a, e0 + g + 8, g + 8 < (info & 0xff), KOFF * t, pol_s);
+            }
+            const float4* wf = a.wfrag + (int64_t)rel * (KT * NT * 32) + lane;
+            float d[NT][4];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) d[n][0] = d[n][1] = d[n][2] = d[n][3] = 0.f;
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) {
+                float x0 = av[kt][0], x1 = av[kt][1], x2 = av[kt][2], x3 = av[kt][3];
+                if (RELU) {
+                    if (cg.real) {
+                        x0 = fmaxf(x0, 0.f);
+                        x2 = fmaxf(x2, 0.f);
+                    }
+                    if (ch.real) {
+                        x1 = fmaxf(x1, 0.f);
+                        x3 = fmaxf(x3, 0.f);
+                    }
+                }
+                uint32_t ah[4], al[4];
+                split_fast(x0 * cg.w, ah[0], al[0]);
+                split_fast(x1 * ch.w, ah[1], al[1]);
+                split_fast(x2 * cg.w, ah[2], al[2]);
+                split_fast(x3 * ch.w, ah[3], al[3]);
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    const float4 bf = __ldg(wf + (kt * NT + n) * 32);
+                    const uint32_t bh0 = __float_as_uint(bf.x), bh1 = __float_as_uint(bf.y);
+                    const uint32_t bl0 = __float_as_uint(bf.z), bl1 = __float_as_uint(bf.w);
+                    mma_tf32(d[n], al[0], al[1], al[2], al[3], bh0, bh1);
+                    mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+                    mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+                }
+            }
+            if (rel == a.self_rel && a.bias != nullptr) {   // one self loop per owner: bias exactly once
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    const int col = 8 * n + 2 * t;
+                    const float bx = col < a.nbias ? a.bias[col] : 0.f;
+                    const float by = col + 1 < a.nbias ? a.bias[col + 1] : 0.f;
+                    d[n][0] += bx;
+                    d[n][1] += by;
+                    d[n][2] += bx;
+                    d[n][3] += by;
+                }
+            }
+            const bool odd = (t & 1) != 0;
+#pragma unroll
+            for (int j = 0; j < NT / 2; ++j) {
+                const int col = odd ? 8 * (2 * j + 1) + 2 * (t - 1) : 8 * (2 * j) + 2 * t;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {   // h = 0: entry g ; h = 1: entry g + 8
+                    const float p0 = d[2 * j][2 * h], p1 = d[2 * j][2 * h + 1];
+                    const float q0 = d[2 * j + 1][2 * h], q1 = d[2 * j + 1][2 * h + 1];
+                    const float rx = __shfl_xor_sync(FULL, odd ? p0 : q0, 1);
+                    const float ry = __shfl_xor_sync(FULL, odd ? p1 : q1, 1);
+                    const int own = h ? ch.own : cg.own;
+                    if (own >= 0 && col < a.nout) {
+                        float* p = a.out + (int64_t)own * a.ldo + col;
+                        if (odd) red_add_v4(p, rx, ry, q0, q1);
+                        else red_add_v4(p, p0, p1, rx, ry);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dL/dW :  D[Kp x Np] += sum over the tile's entries  (w_e x[src_e])^T (x) gout[owner_e]
+// lane (g,t): K slots = entries t, t+4 (first 8) and 8+t, 12+t (second 8); M rows = features 16m+g, +8
+// ---------------------------------------------------------------------------------------------
+template <int KT, int NT, bool RELU>
+__global__ void __launch_bounds__(EW * 32, (KT * NT >= 32) ? 1 : 2) k_ewgrad(const ETileArgs a) {
+    constexpr int KP = KT * 8, MT = KP / 16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int gw = blockIdx.x * EW + warp, nw = gridDim.x * EW;
+    const uint64_t pol_s = policy_evict_first();
+    const uint64_t pol_f =
+        (uint64_t)a.n_rows * (uint64_t)a.ldf * 4ull <= (112ull << 20) ? policy_evict_last() : policy_evict_normal();
+    float d[MT][NT][4];
+    float bsum[NT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) d[m][n][0] = d[m][n][1] = d[m][n][2] = d[m][n][3] = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) bsum[n] = 0.f;
+    int cur_rel = -1;
+
+    auto flush = [&](int rel) {
+        float* dst = rel == a.self_rel ? a.groot : (a.gweight ? a.gweight + (int64_t)rel * a.kin * a.nout : nullptr);
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = 16 * m + g + ((i & 2) ? 8 : 0);
+                    const int col = 8 * n + 2 * t + (i & 1);
+                    if (dst && row < a.kin && col < a.nout) atomicAdd(dst + (int64_t)row * a.nout + col, d[m][n][i]);
+                    d[m][n][i] = 0.f;
+                }
+            }
+    };
+
+    const int num_units = (a.num_tiles + UT - 1) / UT;
+    for (int unit = gw; unit < num_units; unit += nw) {
+        const int t0 = unit * UT, t1 = min(a.num_tiles, t0 + UT);
+        int e0 = a.tile_e0[t0], info = a.tile_info[t0];
+        RowRef r[4];   // entries t, t+4, 8+t, 12+t ; feature offset g folded in
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[i] = make_ref<KP>(a, e0 + t + 4 * i, t + 4 * i < (info & 0xff), g, pol_s);
+        for (int ti = t0; ti < t1; ++ti) {
+            const int rel = info >> 8;
+            if (rel != cur_rel) {
+                if (cur_rel >= 0) flush(cur_rel);
+                cur_rel = rel;
+            }
+            const bool wanted = rel == a.self_rel ? (a.groot != nullptr || a.gbias != nullptr) : a.gweight != nullptr;
+            float av[2][MT][4], bv[2][NT][2];
+            if (wanted) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const RowRef& ra = r[2 * ks];       // K slot t
+                    const RowRef& rb = r[2 * ks + 1];   // K slot t + 4
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        const bool c_lo = 16 * m + g < a.kin, c_hi = 16 * m + 8 + g < a.kin;
+                        av[ks][m][0] = c_lo ? ldg_hint(ra.p + 16 * m, pol_f) : 0.f;
+                        av[ks][m][1] = c_hi ? ldg_hint(ra.p + 16 * m + 8, pol_f) : 0.f;
+                        av[ks][m][2] = c_lo ? ldg_hint(rb.p + 16 * m, pol_f) : 0.f;
+                        av[ks][m][3] = c_hi ? ldg_hint(rb.p + 16 * m + 8, pol_f) : 0.f;
+                    }
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) {
+                        const bool cn = 8 * n + g < a.nout;
+                        bv[ks][n][0] = (cn && ra.own >= 0) ? __ldg(a.gout + (int64_t)ra.own * a.ldg + 8 * n + g) : 0.f;
+                        bv[ks][n][1] = (cn && rb.own >= 0) ? __ldg(a.gout + (int64_t)rb.own * a.ldg + 8 * n + g) : 0.f;
+                    }
+                }
+            }
+            RowRef c[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[i] = r[i];
+            if (ti + 1 < t1) {
+                e0 = a.tile_e0[ti + 1];
+                info = a.tile_info[ti + 1];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) r[i] = make_ref<KP>(a, e0 + t + 4 * i, t + 4 * i < (info & 0xff), g, pol_s);
+            }
+            if (!wanted) continue;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const RowRef& ra = c[2 * ks];
+                const RowRef& rb = c[2 * ks + 1];
+                uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    split_rn(bv[ks][n][0], bh[n][0], bl[n][0]);
+                    split_rn(bv[ks][n][1], bh[n][1], bl[n][1]);
+                    if (rel == a.self_rel) bsum[n] += bv[ks][n][0] + bv[ks][n][1];
+                }
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    float x0 = av[ks][m][0], x1 = av[ks][m][1], x2 = av[ks][m][2], x3 = av[ks][m][3];
+                    if (RELU) {
+                        if (ra.real) {
+                            x0 = fmaxf(x0, 0.f);
+                            x1 = fmaxf(x1, 0.f);
+                        }
+                        if (rb.real) {
+                            x2 = fmaxf(x2, 0.f);
+                            x3 = fmaxf(x3, 0.f);
+                        }
+                    }
+                    uint32_t ah[4], al[4];
+                    split_fast(x0 * ra.w, ah[0], al[0]);
+                    split_fast(x1 * ra.w, ah[1], al[1]);
+                    split_fast(x2 * rb.w, ah[2], al[2]);
+                    split_fast(x3 * rb.w, ah[3], al[3]);
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) {
+                        mma_tf32(d[m][n], al[0], al[1], al[2], al[3], bh[n][0], bh[n][1]);
+                        mma_tf32(d[m][n], ah[0], ah[1], ah[2], ah[3], bl[n][0], bl[n][1]);
+                        mma_tf32(d[m][n], ah[0], ah[1], ah[2], ah[3], bh[n][0], bh[n][1]);
+                    }
+                }
+            }
+        }
+    }
+    if (cur_rel >= 0) flush(cur_rel);
+    if (a.gbias) {   // column 8n+g summed over this lane's K slots; fold the 4 t-lanes, then one atomic
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            float s = bsum[n];
+            s += __shfl_xor_sync(FULL, s, 1);
+            s += __shfl_xor_sync(FULL, s, 2);
+            if (t == 0 && 8 * n + g < a.nout && s != 0.f) atomicAdd(a.gbias + 8 * n + g, s);
+        }
+    }
+}
+
+template <int KT, int NT>
+int run_etile(const ETileArgs& a, bool relu, bool v4, int num_sms, cudaStream_t st) {
+    auto launch = [&](auto kern) -> int {
+        int per_sm = 1;
+        RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EW * 32, 0));
+        per_sm = std::max(per_sm, 1);
+        const int64_t units = ((int64_t)a.num_tiles + UT - 1) / UT;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + EW - 1) / EW, (int64_t)num_sms * per_sm));
+        kern<<<grid, EW * 32, 0, st>>>(a);
+        RGCN_CUDA(cudaGetLastError());
+        return 0;
+    };
+    if (v4) {
+        if (relu) return launch(k_etile<KT, NT, true, true>);
+        return launch(k_etile<KT, NT, false, true>);
+    }
+    if (relu) return launch(k_etile<KT, NT, true, false>);
+    return launch(k_etile<KT, NT, false, false>);
+}
+
+template <int KT, int NT>
+int run_ewgrad(const ETileArgs& a, bool relu, int num_sms, cudaStream_t st) {
+    auto launch = [&](auto kern) -> int {
+        int per_sm = 1;
+        RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EW * 32, 0));
+        per_sm = std::max(per_sm, 1);
+        const int64_t units = ((int64_t)a.num_tiles + UT - 1) / UT;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + EW - 1) / EW, (int64_t)num_sms * per_sm));
+        kern<<<grid, EW * 32, 0, st>>>(a);
+        RGCN_CUDA(cudaGetLastError());
+        return 0;
+    };
+    if (relu) return launch(k_ewgrad<KT, NT, true>);
+    return launch(k_ewgrad<KT, NT, false>);
+}
+
+#define RGCN_DISPATCH_E(FN, kp, np, ...)                                          \
+    do {                                                                          \
+        const int _k = (kp) / 8, _n = (np) / 8;                                   \
+        if (_k == 2 && _n == 2) return FN<2, 2>(__VA_ARGS__);                     \
+        if (_k == 2 && _n == 4) return FN<2, 4>(__VA_ARGS__);                     \
+        if (_k == 2 && _n == 8) return FN<2, 8>(__VA_ARGS__);                     \
+        if (_k == 4 && _n == 2) return FN<4, 2>(__VA_ARGS__);                     \
+        if (_k == 4 && _n == 4) return FN<4, 4>(__VA_ARGS__);                     \
+        if (_k == 4 && _n == 8) return FN<4, 8>(__VA_ARGS__);                     \
+        if (_k == 8 && _n == 2) return FN<8, 2>(__VA_ARGS__);                     \
+        if (_k == 8 && _n == 4) return FN<8, 4>(__VA_ARGS__);                     \
+        if (_k == 8 && _n == 8) return FN<8, 8>(__VA_ARGS__);                     \
+        return fail(RGCN_ERR_UNSUPPORTED, "no entry-tile kernel for this padded shape"); \
+    } while (0)
+
+ETileArgs base_args(const Brc& b) {
+    ETileArgs a{};
+    a.e_idx = b.e_idx;
+    a.e_w = b.e_w;
+    a.e_own = b.e_own;
+    a.tile_e0 = b.tile_e0;
+    a.tile_info = b.tile_info;
+    a.num_tiles = b.num_tiles;
+    return a;
+}
+
+}  // namespace
+
+// one LDG.128 per row per 16 columns needs 16-byte addressable rows and a width in whole quads
+bool etile_vec4_ok(const float* feat, int64_t ldf, int kin, const float* aux) {
+    static int off = -1;
+    if (off < 0) {
+        const char* e = getenv("RGCN_B200_VEC4");
+        off = (e && e[0] == '0') ? 1 : 0;
+    }
+    return !off && ldf % 4 == 0 && kin % 4 == 0 && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)aux & 15) == 0;
+}
+
+bool etile_enabled() {   // RGCN_B200_ETILE=0 selects the staged (shared-memory ring) kernels instead
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RGCN_B200_ETILE");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+int launch_etile_pass(const TilePass& p, int num_sms, cudaStream_t st) {
+    const Brc& b = *p.brc;
+    if (b.num_tiles == 0) return 0;
+    ETileArgs a = base_args(b);
+    a.feat = p.feat;
+    a.ldf = p.ldf;
+    a.kin = p.kin;
+    a.aux = p.aux ? p.aux : p.feat;
+    a.n_rows = p.n_nodes;
+    a.wfrag = p.wfrag;
+    a.bias = p.bias;
+    a.nbias = p.nbias;
+    a.self_rel = p.self_rel;
+    a.out = p.out;
+    a.ldo = p.ldo;
+    a.nout = p.nout;
+    ProfScope prof(p.transposed ? TAG_TILE_BWD : TAG_TILE_FWD, p.kin, p.nout, st);
+    note_launch(1);
+    RGCN_DISPATCH_E(run_etile, p.kp, p.np, a, p.relu_in, p.vec4, num_sms, st);
+}
+
+int launch_ewgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st) {
+    const Brc& b = *p.brc;
+    if (b.num_tiles == 0) return 0;
+    ETileArgs a = base_args(b);
+    a.feat = p.feat;
+    a.ldf = p.ldf;
+    a.kin = p.kin;
+    a.aux = p.aux ? p.aux : p.feat;
+    a.n_rows = p.n_nodes;
+    a.self_rel = p.self_rel;
+    a.gout = p.gout;
+    a.ldg = p.ldg;
+    a.nout = p.nout;
+    a.gweight = p.gweight;
+    a.groot = p.groot;
+    a.gbias = p.gbias;
+    ProfScope prof(TAG_WGRAD, p.kin, p.nout, st);
+    note_launch(1);
+    RGCN_DISPATCH_E(run_ewgrad, p.kp, p.np, a, p.relu_in, num_sms, st);
+}
+
+}  // namespace rgcn

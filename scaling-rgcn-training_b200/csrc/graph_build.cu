@@ -24,7 +24,7 @@ const char* last_error_cstr() { return g_last_error.c_str(); }
 
 void Brc::release() {
     void* ptrs[] = {perm, seg_ptr0, seg_ptr, seg_own, seg_rel, e_idx, e_w, raw_idx, raw_w,
-                    chunk_beg, chunk_end, bat_seg0, bat_info, units};
+                    chunk_beg, chunk_end, bat_seg0, bat_info, units, e_own, tile_e0, tile_info};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     *this = Brc();
@@ -179,7 +179,8 @@ __global__ void k_compact(const int32_t* __restrict__ scan, const int32_t* __res
                           const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ chunk_base,
                           const int32_t* __restrict__ raw_idx, const float* __restrict__ raw_w, int64_t n2, int64_t N,
                           int T, int CH, uint32_t* __restrict__ e_idx, float* __restrict__ e_w,
-                          int32_t* __restrict__ chunk_beg, int32_t* __restrict__ chunk_end) {
+                          int32_t* __restrict__ chunk_beg, int32_t* __restrict__ chunk_end,
+                          const int32_t* __restrict__ seg_own, int32_t* __restrict__ e_own) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n2) return;
     int32_t s = scan[i] - 1;
@@ -189,6 +190,7 @@ __global__ void k_compact(const int32_t* __restrict__ scan, const int32_t* __res
     if (cnt <= T) {
         e_idx[o + p] = (uint32_t)raw_idx[i] | (p == cnt - 1 ? LAST_FLAG : 0u);
         e_w[o + p] = raw_w[i];
+        e_own[o + p] = seg_own[s];
     } else if (p % CH == 0) {
         int32_t j = p / CH, nc = (cnt + CH - 1) / CH;
         int32_t c = chunk_base[s] + j;
@@ -196,6 +198,7 @@ __global__ void k_compact(const int32_t* __restrict__ scan, const int32_t* __res
         chunk_end[c] = min((int32_t)i + CH, b);
         e_idx[o + j] = (uint32_t)(N + c) | (j == nc - 1 ? LAST_FLAG : 0u);
         e_w[o + j] = 1.0f;
+        e_own[o + j] = seg_own[s];
     }
 }
 
@@ -240,6 +243,30 @@ __global__ void k_batch_fill(const int32_t* __restrict__ bat_base, const int32_t
 }
 
 __global__ void k_set_i32(int32_t* p, int32_t v) { *p = v; }
+
+// entry tiles: each (range, relation) group's entries cut into runs of <= ET
+__global__ void k_group_ntiles(const int32_t* __restrict__ grp_seg, const int32_t* __restrict__ seg_ptr, int32_t G,
+                               int32_t* __restrict__ nt) {
+    int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    nt[g] = (seg_ptr[grp_seg[g + 1]] - seg_ptr[grp_seg[g]] + ET - 1) / ET;
+}
+__global__ void k_tile_fill(const int32_t* __restrict__ tile_base, const int32_t* __restrict__ grp_seg,
+                            const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_rel, int32_t G,
+                            int32_t NT, int32_t* __restrict__ tile_e0, int32_t* __restrict__ tile_info) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= NT) return;
+    int lo = 0, hi = G - 1;   // largest g with tile_base[g] <= i
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (tile_base[mid] <= (int32_t)i) lo = mid;
+        else hi = mid - 1;
+    }
+    const int32_t e_beg = seg_ptr[grp_seg[lo]], e_end = seg_ptr[grp_seg[lo + 1]];
+    const int32_t e0 = e_beg + ((int32_t)i - tile_base[lo]) * ET;
+    tile_e0[i] = e0;
+    tile_info[i] = (seg_rel[grp_seg[lo]] << 8) | min(ET, e_end - e0);
+}
 
 // Work units: cut the batch list into NU pieces of equal cost c(b) = first_entry(b) + 24 b
 // (entries + a per-batch overhead), so that warps taking units round-robin finish together.
@@ -360,8 +387,9 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const 
     RGCN_CUDA(cudaMalloc(&b.e_w, std::max(E3, 1) * 4));
     RGCN_CUDA(cudaMalloc(&b.chunk_beg, std::max(NC, 1) * 4));
     RGCN_CUDA(cudaMalloc(&b.chunk_end, std::max(NC, 1) * 4));
+    RGCN_CUDA(cudaMalloc(&b.e_own, std::max(E3, 1) * 4));
     k_compact<<<blocks_for(n2), TPB, 0, st>>>(scan.p, b.seg_ptr0, b.seg_ptr, chunk_base.p, b.raw_idx, b.raw_w, n2, n_gat, T,
-                                              CH, b.e_idx, b.e_w, b.chunk_beg, b.chunk_end);
+                                              CH, b.e_idx, b.e_w, b.chunk_beg, b.chunk_end, b.seg_own, b.e_own);
 
     // groups and batches
     Dev<int32_t> ghead, gscan;
@@ -392,6 +420,24 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const 
     RGCN_CUDA(cudaMalloc(&b.bat_info, std::max(NB, 1) * 4));
     if (NB > 0)
         k_batch_fill<<<blocks_for(NB), TPB, 0, st>>>(bat_base.p, grp_seg.p, b.seg_rel, G, NB, b.bat_seg0, b.bat_info);
+    {   // entry tiles
+        Dev<int32_t> ntl, tile_base;
+        RGCN_CUDA(ntl.alloc(G + 1));
+        RGCN_CUDA(tile_base.alloc(G + 1));
+        int32_t NTL = 0;
+        if (G > 0) {
+            RGCN_CUDA(cudaMemsetAsync(ntl.p, 0, (size_t)(G + 1) * 4, st));
+            k_group_ntiles<<<blocks_for(G), TPB, 0, st>>>(grp_seg.p, b.seg_ptr, G, ntl.p);
+            RGCN_CUDA(scan_exclusive(ntl.p, tile_base.p, (int64_t)G + 1, st));
+            RGCN_CUDA(cudaMemcpy(&NTL, tile_base.p + G, 4, cudaMemcpyDeviceToHost));
+        }
+        b.num_tiles = NTL;
+        RGCN_CUDA(cudaMalloc(&b.tile_e0, std::max(NTL, 1) * 4));
+        RGCN_CUDA(cudaMalloc(&b.tile_info, std::max(NTL, 1) * 4));
+        if (NTL > 0)
+            k_tile_fill<<<blocks_for(NTL), TPB, 0, st>>>(tile_base.p, grp_seg.p, b.seg_ptr, b.seg_rel, G, NTL, b.tile_e0,
+                                                         b.tile_info);
+    }
     {
         const int64_t total = (int64_t)E3 + (int64_t)UNIT_BATCH_COST * NB;
         int64_t nu = std::min<int64_t>(UNIT_MAX, std::max<int64_t>(1, total / UNIT_MIN_COST));
@@ -519,7 +565,7 @@ extern "C" int rgcn_graph_create_part(const int64_t* src, int64_t src_stride, co
     g->n_own = own_hi - own_lo;
     cudaGetDevice(&g->device);
     cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, g->device);
-    g->split_threshold = split_threshold > 0 ? split_threshold : 256;
+    g->split_threshold = split_threshold > 0 ? split_threshold : 32;
     g->chunk_size = chunk_size > 0 ? chunk_size : 256;
     int64_t nr = range_nodes > 0 ? range_nodes : 16384;
     // small graphs: one range (pure relation-major); large: blocked so accumulate targets stay L2-hot
@@ -600,6 +646,7 @@ extern "C" int rgcn_graph_query(const rgcn_graph* g, int32_t brc, int32_t key, i
         case RGCN_Q_NUM_OWNED: *out = g->n_own; break;
         case RGCN_Q_OWN_LO: *out = g->own_lo; break;
         case RGCN_Q_NUM_ENTRIES0: *out = b.num_entries0; break;
+        case RGCN_Q_NUM_TILES: *out = b.num_tiles; break;
         case RGCN_Q_DEVICE_BYTES:
             *out = g->brc[0].bytes + g->brc[1].bytes + (g->rel_is_fwd ? 0 : g->brc[2].bytes);
             break;
@@ -628,6 +675,9 @@ extern "C" int rgcn_graph_export(const rgcn_graph* g, int32_t brc, int32_t array
         case RGCN_A_CHUNK_END: p = b.chunk_end; n = b.num_chunks; break;
         case RGCN_A_BAT_SEG0: p = b.bat_seg0; n = b.num_batches; break;
         case RGCN_A_BAT_INFO: p = b.bat_info; n = b.num_batches; break;
+        case RGCN_A_E_OWN: p = b.e_own; n = b.num_entries; break;
+        case RGCN_A_TILE_E0: p = b.tile_e0; n = b.num_tiles; break;
+        case RGCN_A_TILE_INFO: p = b.tile_info; n = b.num_tiles; break;
         default: return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_export: unknown array");
     }
     if (bytes != n * 4) return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_export: byte count mismatch");

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256) k_chunk_sum(const int32_t* __restrict__ r
 //   B = W_rel (rows<fin, cols<fout) or its transpose; rel == R is the root matrix.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_wprep(const float* __restrict__ weight, const float* __restrict__ root, int R, int fin, int fout,
-                        int KT, int NT, int transpose, float4* __restrict__ wfrag) {
+                        int KT, int NT, int transpose, int perm, float4* __restrict__ wfrag) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)(R + 1) * KT * NT * 32;
     if (i >= total) return;
@@ -249,7 +249,8 @@ __global__ void k_wprep(const float* __restrict__ weight, const float* __restric
     float b[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const int k = 8 * kt + t + 4 * h;
+        // K slot (t + 4h) of step kt: natural order, or the vector-load order 16(kt/2) + 4t + 2(kt%2) + h
+        const int k = perm ? 16 * (kt >> 1) + 4 * t + 2 * (kt & 1) + h : 8 * kt + t + 4 * h;
         float v = 0.f;
         if (W) {
             if (!transpose) {
@@ -808,7 +809,7 @@ int launch_wprep(const WPrep& p, cudaStream_t st) {
     ProfScope prof(TAG_WPREP, p.fin, p.fout, st);
     note_launch(1);
     k_wprep<<<(int)((total + tpb - 1) / tpb), tpb, 0, st>>>(p.weight, p.root, p.R, p.fin, p.fout, KT, NT,
-                                                            p.transpose ? 1 : 0, p.wfrag);
+                                                            p.transpose ? 1 : 0, p.perm ? 1 : 0, p.wfrag);
     RGCN_CUDA(cudaGetLastError());
     return 0;
 }

@@ -73,6 +73,8 @@ class RGCNGraph:
             _lib.A_E_IDX: self.query(_lib.Q_NUM_ENTRIES, brc), _lib.A_E_W: self.query(_lib.Q_NUM_ENTRIES, brc),
             _lib.A_CHUNK_BEG: self.query(_lib.Q_NUM_CHUNKS, brc), _lib.A_CHUNK_END: self.query(_lib.Q_NUM_CHUNKS, brc),
             _lib.A_BAT_SEG0: self.query(_lib.Q_NUM_BATCHES, brc), _lib.A_BAT_INFO: self.query(_lib.Q_NUM_BATCHES, brc),
+            _lib.A_E_OWN: self.query(_lib.Q_NUM_ENTRIES, brc), _lib.A_TILE_E0: self.query(_lib.Q_NUM_TILES, brc),
+            _lib.A_TILE_INFO: self.query(_lib.Q_NUM_TILES, brc),
         }[array]
         out = np.empty(n, dtype=_ARRAY_DTYPES.get(array, np.int32))
         with torch.cuda.device(self.device):

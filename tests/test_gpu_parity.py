@@ -29,10 +29,12 @@ def _check_brc(g, which, want):
     assert g.query(_lib.Q_NUM_CHUNKS, which) == want['num_chunks']
     assert g.query(_lib.Q_NUM_BATCHES, which) == want['num_batches']
     assert g.query(_lib.Q_NUM_GROUPS, which) == want['num_groups']
+    assert g.query(_lib.Q_NUM_TILES, which) == want['num_tiles']
     pairs = [(_lib.A_PERM, 'perm'), (_lib.A_SEG_PTR, 'seg_ptr'), (_lib.A_SEG_OWN, 'seg_own'), (_lib.A_SEG_REL, 'seg_rel'),
              (_lib.A_E_IDX, 'e_idx'), (_lib.A_E_W, 'e_w'), (_lib.A_RAW_IDX, 'raw_idx'), (_lib.A_RAW_W, 'raw_w'),
              (_lib.A_CHUNK_BEG, 'chunk_beg'), (_lib.A_CHUNK_END, 'chunk_end'), (_lib.A_BAT_SEG0, 'bat_seg0'),
-             (_lib.A_BAT_INFO, 'bat_info')]
+             (_lib.A_BAT_INFO, 'bat_info'), (_lib.A_E_OWN, 'e_own'), (_lib.A_TILE_E0, 'tile_e0'),
+             (_lib.A_TILE_INFO, 'tile_info')]
     for aid, name in pairs:
         got = g.export(aid, which)
         assert got.dtype == want[name].dtype or got.view(want[name].dtype).dtype == want[name].dtype
@@ -45,7 +47,7 @@ def _check_brc(g, which, want):
 def test_graph_build_bit_exact(name, nr, t, ch):
     ei, et, n, r = golden_graph(name)
     g = RGCNGraph(ei.to(DEV), et.to(DEV), n, r, range_nodes=nr, split_threshold=t, chunk_size=ch)
-    nr_eff, t_eff, ch_eff = (nr or 16384), (t or 256), (ch or 256)
+    nr_eff, t_eff, ch_eff = (nr or 16384), (t or 32), (ch or 256)
     src, dst, rel = ei[0].numpy(), ei[1].numpy(), et.numpy()
     fwd, bwd = csr_oracle.build_graph(src, dst, rel, n, r, nr_eff, t_eff, ch_eff)
     _check_brc(g, _lib.BRC_FWD, fwd)

@@ -14,17 +14,9 @@ PY
 for v in "$@"; do
   case $v in
     default) run default A=1;;
-    breg1) run breg1 RGCN_B200_BREG=1;;
+    ring) run ring RGCN_B200_ETILE=0;;
     relmajor) run relmajor RGCN_B200_RANGE_NODES=1000000000;;
-    nr16k) run nr16k RGCN_B200_RANGE_NODES=16384;;
+    nr4k) run nr4k RGCN_B200_RANGE_NODES=4096;;
     nr64k) run nr64k RGCN_B200_RANGE_NODES=65536;;
-    nr1k) run nr1k RGCN_B200_RANGE_NODES=1024;;
-  esac
-done
-for v in "$@"; do
-  case $v in
-    dbg1) run dbg1 RGCN_B200_DBG=1;;
-    dbg2) run dbg2 RGCN_B200_DBG=2;;
-    dbg3) run dbg3 RGCN_B200_DBG=3;;
   esac
 done
