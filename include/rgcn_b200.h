@@ -134,6 +134,12 @@ int rgcn_map_gather(const float* const* host_emb, const int32_t* const* host_idx
                     const float* const* host_fallback, int32_t num_sums,
                     int64_t num_nodes, int32_t feat, int32_t mode, float* out, void* stream);
 
+/* Zero-padded, 16-byte addressable mirror of an odd-width feature matrix (e.g. the reference's
+ * emb = 63): dst[r][c] = c < cols ? src[r][c] : 0 for c < ldd.  Passing the mirror (ldx = ldd) as x
+ * to rgcn_layer_fwd / rgcn_layer_bwd lets the kernels use 128-bit row loads. */
+int rgcn_pad_rows(const float* src, int64_t lds, int32_t cols, float* dst, int64_t ldd, int64_t num_rows,
+                  void* stream);
+
 /* Instrumentation (no reference counterpart).  rgcn_kernel_launch_count: engine kernels launched
  * by this process so far.  rgcn_profile_enable(1): every pass launch is bracketed by a CUDA-event
  * pair on its own stream; rgcn_profile_collect synchronises those events, returns up to

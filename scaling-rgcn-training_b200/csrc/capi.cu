@@ -32,14 +32,14 @@ inline int64_t ws_take(int64_t count, int64_t elem) { return align_up(std::max<i
 // Which kernel family gathers a pass whose gathered rows are padded to `kp` columns:
 // RGCN_B200_ETILE=1 / 0 forces the entry-tile / staged kernels, default = entry tiles for rows of
 // up to 32 columns, staged (coalesced 128-byte row loads through shared memory) for wider rows.
-bool etile_choice(int kp) {
+bool etile_choice(int kp, bool vec4_ok) {
     static int mode = -2;
     if (mode == -2) {
         const char* e = getenv("RGCN_B200_ETILE");
         mode = e ? (e[0] == '0' ? 0 : 1) : -1;
     }
     if (mode >= 0) return mode == 1;
-    return kp <= 32;
+    return kp <= 32 || vec4_ok;
 }
 
 bool direct_target(const void* p, int64_t ld, int width) {
@@ -106,8 +106,9 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     int rc;
     // wide rows that are not 16-byte addressable (Fin = 63) go through the staged kernels; everything
     // else is gathered straight into MMA fragments
-    const bool et = etile_choice(kp);
-    const bool v4 = et && etile_vec4_ok(x, ldx, fin, aux);
+    const bool v4ok = etile_vec4_ok(x, ldx, fin, aux);
+    const bool et = etile_choice(kp, v4ok);
+    const bool v4 = et && v4ok;
     WPrep wp{weight, root, g->R, fin, fout, kp, np, false, v4, wfrag};
     if ((rc = launch_wprep(wp, st))) return rc;
     TilePass p{};
@@ -199,12 +200,15 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
         p.gout = gout; p.ldg = ldg; p.nout = fout;
         p.gweight = gweight; p.groot = groot; p.gbias = gbias;
         p.kp = kp; p.np = np; p.relu_in = relu;
-        if ((rc = etile_choice(kp) ? launch_ewgrad_pass(p, g->num_sms, st) : launch_wgrad_pass(p, g->num_sms, st))) return rc;
+        const bool v4ok = kp >= 32 && etile_vec4_ok(x, ldx, fin, xaux);
+        p.vec4 = v4ok;
+        if ((rc = etile_choice(kp, v4ok) ? launch_ewgrad_pass(p, g->num_sms, st) : launch_wgrad_pass(p, g->num_sms, st))) return rc;
     }
     if (gx) {
         // dx: transposed structure, gathers gout rows (width fout), B = W^T : [np x kp]
-        const bool et = etile_choice(np);
-        const bool v4 = et && etile_vec4_ok(gout_gather, ldgg, fout, gaux);
+        const bool v4ok = etile_vec4_ok(gout_gather, ldgg, fout, gaux);
+        const bool et = etile_choice(np, v4ok);
+        const bool v4 = et && v4ok;
         WPrep wp{weight, root, g->R, fin, fout, np, kp, true, v4, wtfrag};
         if ((rc = launch_wprep(wp, st))) return rc;
         const int64_t tld = direct ? ldgx : kp;
@@ -227,4 +231,11 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
         if (relu && (rc = launch_relu_mask(gx, ldgx, x_own, ldx, g->n_own, fin, st))) return rc;
     }
     return 0;
+}
+
+extern "C" int rgcn_pad_rows(const float* src, int64_t lds, int32_t cols, float* dst, int64_t ldd, int64_t n,
+                             void* stream) {
+    if (!src || !dst || cols <= 0 || lds < cols || ldd < cols || n < 0)
+        return fail(RGCN_ERR_INVALID_ARG, "rgcn_pad_rows: bad argument");
+    return launch_pad_rows(src, lds, cols, dst, ldd, n, (cudaStream_t)stream);
 }

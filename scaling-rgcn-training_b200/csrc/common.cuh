@@ -132,6 +132,7 @@ struct WGradPass {
     float* gbias;          // [nout] nullable (zeroed)
     int kp, np;
     bool relu_in;
+    bool vec4;             // entry-tile kernel with 16-byte row loads
 };
 int launch_wgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st);
 // entry-tile variants (etile_kernels.cu): rows gathered straight into MMA fragments
@@ -141,6 +142,7 @@ int launch_etile_pass(const TilePass& p, int num_sms, cudaStream_t st);
 int launch_ewgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st);
 
 int launch_copy_cols(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t n, int cols, cudaStream_t st);
+int launch_pad_rows(const float* src, int64_t lds, int cols, float* dst, int64_t ldd, int64_t n, cudaStream_t st);
 int launch_relu_mask(float* g, int64_t ldg, const float* pre, int64_t ldp, int64_t n, int cols, cudaStream_t st);
 
 // generic scalar path (any fin/fout)

@@ -225,9 +225,14 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
 // dL/dW :  D[Kp x Np] += sum over the tile's entries  (w_e x[src_e])^T (x) gout[owner_e]
 // lane (g,t): K slots = entries t, t+4 (first 8) and 8+t, 12+t (second 8); M rows = features 16m+g, +8
 // ---------------------------------------------------------------------------------------------
-template <int KT, int NT, bool RELU>
+// V4 (rows 16-byte addressable, Kp >= 32): lane (g,t) reads columns 32b+4g..+3 of its entries with
+// LDG.128 (8 lanes x 16 B = 128 contiguous bytes per row) and those four values serve M rows
+// (m-tile 2b, rows g / g+8) and (m-tile 2b+1, rows g / g+8): feature(m, h) = 32(m>>1) + 4g + 2(m&1) + h.
+// M is an output index here, so the permutation is undone when D is flushed.
+template <int KT, int NT, bool RELU, bool V4>
 __global__ void __launch_bounds__(EW * 32, (KT * NT >= 32) ? 1 : 2) k_ewgrad(const ETileArgs a) {
     constexpr int KP = KT * 8, MT = KP / 16;
+    static_assert(!V4 || KP >= 32, "vector loads need at least 32 columns");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int gw = blockIdx.x * EW + warp, nw = gridDim.x * EW;
@@ -252,7 +257,8 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 32) ? 1 : 2) k_ewgrad(con
             for (int n = 0; n < NT; ++n) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int row = 16 * m + g + ((i & 2) ? 8 : 0);
+                    const int h = (i & 2) ? 1 : 0;
+                    const int row = V4 ? 32 * (m >> 1) + 4 * g + 2 * (m & 1) + h : 16 * m + g + 8 * h;
                     const int col = 8 * n + 2 * t + (i & 1);
                     if (dst && row < a.kin && col < a.nout) atomicAdd(dst + (int64_t)row * a.nout + col, d[m][n][i]);
                     d[m][n][i] = 0.f;
@@ -260,13 +266,14 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 32) ? 1 : 2) k_ewgrad(con
             }
     };
 
+    constexpr int KOFF = V4 ? 4 : 1;
     const int num_units = (a.num_tiles + UT - 1) / UT;
     for (int unit = gw; unit < num_units; unit += nw) {
         const int t0 = unit * UT, t1 = min(a.num_tiles, t0 + UT);
         int e0 = a.tile_e0[t0], info = a.tile_info[t0];
-        RowRef r[4];   // entries t, t+4, 8+t, 12+t ; feature offset g folded in
+        RowRef r[4];   // entries t, t+4, 8+t, 12+t ; feature offset of lane g folded in
 #pragma unroll
-        for (int i = 0; i < 4; ++i) r[i] = make_ref<KP>(a, e0 + t + 4 * i, t + 4 * i < (info & 0xff), g, pol_s);
+        for (int i = 0; i < 4; ++i) r[i] = make_ref<KP>(a, e0 + t + 4 * i, t + 4 * i < (info & 0xff), KOFF * g, pol_s);
         for (int ti = t0; ti < t1; ++ti) {
             const int rel = info >> 8;
             if (rel != cur_rel) {
@@ -280,13 +287,32 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 32) ? 1 : 2) k_ewgrad(con
                 for (int ks = 0; ks < 2; ++ks) {
                     const RowRef& ra = r[2 * ks];       // K slot t
                     const RowRef& rb = r[2 * ks + 1];   // K slot t + 4
+                    if constexpr (V4) {
 #pragma unroll
-                    for (int m = 0; m < MT; ++m) {
-                        const bool c_lo = 16 * m + g < a.kin, c_hi = 16 * m + 8 + g < a.kin;
-                        av[ks][m][0] = c_lo ? ldg_hint(ra.p + 16 * m, pol_f) : 0.f;
-                        av[ks][m][1] = c_hi ? ldg_hint(ra.p + 16 * m + 8, pol_f) : 0.f;
-                        av[ks][m][2] = c_lo ? ldg_hint(rb.p + 16 * m, pol_f) : 0.f;
-                        av[ks][m][3] = c_hi ? ldg_hint(rb.p + 16 * m + 8, pol_f) : 0.f;
+                        for (int jb = 0; jb < MT / 2; ++jb) {
+                            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+                            if (32 * jb + 4 * g < a.kin) {
+                                va = ldg128_hint(reinterpret_cast<const float4*>(ra.p + 32 * jb), pol_f);
+                                vb = ldg128_hint(reinterpret_cast<const float4*>(rb.p + 32 * jb), pol_f);
+                            }
+                            av[ks][2 * jb][0] = va.x;       // m-tile 2jb  : row g   (K slot t)
+                            av[ks][2 * jb][1] = va.y;       //               row g+8
+                            av[ks][2 * jb + 1][0] = va.z;   // m-tile 2jb+1: row g
+                            av[ks][2 * jb + 1][1] = va.w;   //               row g+8
+                            av[ks][2 * jb][2] = vb.x;       // same rows, K slot t+4
+                            av[ks][2 * jb][3] = vb.y;
+                            av[ks][2 * jb + 1][2] = vb.z;
+                            av[ks][2 * jb + 1][3] = vb.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) {
+                            const bool c_lo = 16 * m + g < a.kin, c_hi = 16 * m + 8 + g < a.kin;
+                            av[ks][m][0] = c_lo ? ldg_hint(ra.p + 16 * m, pol_f) : 0.f;
+                            av[ks][m][1] = c_hi ? ldg_hint(ra.p + 16 * m + 8, pol_f) : 0.f;
+                            av[ks][m][2] = c_lo ? ldg_hint(rb.p + 16 * m, pol_f) : 0.f;
+                            av[ks][m][3] = c_hi ? ldg_hint(rb.p + 16 * m + 8, pol_f) : 0.f;
+                        }
                     }
 #pragma unroll
                     for (int n = 0; n < NT; ++n) {
@@ -303,7 +329,8 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 32) ? 1 : 2) k_ewgrad(con
                 e0 = a.tile_e0[ti + 1];
                 info = a.tile_info[ti + 1];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) r[i] = make_ref<KP>(a, e0 + t + 4 * i, t + 4 * i < (info & 0xff), g, pol_s);
+                for (int i = 0; i < 4; ++i)
+                    r[i] = make_ref<KP>(a, e0 + t + 4 * i, t + 4 * i < (info & 0xff), KOFF * g, pol_s);
             }
             if (!wanted) continue;
 #pragma unroll
@@ -378,7 +405,7 @@ int run_etile(const ETileArgs& a, bool relu, bool v4, int num_sms, cudaStream_t 
 }
 
 template <int KT, int NT>
-int run_ewgrad(const ETileArgs& a, bool relu, int num_sms, cudaStream_t st) {
+int run_ewgrad(const ETileArgs& a, bool relu, bool v4, int num_sms, cudaStream_t st) {
     auto launch = [&](auto kern) -> int {
         int per_sm = 1;
         RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EW * 32, 0));
@@ -389,8 +416,14 @@ int run_ewgrad(const ETileArgs& a, bool relu, int num_sms, cudaStream_t st) {
         RGCN_CUDA(cudaGetLastError());
         return 0;
     };
-    if (relu) return launch(k_ewgrad<KT, NT, true>);
-    return launch(k_ewgrad<KT, NT, false>);
+    if constexpr (KT >= 4) {
+        if (v4) {
+            if (relu) return launch(k_ewgrad<KT, NT, true, true>);
+            return launch(k_ewgrad<KT, NT, false, true>);
+        }
+    }
+    if (relu) return launch(k_ewgrad<KT, NT, true, false>);
+    return launch(k_ewgrad<KT, NT, false, false>);
 }
 
 #define RGCN_DISPATCH_E(FN, kp, np, ...)                                          \
@@ -428,7 +461,8 @@ bool etile_vec4_ok(const float* feat, int64_t ldf, int kin, const float* aux) {
         const char* e = getenv("RGCN_B200_VEC4");
         off = (e && e[0] == '0') ? 1 : 0;
     }
-    return !off && ldf % 4 == 0 && kin % 4 == 0 && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)aux & 15) == 0;
+    // rows may be wider than the logical width (zero-padded mirror): whole quads must stay inside a row
+    return !off && ldf % 4 == 0 && ((kin + 3) & ~3) <= ldf && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)aux & 15) == 0;
 }
 
 bool etile_enabled() {   // RGCN_B200_ETILE=0 selects the staged (shared-memory ring) kernels instead
@@ -479,7 +513,7 @@ int launch_ewgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st) {
     a.gbias = p.gbias;
     ProfScope prof(TAG_WGRAD, p.kin, p.nout, st);
     note_launch(1);
-    RGCN_DISPATCH_E(run_ewgrad, p.kp, p.np, a, p.relu_in, num_sms, st);
+    RGCN_DISPATCH_E(run_ewgrad, p.kp, p.np, a, p.relu_in, p.vec4, num_sms, st);
 }
 
 }  // namespace rgcn

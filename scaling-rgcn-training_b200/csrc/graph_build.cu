@@ -565,8 +565,8 @@ extern "C" int rgcn_graph_create_part(const int64_t* src, int64_t src_stride, co
     g->n_own = own_hi - own_lo;
     cudaGetDevice(&g->device);
     cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, g->device);
-    g->split_threshold = split_threshold > 0 ? split_threshold : 32;
-    g->chunk_size = chunk_size > 0 ? chunk_size : 256;
+    g->split_threshold = split_threshold > 0 ? split_threshold : 16;
+    g->chunk_size = chunk_size > 0 ? chunk_size : 64;
     int64_t nr = range_nodes > 0 ? range_nodes : 16384;
     // small graphs: one range (pure relation-major); large: blocked so accumulate targets stay L2-hot
     if (nr >= g->n_own) nr = g->n_own;

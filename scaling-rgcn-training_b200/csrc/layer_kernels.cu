@@ -668,6 +668,19 @@ __global__ void __launch_bounds__(256) k_copy_cols(const float* __restrict__ src
     }
 }
 
+// dst[r][c] = c < cols ? src[r][c] : 0 for c < ldd  (16-byte aligned mirror of an odd-width matrix)
+__global__ void __launch_bounds__(256) k_pad_rows(const float* __restrict__ src, int64_t lds, int cols,
+                                                  float* __restrict__ dst, int64_t ldd, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * 8;
+    for (int64_t r = wid; r < n; r += nw) {
+        const float* sp = src + r * lds;
+        float* dp = dst + r * ldd;
+        for (int c = lane; c < (int)ldd; c += 32) dp[c] = c < cols ? __ldg(sp + c) : 0.f;
+    }
+}
+
 __global__ void k_relu_mask(float* __restrict__ gr, int64_t ldg, const float* __restrict__ pre, int64_t ldp, int64_t n,
                             int cols) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -884,6 +897,15 @@ int launch_copy_cols(const float* src, int64_t lds, float* dst, int64_t ldd, int
     ProfScope prof(TAG_COPY, cols, 0, st);
     note_launch(1);
     k_copy_cols<<<(int)std::min<int64_t>((n + 7) / 8, 148 * 16), 256, 0, st>>>(src, lds, dst, ldd, n, cols);
+    RGCN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_pad_rows(const float* src, int64_t lds, int cols, float* dst, int64_t ldd, int64_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    ProfScope prof(TAG_COPY, cols, (int)ldd, st);
+    note_launch(1);
+    k_pad_rows<<<(int)std::min<int64_t>((n + 7) / 8, 148 * 16), 256, 0, st>>>(src, lds, cols, dst, ldd, n);
     RGCN_CUDA(cudaGetLastError());
     return 0;
 }

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'librgcn_b200.so')
 EXPORTS = (
     'rgcn_last_error', 'rgcn_abi_version', 'rgcn_graph_create', 'rgcn_graph_create_part', 'rgcn_graph_destroy', 'rgcn_graph_query',
     'rgcn_graph_export', 'rgcn_layer_workspace_bytes', 'rgcn_layer_fwd', 'rgcn_layer_bwd', 'rgcn_map_gather',
-    'rgcn_kernel_launch_count', 'rgcn_profile_enable', 'rgcn_profile_collect',
+    'rgcn_kernel_launch_count', 'rgcn_profile_enable', 'rgcn_profile_collect', 'rgcn_pad_rows',
 )
 
 BRC_FWD, BRC_BWD, BRC_FWD_REL = 0, 1, 2
@@ -65,6 +65,8 @@ def load():
     lib.rgcn_layer_bwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, i64, vp, i64, i32, vp, i64, vp, vp, vp, u32, vp, i64, vp]
     lib.rgcn_map_gather.restype = C.c_int
     lib.rgcn_map_gather.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i32, i64, i32, i32, vp, vp]
+    lib.rgcn_pad_rows.restype = C.c_int
+    lib.rgcn_pad_rows.argtypes = [vp, i64, i32, vp, i64, i64, vp]
     lib.rgcn_kernel_launch_count.restype = i64
     lib.rgcn_kernel_launch_count.argtypes = []
     lib.rgcn_profile_enable.restype = C.c_int

@@ -11,6 +11,7 @@ re-assignment keep working.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -24,6 +25,9 @@ def _glorot_(t: Tensor) -> None:   # PyG inits.glorot
     a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
     with torch.no_grad():
         t.uniform_(-a, a)
+
+
+_PAD_WIDE = os.environ.get('RGCN_B200_PAD', '1') != '0'
 
 
 def _ptr(t: Optional[Tensor]) -> int:
@@ -61,6 +65,16 @@ class _RGCNLayerFn(torch.autograd.Function):
         r, fin_w, fout = weight.shape
         if fin_w != fin or r != graph.num_relations:
             raise ValueError('RGCNConv: weight shape does not match input / num_relations')
+        if fin > 32 and (x.stride(0) % 4 != 0 or x.data_ptr() % 16 != 0) and _PAD_WIDE:
+            # odd-width wide rows (the reference's emb = 63): gather from a zero-padded 16-byte
+            # addressable mirror (one streaming copy) so the kernels can use 128-bit row loads;
+            # the mirror is what backward re-gathers, the caller's tensor is not kept
+            ldp = (fin + 3) // 4 * 4
+            xp = torch.empty((x.size(0), ldp), dtype=torch.float32, device=x.device)
+            with torch.cuda.device(x.device):
+                _lib.check(lib.rgcn_pad_rows(x.data_ptr(), x.stride(0), fin, xp.data_ptr(), ldp, x.size(0),
+                                             _stream(x.device)), 'rgcn_pad_rows')
+            x = xp
         out = torch.empty((graph.num_owned, fout), dtype=torch.float32, device=x.device)
         ws_bytes = graph.workspace_bytes(fin, fout, False)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
@@ -69,7 +83,7 @@ class _RGCNLayerFn(torch.autograd.Function):
                                     _ptr(bias_c), out.data_ptr(), out.stride(0), fout, flags, ws.data_ptr(), ws_bytes,
                                     _stream(x.device))
         _lib.check(rc, 'rgcn_layer_fwd')
-        ctx.graph, ctx.flags, ctx.comm = graph, flags, comm
+        ctx.graph, ctx.flags, ctx.comm, ctx.fin = graph, flags, comm, fin
         ctx.has_root, ctx.has_bias = root is not None, bias is not None
         ctx.save_for_backward(x, weight, root_c if root_c is not None else x.new_empty(0))
         return out
@@ -84,7 +98,7 @@ class _RGCNLayerFn(torch.autograd.Function):
         need_root = need_root and ctx.has_root
         need_bias = need_bias and ctx.has_bias
         gout = gout.contiguous()
-        n, fin = x.shape
+        fin = ctx.fin              # x may be the zero-padded mirror (wider than fin)
         fout = weight.size(2)
         dev = x.device
         comm = ctx.comm

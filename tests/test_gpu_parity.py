@@ -47,7 +47,7 @@ def _check_brc(g, which, want):
 def test_graph_build_bit_exact(name, nr, t, ch):
     ei, et, n, r = golden_graph(name)
     g = RGCNGraph(ei.to(DEV), et.to(DEV), n, r, range_nodes=nr, split_threshold=t, chunk_size=ch)
-    nr_eff, t_eff, ch_eff = (nr or 16384), (t or 32), (ch or 256)
+    nr_eff, t_eff, ch_eff = (nr or 16384), (t or 16), (ch or 64)
     src, dst, rel = ei[0].numpy(), ei[1].numpy(), et.numpy()
     fwd, bwd = csr_oracle.build_graph(src, dst, rel, n, r, nr_eff, t_eff, ch_eff)
     _check_brc(g, _lib.BRC_FWD, fwd)

@@ -20,3 +20,12 @@ for v in "$@"; do
     nr64k) run nr64k RGCN_B200_RANGE_NODES=65536;;
   esac
 done
+for v in "$@"; do
+  case $v in
+    t8) run t8 RGCN_B200_SPLIT=8;;
+    t16) run t16 RGCN_B200_SPLIT=16;;
+    t64) run t64 RGCN_B200_SPLIT=64;;
+    t16c64) run t16c64 RGCN_B200_SPLIT=16 RGCN_B200_CHUNK=64;;
+    t32c64) run t32c64 RGCN_B200_SPLIT=32 RGCN_B200_CHUNK=64;;
+  esac
+done
