@@ -110,51 +110,63 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
     const uint64_t pol_s = policy_evict_first();
     const uint64_t pol_f =
         (uint64_t)a.n_rows * (uint64_t)a.ldf * 4ull <= (112ull << 20) ? policy_evict_last() : policy_evict_normal();
+    constexpr int KOFF = V4 ? 4 : 1;   // lane's column offset inside a row: 4t (vector) or t
+    struct TileRef {   // the two rows of this lane in one tile
+        RowRef g8, h8;
+        int rel;
+    };
+    auto load_meta = [&](int ti) {
+        TileRef r;
+        const int e0 = a.tile_e0[ti], info = a.tile_info[ti];
+        r.rel = info >> 8;
+        r.g8 = make_ref<KP>(a, e0 + g, g < (info & 0xff), KOFF * t, pol_s);
+        r.h8 = make_ref<KP>(a, e0 + g + 8, g + 8 < (info & 0xff), KOFF * t, pol_s);
+        return r;
+    };
+    // A fragments: raw loads (all independent); the arithmetic happens one tile later
+    auto load_rows = [&](const TileRef& r, float (&av)[KT][4]) {
+        if constexpr (V4) {
+#pragma unroll
+            for (int j = 0; j < KT / 2; ++j) {
+                float4 vg = make_float4(0.f, 0.f, 0.f, 0.f), vh = vg;
+                if (16 * j + 4 * t < a.kin) {
+                    vg = ldg128_hint(reinterpret_cast<const float4*>(r.g8.p + 16 * j), pol_f);
+                    vh = ldg128_hint(reinterpret_cast<const float4*>(r.h8.p + 16 * j), pol_f);
+                }
+                av[2 * j][0] = vg.x;       // step 2j  : slot t   <- col 16j+4t
+                av[2 * j][2] = vg.y;       //            slot t+4 <- col 16j+4t+1
+                av[2 * j + 1][0] = vg.z;   // step 2j+1: slot t   <- col 16j+4t+2
+                av[2 * j + 1][2] = vg.w;   //            slot t+4 <- col 16j+4t+3
+                av[2 * j][1] = vh.x;
+                av[2 * j][3] = vh.y;
+                av[2 * j + 1][1] = vh.z;
+                av[2 * j + 1][3] = vh.w;
+            }
+        } else {
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) {
+                const bool c_lo = 8 * kt + t < a.kin, c_hi = 8 * kt + 4 + t < a.kin;
+                av[kt][0] = c_lo ? ldg_hint(r.g8.p + 8 * kt, pol_f) : 0.f;
+                av[kt][1] = c_lo ? ldg_hint(r.h8.p + 8 * kt, pol_f) : 0.f;
+                av[kt][2] = c_hi ? ldg_hint(r.g8.p + 8 * kt + 4, pol_f) : 0.f;
+                av[kt][3] = c_hi ? ldg_hint(r.h8.p + 8 * kt + 4, pol_f) : 0.f;
+            }
+        }
+    };
     const int num_units = (a.num_tiles + UT - 1) / UT;
     for (int unit = gw; unit < num_units; unit += nw) {
         const int t0 = unit * UT, t1 = min(a.num_tiles, t0 + UT);
-        int e0 = a.tile_e0[t0], info = a.tile_info[t0];
-        constexpr int KOFF = V4 ? 4 : 1;   // lane's column offset inside a row: 4t (vector) or t
-        RowRef rg = make_ref<KP>(a, e0 + g, g < (info & 0xff), KOFF * t, pol_s);
-        RowRef rh = make_ref<KP>(a, e0 + g + 8, g + 8 < (info & 0xff), KOFF * t, pol_s);
+        // pipeline: indices two tiles ahead, rows one tile ahead of the tensor-pipe work
+        TileRef cur = load_meta(t0), nxt = cur;
+        if (t0 + 1 < t1) nxt = load_meta(t0 + 1);
+        float av[KT][4], avn[KT][4];
+        load_rows(cur, av);
         for (int ti = t0; ti < t1; ++ti) {
-            const int rel = info >> 8;
-            // A fragments: raw loads first (all independent), arithmetic afterwards
-            float av[KT][4];
-            if constexpr (V4) {
-#pragma unroll
-                for (int j = 0; j < KT / 2; ++j) {
-                    float4 vg = make_float4(0.f, 0.f, 0.f, 0.f), vh = vg;
-                    if (16 * j + 4 * t < a.kin) {
-                        vg = ldg128_hint(reinterpret_cast<const float4*>(rg.p + 16 * j), pol_f);
-                        vh = ldg128_hint(reinterpret_cast<const float4*>(rh.p + 16 * j), pol_f);
-                    }
-                    av[2 * j][0] = vg.x;       // step 2j  : slot t   <- col 16j+4t
-                    av[2 * j][2] = vg.y;       //            slot t+4 <- col 16j+4t+1
-                    av[2 * j + 1][0] = vg.z;   // step 2j+1: slot t   <- col 16j+4t+2
-                    av[2 * j + 1][2] = vg.w;   //            slot t+4 <- col 16j+4t+3
-                    av[2 * j][1] = vh.x;
-                    av[2 * j][3] = vh.y;
-                    av[2 * j + 1][1] = vh.z;
-                    av[2 * j + 1][3] = vh.w;
-                }
-            } else {
-#pragma unroll
-                for (int kt = 0; kt < KT; ++kt) {
-                    const bool c_lo = 8 * kt + t < a.kin, c_hi = 8 * kt + 4 + t < a.kin;
-                    av[kt][0] = c_lo ? ldg_hint(rg.p + 8 * kt, pol_f) : 0.f;
-                    av[kt][1] = c_lo ? ldg_hint(rh.p + 8 * kt, pol_f) : 0.f;
-                    av[kt][2] = c_hi ? ldg_hint(rg.p + 8 * kt + 4, pol_f) : 0.f;
-                    av[kt][3] = c_hi ? ldg_hint(rh.p + 8 * kt + 4, pol_f) : 0.f;
-                }
-            }
-            const RowRef cg = rg, ch = rh;
-            if (ti + 1 < t1) {   // next tile's indices are in flight while this tile computes
-                e0 = a.tile_e0[ti + 1];
-                info = a.tile_info[ti + 1];
-                rg = make_ref<KP>(a, e0 + g, g < (info & 0xff), KOFF * t, pol_s);
-                rh = make_ref<KP>(a, e0 + g + 8, g + 8 < (info & 0xff), KOFF * t, pol_s);
-            }
+            const int rel = cur.rel;
+            const RowRef cg = cur.g8, ch = cur.h8;
+            if (ti + 1 < t1) load_rows(nxt, avn);
+            TileRef nn = nxt;
+            if (ti + 2 < t1) nn = load_meta(ti + 2);
             const float4* wf = a.wfrag + (int64_t)rel * (KT * NT * 32) + lane;
             float d[NT][4];
 #pragma unroll
@@ -217,6 +229,12 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
                     }
                 }
             }
+            cur = nxt;
+            nxt = nn;
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) av[kt][i] = avn[kt][i];
         }
     }
 }
@@ -267,9 +285,12 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 32) ? 1 : 2) k_ewgrad(con
     };
 
     constexpr int KOFF = V4 ? 4 : 1;
-    const int num_units = (a.num_tiles + UT - 1) / UT;
-    for (int unit = gw; unit < num_units; unit += nw) {
-        const int t0 = unit * UT, t1 = min(a.num_tiles, t0 + UT);
+    // contiguous span of tiles per warp (tiles cost the same): D stays in registers across the whole
+    // span and is flushed only where the relation changes -> a few atomics per warp, not per unit
+    const int per = (a.num_tiles + nw - 1) / nw;
+    {
+        const int t0 = min(a.num_tiles, gw * per), t1 = min(a.num_tiles, gw * per + per);
+        if (t0 >= t1) return;
         int e0 = a.tile_e0[t0], info = a.tile_info[t0];
         RowRef r[4];   // entries t, t+4, 8+t, 12+t ; feature offset of lane g folded in
 #pragma unroll
