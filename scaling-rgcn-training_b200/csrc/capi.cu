@@ -98,11 +98,15 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     WsCarver ws(workspace, workspace_bytes);
     float4* wfrag = (float4*)ws.take<float>((int64_t)(g->R + 1) * kp * np * 2);
     float* aux = ws.take<float>((int64_t)g->brc[RGCN_BRC_FWD].num_chunks * kp);
-    const bool direct = direct_target(out, ldo, fout);
+    // accumulate straight into `out` when its rows are 16-byte addressable and hold whole quads
+    // (ldo == fout % 4 == 0, or a caller-padded row: ldo % 4 == 0 and ldo >= ceil4(fout); the pad
+    // columns then receive zeros); otherwise through a padded buffer + column copy
+    const int fout4 = (fout + 3) & ~3;
+    const bool direct = ldo % 4 == 0 && ldo >= fout4 && ((uintptr_t)out & 15) == 0;
     float* target = direct ? out : ws.take<float>((int64_t)g->n_own * np);
     if (!ws.ok) return fail(RGCN_ERR_WORKSPACE, "rgcn_layer_fwd: workspace too small (see rgcn_layer_workspace_bytes)");
     const int64_t tld = direct ? ldo : np;
-    const int tn = direct ? fout : np;
+    const int tn = direct ? fout4 : np;
     int rc;
     // wide rows that are not 16-byte addressable (Fin = 63) go through the staged kernels; everything
     // else is gathered straight into MMA fragments
@@ -119,7 +123,7 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     p.aux = aux;
     p.wfrag = wfrag;
     p.bias = bias; p.nbias = fout;
-    p.out = target; p.ldo = tld; p.nout = tn;
+    p.out = target; p.ldo = tld; p.nout = tn; p.tag_out = fout;
     p.kp = kp; p.np = np;
     p.relu_in = relu;
     p.vec4 = v4;
@@ -219,7 +223,7 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
         p.aux = gaux;
         p.wfrag = wtfrag;
         p.bias = nullptr; p.nbias = 0;
-        p.out = target; p.ldo = tld; p.nout = direct ? fin : kp;
+        p.out = target; p.ldo = tld; p.nout = direct ? fin : kp; p.tag_out = fin;
         p.kp = np; p.np = kp;
         p.relu_in = false;
         p.transposed = true;

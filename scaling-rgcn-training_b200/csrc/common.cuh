@@ -105,6 +105,7 @@ struct TilePass {
     bool relu_in;
     bool transposed;                                // dL/dx pass (profiling tag only)
     bool vec4;                                      // entry-tile kernel: 16-byte row loads, wfrag prepared with perm
+    int tag_out;                                    // logical output width (profiling tag)
 };
 int launch_chunk_prepass(const TilePass& p, cudaStream_t st);
 int launch_tile_pass(const TilePass& p, int num_sms, cudaStream_t st);

@@ -110,6 +110,9 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
     const uint64_t pol_s = policy_evict_first();
     const uint64_t pol_f =
         (uint64_t)a.n_rows * (uint64_t)a.ldf * 4ull <= (112ull << 20) ? policy_evict_last() : policy_evict_normal();
+    constexpr bool BREG = (KT * NT <= 4);
+    float4 bfrag[BREG ? KT * NT : 1];
+    int breg_rel = -1;
     constexpr int KOFF = V4 ? 4 : 1;   // lane's column offset inside a row: 4t (vector) or t
     struct TileRef {   // the two rows of this lane in one tile
         RowRef g8, h8;
@@ -168,6 +171,13 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
             TileRef nn = nxt;
             if (ti + 2 < t1) nn = load_meta(ti + 2);
             const float4* wf = a.wfrag + (int64_t)rel * (KT * NT * 32) + lane;
+            if constexpr (BREG) {   // few fragments: keep the current relation's in registers
+                if (rel != breg_rel) {
+#pragma unroll
+                    for (int i = 0; i < KT * NT; ++i) bfrag[i] = __ldg(wf + i * 32);
+                    breg_rel = rel;
+                }
+            }
             float d[NT][4];
 #pragma unroll
             for (int n = 0; n < NT; ++n) d[n][0] = d[n][1] = d[n][2] = d[n][3] = 0.f;
@@ -191,7 +201,9 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
                 split_fast(x3 * ch.w, ah[3], al[3]);
 #pragma unroll
                 for (int n = 0; n < NT; ++n) {
-                    const float4 bf = __ldg(wf + (kt * NT + n) * 32);
+                    float4 bf;
+                    if constexpr (BREG) bf = bfrag[kt * NT + n];
+                    else bf = __ldg(wf + (kt * NT + n) * 32);
                     const uint32_t bh0 = __float_as_uint(bf.x), bh1 = __float_as_uint(bf.y);
                     const uint32_t bl0 = __float_as_uint(bf.z), bl1 = __float_as_uint(bf.w);
                     mma_tf32(d[n], al[0], al[1], al[2], al[3], bh0, bh1);
@@ -511,7 +523,7 @@ int launch_etile_pass(const TilePass& p, int num_sms, cudaStream_t st) {
     a.out = p.out;
     a.ldo = p.ldo;
     a.nout = p.nout;
-    ProfScope prof(p.transposed ? TAG_TILE_BWD : TAG_TILE_FWD, p.kin, p.nout, st);
+    ProfScope prof(p.transposed ? TAG_TILE_BWD : TAG_TILE_FWD, p.kin, p.tag_out, st);
     note_launch(1);
     RGCN_DISPATCH_E(run_etile, p.kp, p.np, a, p.relu_in, p.vec4, num_sms, st);
 }

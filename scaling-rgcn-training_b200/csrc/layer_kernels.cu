@@ -674,10 +674,25 @@ __global__ void __launch_bounds__(256) k_pad_rows(const float* __restrict__ src,
     const int lane = threadIdx.x & 31;
     const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t nw = (int64_t)gridDim.x * 8;
-    for (int64_t r = wid; r < n; r += nw) {
-        const float* sp = src + r * lds;
-        float* dp = dst + r * ldd;
-        for (int c = lane; c < (int)ldd; c += 32) dp[c] = c < cols ? __ldg(sp + c) : 0.f;
+    for (int64_t r0 = wid * 4; r0 < n; r0 += nw * 4) {
+        float v[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = lane + 32 * j;
+                v[i][j] = (r0 + i < n && c < cols) ? __ldg(src + (r0 + i) * lds + c) : 0.f;
+            }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = lane + 32 * j;
+                if (r0 + i < n && c < (int)ldd) dst[(r0 + i) * ldd + c] = v[i][j];
+            }
+        for (int c = lane + 128; c < (int)ldd; c += 32)
+            for (int i = 0; i < 4; ++i)
+                if (r0 + i < n) dst[(r0 + i) * ldd + c] = c < cols ? __ldg(src + (r0 + i) * lds + c) : 0.f;
     }
 }
 
@@ -854,7 +869,7 @@ int launch_tile_pass(const TilePass& p, int num_sms, cudaStream_t st) {
     a.ldo = p.ldo;
     a.nout = p.nout;
     a.relu_in = p.relu_in ? 1 : 0;
-    ProfScope prof(p.transposed ? TAG_TILE_BWD : TAG_TILE_FWD, p.kin, p.nout, st);
+    ProfScope prof(p.transposed ? TAG_TILE_BWD : TAG_TILE_FWD, p.kin, p.tag_out, st);
     note_launch(1);
     RGCN_DISPATCH_KN(run_tile, p.kp, p.np, a, num_sms, st);
 }
@@ -905,7 +920,7 @@ int launch_pad_rows(const float* src, int64_t lds, int cols, float* dst, int64_t
     if (n == 0) return 0;
     ProfScope prof(TAG_COPY, cols, (int)ldd, st);
     note_launch(1);
-    k_pad_rows<<<(int)std::min<int64_t>((n + 7) / 8, 148 * 16), 256, 0, st>>>(src, lds, cols, dst, ldd, n);
+    k_pad_rows<<<(int)std::min<int64_t>((n + 31) / 32, 148 * 8), 256, 0, st>>>(src, lds, cols, dst, ldd, n);
     RGCN_CUDA(cudaGetLastError());
     return 0;
 }

@@ -75,12 +75,16 @@ class _RGCNLayerFn(torch.autograd.Function):
                 _lib.check(lib.rgcn_pad_rows(x.data_ptr(), x.stride(0), fin, xp.data_ptr(), ldp, x.size(0),
                                              _stream(x.device)), 'rgcn_pad_rows')
             x = xp
-        out = torch.empty((graph.num_owned, fout), dtype=torch.float32, device=x.device)
+        # rows padded to whole quads so the kernel can accumulate in place with 128-bit atomics; the
+        # caller sees the [:, :fout] view (no column copy)
+        ldo = (fout + 3) // 4 * 4
+        out_buf = torch.empty((graph.num_owned, ldo), dtype=torch.float32, device=x.device)
+        out = out_buf[:, :fout] if ldo != fout else out_buf
         ws_bytes = graph.workspace_bytes(fin, fout, False)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         with torch.cuda.device(x.device):
             rc = lib.rgcn_layer_fwd(graph.handle, x.data_ptr(), x.stride(0), fin, weight.data_ptr(), _ptr(root_c),
-                                    _ptr(bias_c), out.data_ptr(), out.stride(0), fout, flags, ws.data_ptr(), ws_bytes,
+                                    _ptr(bias_c), out_buf.data_ptr(), ldo, fout, flags, ws.data_ptr(), ws_bytes,
                                     _stream(x.device))
         _lib.check(rc, 'rgcn_layer_fwd')
         ctx.graph, ctx.flags, ctx.comm, ctx.fin = graph, flags, comm, fin
