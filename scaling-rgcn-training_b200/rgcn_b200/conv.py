@@ -106,23 +106,40 @@ class _RGCNLayerFn(torch.autograd.Function):
         fout = weight.size(2)
         dev = x.device
         comm = ctx.comm
-        gout_all = comm.all_gather_rows(gout) if (comm is not None and need_x) else None
+        # partitioned graph: the all-gather of gout (needed only by dL/dx) is started first and
+        # overlaps the dL/dW pass, which reads the owned rows only
+        gout_all, work = None, None
+        if comm is not None and need_x:
+            if hasattr(comm, 'all_gather_rows_async'):
+                gout_all, work = comm.all_gather_rows_async(gout)
+            else:
+                gout_all = comm.all_gather_rows(gout)
         gx = torch.empty((graph.num_owned, fin), dtype=torch.float32, device=dev) if need_x else None
         gw = torch.empty_like(weight) if need_w else None
         groot = torch.empty((fin, fout), dtype=torch.float32, device=dev) if need_root else None
         gbias = torch.empty((fout,), dtype=torch.float32, device=dev) if need_bias else None
-        if need_x or need_w or need_root or need_bias:
+
+        def call(gx_t, gw_t, groot_t, gbias_t):
             ws_bytes = graph.workspace_bytes(fin, fout, True)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             with torch.cuda.device(dev):
                 rc = lib.rgcn_layer_bwd(graph.handle, x.data_ptr(), x.stride(0), fin, weight.data_ptr(), _ptr(root),
                                         gout.data_ptr(), gout.stride(0), _ptr(gout_all),
-                                        gout_all.stride(0) if gout_all is not None else 0, fout, _ptr(gx), fin,
-                                        _ptr(gw), _ptr(groot), _ptr(gbias), ctx.flags, ws.data_ptr(), ws_bytes,
+                                        gout_all.stride(0) if gout_all is not None else 0, fout, _ptr(gx_t), fin,
+                                        _ptr(gw_t), _ptr(groot_t), _ptr(gbias_t), ctx.flags, ws.data_ptr(), ws_bytes,
                                         _stream(dev))
             _lib.check(rc, 'rgcn_layer_bwd')
-            if comm is not None:
-                comm.all_reduce_sum_([t for t in (gw, groot, gbias) if t is not None])
+
+        if work is not None and (need_w or need_root or need_bias):
+            call(None, gw, groot, gbias)      # runs while the all-gather is in flight
+            work.wait()
+            call(gx, None, None, None)
+        elif need_x or need_w or need_root or need_bias:
+            if work is not None:
+                work.wait()
+            call(gx, gw, groot, gbias)
+        if comm is not None:
+            comm.all_reduce_sum_([t for t in (gw, groot, gbias) if t is not None])
         return gx, gw, groot, gbias, None, None, None
 
 

@@ -49,6 +49,20 @@ class RowComm:
         self.lo, self.hi = self.ranges[self.rank]
         self.bytes_gathered = 0
 
+    def all_gather_rows_async(self, t: Tensor):
+        """Start the all-gather on the communicator's stream; returns (out, work). The caller runs
+        independent kernels (dL/dW needs only the owned gout rows) and calls work.wait() before the
+        first consumer of `out` — the transfer then overlaps that compute."""
+        n_own, f = t.shape
+        if n_own != self.chunk:
+            pad = t.new_zeros((self.chunk, f))
+            pad[:n_own] = t
+            t = pad
+        out = t.new_empty((self.world * self.chunk, f))
+        work = dist.all_gather_into_tensor(out, t.contiguous(), group=self.group, async_op=True)
+        self.bytes_gathered += out.numel() * out.element_size()
+        return out, work
+
     def all_gather_rows(self, t: Tensor) -> Tensor:
         """[n_owned, F] on every rank -> [world*chunk, F]; row i is node i for i < num_nodes."""
         n_own, f = t.shape
