@@ -51,6 +51,7 @@ int64_t fwd_ws(const rgcn_graph* g, int fin, int fout) {
     if (!kp || !np) return 256;
     int64_t b = 0;
     b += ws_take((int64_t)(g->R + 1) * kp * np * 2, 4);                      // wfrag (hi,lo)
+    b += ws_take((int64_t)(g->R + 1) * kp * np, 4);                          // wfrag2 (fp32 pairs)
     b += ws_take((int64_t)g->brc[RGCN_BRC_FWD].num_chunks * kp, 4);          // chunk rows
     b += ws_take((int64_t)g->n_own * np, 4);                                 // padded accumulate target
     return b;
@@ -62,6 +63,7 @@ int64_t bwd_ws(const rgcn_graph* g, int fin, int fout) {
     int64_t b = 0;
     b += ws_take((int64_t)g->brc[RGCN_BRC_FWD_REL].num_chunks * kp, 4);      // chunk rows of x (dW pass)
     b += ws_take((int64_t)(g->R + 1) * kp * np * 2, 4);                      // W^T frags
+    b += ws_take((int64_t)(g->R + 1) * kp * np, 4);                          // W^T frags, fp32 pairs
     b += ws_take((int64_t)g->brc[RGCN_BRC_BWD].num_chunks * np, 4);          // chunk rows of gout (dx pass)
     b += ws_take((int64_t)g->n_own * kp, 4);                                 // padded dx target
     return b;
@@ -97,6 +99,7 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     }
     WsCarver ws(workspace, workspace_bytes);
     float4* wfrag = (float4*)ws.take<float>((int64_t)(g->R + 1) * kp * np * 2);
+    float2* wfrag2 = (float2*)ws.take<float>((int64_t)(g->R + 1) * kp * np);
     float* aux = ws.take<float>((int64_t)g->brc[RGCN_BRC_FWD].num_chunks * kp);
     // accumulate straight into `out` when its rows are 16-byte addressable and hold whole quads
     // (ldo == fout % 4 == 0, or a caller-padded row: ldo % 4 == 0 and ldo >= ceil4(fout); the pad
@@ -113,7 +116,7 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     const bool v4ok = etile_vec4_ok(x, ldx, fin, aux);
     const bool et = etile_choice(kp, v4ok);
     const bool v4 = et && v4ok;
-    WPrep wp{weight, root, g->R, fin, fout, kp, np, false, v4, wfrag};
+    WPrep wp{weight, root, g->R, fin, fout, kp, np, false, v4, wfrag, wfrag2};
     if ((rc = launch_wprep(wp, st))) return rc;
     TilePass p{};
     p.brc = &g->brc[RGCN_BRC_FWD];
@@ -122,6 +125,7 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     p.feat = x; p.ldf = ldx; p.kin = fin;
     p.aux = aux;
     p.wfrag = wfrag;
+    p.wfrag2 = wfrag2;
     p.bias = bias; p.nbias = fout;
     p.out = target; p.ldo = tld; p.nout = tn; p.tag_out = fout;
     p.kp = kp; p.np = np;
@@ -186,6 +190,7 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     WsCarver ws(workspace, workspace_bytes);
     float* xaux = ws.take<float>((int64_t)g->brc[RGCN_BRC_FWD_REL].num_chunks * kp);
     float4* wtfrag = (float4*)ws.take<float>((int64_t)(g->R + 1) * kp * np * 2);
+    float2* wtfrag2 = (float2*)ws.take<float>((int64_t)(g->R + 1) * kp * np);
     float* gaux = ws.take<float>((int64_t)g->brc[RGCN_BRC_BWD].num_chunks * np);
     const bool direct = gx && direct_target(gx, ldgx, fin);
     float* target = gx ? (direct ? gx : ws.take<float>((int64_t)g->n_own * kp)) : nullptr;
@@ -213,7 +218,7 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
         const bool v4ok = etile_vec4_ok(gout_gather, ldgg, fout, gaux);
         const bool et = etile_choice(np, v4ok);
         const bool v4 = et && v4ok;
-        WPrep wp{weight, root, g->R, fin, fout, np, kp, true, v4, wtfrag};
+        WPrep wp{weight, root, g->R, fin, fout, np, kp, true, v4, wtfrag, wtfrag2};
         if ((rc = launch_wprep(wp, st))) return rc;
         const int64_t tld = direct ? ldgx : kp;
         TilePass p{};
@@ -222,6 +227,7 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
         p.feat = gout_gather; p.ldf = ldgg; p.kin = fout;
         p.aux = gaux;
         p.wfrag = wtfrag;
+        p.wfrag2 = wtfrag2;
         p.bias = nullptr; p.nbias = 0;
         p.out = target; p.ldo = tld; p.nout = direct ? fin : kp; p.tag_out = fin;
         p.kp = np; p.np = kp;

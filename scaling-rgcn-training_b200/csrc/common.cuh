@@ -99,6 +99,7 @@ struct TilePass {
     const float* feat; int64_t ldf; int kin;       // gathered rows
     float* aux;                                     // [num_chunks, kp] chunk rows (written by pre-pass)
     const float4* wfrag;                            // [(R+1), kp/8, np/8, 32] fragment-ordered hi/lo split
+    const float2* wfrag2;                           // same fragments, unsplit fp32 pairs (half the bytes)
     const float* bias; int nbias;                   // nullable, [nbias]
     float* out; int64_t ldo; int nout;              // accumulate target (zeroed by caller), nout % 4 == 0
     int kp, np;
@@ -118,6 +119,7 @@ struct WPrep {
     bool transpose;        // B[k][n] = W[n][k]
     bool perm;             // K order of the vector-load entry-tile kernel (see etile_kernels.cu)
     float4* wfrag;
+    float2* wfrag2;        // nullable: unsplit fp32 pairs in the same fragment order
 };
 int launch_wprep(const WPrep& p, cudaStream_t st);
 

@@ -43,6 +43,7 @@ struct ETileArgs {
     const float* aux;
     int64_t n_rows;
     const float4* wfrag;
+    const float2* wfrag2;
     const float* bias;
     int nbias;
     int self_rel;
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
             TileRef nn = nxt;
             if (ti + 2 < t1) nn = load_meta(ti + 2);
             const float4* wf = a.wfrag + (int64_t)rel * (KT * NT * 32) + lane;
+            const float2* wf2 = a.wfrag2 + (int64_t)rel * (KT * NT * 32) + lane;
             if constexpr (BREG) {   // few fragments: keep the current relation's in registers
                 if (rel != breg_rel) {
 #pragma unroll
@@ -201,11 +203,16 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
                 split_fast(x3 * ch.w, ah[3], al[3]);
 #pragma unroll
                 for (int n = 0; n < NT; ++n) {
-                    float4 bf;
-                    if constexpr (BREG) bf = bfrag[kt * NT + n];
-                    else bf = __ldg(wf + (kt * NT + n) * 32);
-                    const uint32_t bh0 = __float_as_uint(bf.x), bh1 = __float_as_uint(bf.y);
-                    const uint32_t bl0 = __float_as_uint(bf.z), bl1 = __float_as_uint(bf.w);
+                    uint32_t bh0, bh1, bl0, bl1;
+                    if constexpr (BREG) {
+                        const float4 bf = bfrag[kt * NT + n];
+                        bh0 = __float_as_uint(bf.x), bh1 = __float_as_uint(bf.y);
+                        bl0 = __float_as_uint(bf.z), bl1 = __float_as_uint(bf.w);
+                    } else {   // fp32 pairs from L1 (half the bytes of the pre-split form), split here
+                        const float2 b2 = __ldg(wf2 + (kt * NT + n) * 32);
+                        split_rn(b2.x, bh0, bl0);
+                        split_rn(b2.y, bh1, bl1);
+                    }
                     mma_tf32(d[n], al[0], al[1], al[2], al[3], bh0, bh1);
                     mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
                     mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
@@ -517,6 +524,7 @@ int launch_etile_pass(const TilePass& p, int num_sms, cudaStream_t st) {
     a.aux = p.aux ? p.aux : p.feat;
     a.n_rows = p.n_nodes;
     a.wfrag = p.wfrag;
+    a.wfrag2 = p.wfrag2;
     a.bias = p.bias;
     a.nbias = p.nbias;
     a.self_rel = p.self_rel;

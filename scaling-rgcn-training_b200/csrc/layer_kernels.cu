@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(256) k_chunk_sum(const int32_t* __restrict__ r
 //   B = W_rel (rows<fin, cols<fout) or its transpose; rel == R is the root matrix.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_wprep(const float* __restrict__ weight, const float* __restrict__ root, int R, int fin, int fout,
-                        int KT, int NT, int transpose, int perm, float4* __restrict__ wfrag) {
+                        int KT, int NT, int transpose, int perm, float4* __restrict__ wfrag,
+                        float2* __restrict__ wfrag2) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)(R + 1) * KT * NT * 32;
     if (i >= total) return;
@@ -265,6 +266,7 @@ __global__ void k_wprep(const float* __restrict__ weight, const float* __restric
     split_tf32(b[0], h0, l0);
     split_tf32(b[1], h1, l1);
     wfrag[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+    if (wfrag2) wfrag2[i] = make_float2(b[0], b[1]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -837,7 +839,7 @@ int launch_wprep(const WPrep& p, cudaStream_t st) {
     ProfScope prof(TAG_WPREP, p.fin, p.fout, st);
     note_launch(1);
     k_wprep<<<(int)((total + tpb - 1) / tpb), tpb, 0, st>>>(p.weight, p.root, p.R, p.fin, p.fout, KT, NT,
-                                                            p.transpose ? 1 : 0, p.perm ? 1 : 0, p.wfrag);
+                                                            p.transpose ? 1 : 0, p.perm ? 1 : 0, p.wfrag, p.wfrag2);
     RGCN_CUDA(cudaGetLastError());
     return 0;
 }
