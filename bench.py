@@ -278,6 +278,14 @@ def run_engine(args):
     agg = {}
     for name, dims, ms in recs:
         agg.setdefault((name, dims[0], dims[1]), []).append(ms)
+    # the self-loop (root + bias) launch belongs to the pass whose bytes include the N x (Fin + Fout) term
+    for (name, d0, d1), v in list(agg.items()):
+        if name == 'self_loop':
+            for host in ('tile_fwd', 'tile_dx'):
+                if (host, d0, d1) in agg and len(agg[(host, d0, d1)]) == len(v):
+                    agg[(host, d0, d1)] = [x + y for x, y in zip(agg[(host, d0, d1)], v)]
+                    del agg[(name, d0, d1)]
+                    break
     tot = {k: sum(v) for k, v in agg.items()}
     pb = {}
     for (fin, fout) in ((EMB, HIDDEN), (HIDDEN, CLASSES)):

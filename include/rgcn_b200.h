@@ -52,7 +52,7 @@ enum {
     RGCN_Q_NUM_SEGMENTS = 3, RGCN_Q_NUM_ENTRIES = 4, RGCN_Q_NUM_CHUNKS = 5,
     RGCN_Q_NUM_GROUPS = 6, RGCN_Q_NUM_BATCHES = 7, RGCN_Q_RANGE_NODES = 8,
     RGCN_Q_DEVICE_BYTES = 9, RGCN_Q_NUM_OWNED = 10, RGCN_Q_OWN_LO = 11, RGCN_Q_NUM_ENTRIES0 = 12,
-    RGCN_Q_NUM_TILES = 13
+    RGCN_Q_NUM_TILES = 13, RGCN_Q_NUM_TILES_NOSELF = 14
 };
 
 /* rgcn_graph_export array ids (element type in brackets) */
@@ -145,7 +145,8 @@ int rgcn_pad_rows(const float* src, int64_t lds, int32_t cols, float* dst, int64
  * pair on its own stream; rgcn_profile_collect synchronises those events, returns up to
  * max_records (tag, dims[2], milliseconds) records and clears the log.  Tags: 1 weight-fragment
  * prep, 2 chunk pre-pass, 3 forward tile pass, 4 dL/dx tile pass, 5 dL/dW pass, 6 column copy,
- * 7 ReLU mask, 8 generic kernels, 9 map gather.  dims = (gathered width, output width). */
+ * 7 ReLU mask, 8 generic kernels, 9 map gather, 10 self-loop (root + bias) pass.
+ * dims = (gathered width, output width). */
 int64_t rgcn_kernel_launch_count(void);
 int rgcn_profile_enable(int32_t on);
 int rgcn_profile_collect(int32_t* tags, int32_t* dims, float* ms, int32_t max_records, int32_t* n_out);

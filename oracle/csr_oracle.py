@@ -10,7 +10,8 @@ edges" is a testable property (``edges_from_brc``).
 
 Blocked relational CSR (BRC), spec shared with scaling-rgcn-training_b200/csrc/graph_build.cu:
   entries   the E edges plus one self-loop per node (relation id R, weight 1)  -> root term
-  key       (owner // NR) * (R+1) * NR + rel * NR + owner % NR ; stable sort
+  key       (owner // NR) * (R+1) * NR + rel * NR + owner % NR ; self loops after all ranges, by owner;
+            stable sort
   segment   maximal run of equal key = one (relation, owner) pair; cnt = multiplicity
   weight    1/cnt of the FORWARD segment of the entry (per-(relation, dst) mean normaliser)
   chunking  segments with cnt > T are replaced by ceil(cnt/CH) virtual entries N+chunk_id
@@ -53,7 +54,9 @@ def build_brc(own, gat, rel, n, r, nr, t, ch, w_edge=None, lo=0, hi=None):
     w_entry = np.concatenate([np.asarray(w_edge, dtype=np.float32)[sel], np.ones(n_own, dtype=np.float32)])
     e = int(sel.sum())
     n = n_own
-    key = (own2 // nr) * ((r + 1) * nr) + rel2 * nr + own2 % nr
+    nranges = max((n + nr - 1) // nr, 1)
+    self_base = nranges * (r + 1) * nr            # self loops (relation r) sort after every range, by owner
+    key = np.where(rel2 == r, self_base + own2, (own2 // nr) * ((r + 1) * nr) + rel2 * nr + own2 % nr)
     perm = np.argsort(key, kind='stable')
     skey = key[perm]
     e2 = e + n
@@ -65,9 +68,10 @@ def build_brc(own, gat, rel, n, r, nr, t, ch, w_edge=None, lo=0, hi=None):
     seg_ptr0 = np.concatenate([seg_ptr0, [e2]])
     cnt = np.diff(seg_ptr0)
     seg_key = skey[seg_ptr0[:-1]]
-    seg_range = seg_key // ((r + 1) * nr)
-    seg_rel = (seg_key // nr) % (r + 1)
-    seg_own = seg_range * nr + seg_key % nr
+    is_self = seg_key >= self_base
+    seg_rel = np.where(is_self, r, (seg_key // nr) % (r + 1))
+    seg_own = np.where(is_self, seg_key - self_base, (seg_key // ((r + 1) * nr)) * nr + seg_key % nr)
+    seg_range = seg_own // nr
     raw_idx = gat2[perm].astype(np.int32)
     raw_w = w_entry[perm].astype(np.float32)
     # chunking
@@ -125,7 +129,8 @@ def build_brc(own, gat, rel, n, r, nr, t, ch, w_edge=None, lo=0, hi=None):
         for e0 in range(a, bnd, 16):
             tile_e0.append(e0)
             tile_info.append((int(grp_rel[gi]) << 8) | min(16, bnd - e0))
-    return dict(e_own=e_own, tile_e0=np.asarray(tile_e0, dtype=np.int32), tile_info=np.asarray(tile_info, dtype=np.int32),
+    num_tiles_noself = int(sum(1 for ti in tile_info if (ti >> 8) != r))
+    return dict(num_tiles_noself=num_tiles_noself, e_own=e_own, tile_e0=np.asarray(tile_e0, dtype=np.int32), tile_info=np.asarray(tile_info, dtype=np.int32),
                 num_tiles=len(tile_e0), perm=perm.astype(np.int32), num_seg=s, seg_ptr=seg_ptr.astype(np.int32),
                 seg_own=seg_own.astype(np.int32), seg_rel=seg_rel.astype(np.int32), cnt=cnt.astype(np.int32),
                 e_idx=e_idx, e_w=e_w, raw_idx=raw_idx, raw_w=raw_w, w_entry=w_entry,

@@ -132,8 +132,13 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     p.relu_in = relu;
     p.vec4 = v4;
     if ((rc = launch_chunk_prepass(p, st))) return rc;
-    RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->n_own * tld * 4, st));
-    if ((rc = et ? launch_etile_pass(p, g->num_sms, st) : launch_tile_pass(p, g->num_sms, st))) return rc;
+    if (et) {   // root + bias with plain stores (initialises the target), then the edge tiles accumulate
+        if ((rc = launch_selfloop_pass(p, g->own_lo, g->n_own, g->R, g->num_sms, st))) return rc;
+        if ((rc = launch_etile_pass(p, g->num_sms, st))) return rc;
+    } else {
+        RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->n_own * tld * 4, st));
+        if ((rc = launch_tile_pass(p, g->num_sms, st))) return rc;
+    }
     if (!direct) return launch_copy_cols(target, tld, out, ldo, g->n_own, fout, st);
     return 0;
 }
@@ -235,8 +240,13 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
         p.transposed = true;
         p.vec4 = v4;
         if ((rc = launch_chunk_prepass(p, st))) return rc;
-        RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->n_own * tld * 4, st));
-        if ((rc = et ? launch_etile_pass(p, g->num_sms, st) : launch_tile_pass(p, g->num_sms, st))) return rc;
+        if (et) {
+            if ((rc = launch_selfloop_pass(p, g->own_lo, g->n_own, g->R, g->num_sms, st))) return rc;
+            if ((rc = launch_etile_pass(p, g->num_sms, st))) return rc;
+        } else {
+            RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->n_own * tld * 4, st));
+            if ((rc = launch_tile_pass(p, g->num_sms, st))) return rc;
+        }
         if (!direct && (rc = launch_copy_cols(target, tld, gx, ldgx, g->n_own, fin, st))) return rc;
         if (relu && (rc = launch_relu_mask(gx, ldgx, x_own, ldx, g->n_own, fin, st))) return rc;
     }

@@ -17,12 +17,11 @@ constexpr int ET = 16;                        // entries per entry tile (MMA M o
 constexpr uint32_t LAST_FLAG = 0x80000000u;   // bit 31 of e_idx: last entry of its segment
 constexpr uint32_t IDX_MASK = 0x7fffffffu;
 
-void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 
 // pass tags reported by rgcn_profile_collect (see include/rgcn_b200.h)
 enum { TAG_WPREP = 1, TAG_PREPASS = 2, TAG_TILE_FWD = 3, TAG_TILE_BWD = 4, TAG_WGRAD = 5, TAG_COPY = 6, TAG_MASK = 7,
-       TAG_SIMPLE = 8, TAG_MAP = 9 };
+       TAG_SIMPLE = 8, TAG_MAP = 9, TAG_SELF = 10 };
 void note_launch(int n);
 struct ProfScope {   // records a CUDA-event pair around a launch when profiling is enabled
     ProfScope(int tag, int d0, int d1, cudaStream_t st);
@@ -64,6 +63,7 @@ struct Brc {
     int32_t* tile_e0 = nullptr;    // [NT] entry tiles: <= 16 consecutive entries of one (range, relation) group
     int32_t* tile_info = nullptr;  // [NT] rel << 8 | count
     int32_t num_tiles = 0;
+    int32_t num_tiles_noself = 0;  // tiles before the self-loop tiles (which sort last)
     int64_t bytes = 0;
     void release();
 };
@@ -84,10 +84,6 @@ struct rgcn_graph {
 namespace rgcn {
 
 // ---- launchers implemented in layer_kernels.cu / simple_kernels.cu / map_gather.cu --------------
-struct LayerDims {
-    int fin, fout;   // logical
-    int kp, np;      // padded to {16,32,64}; 0 when unsupported by the MMA path
-};
 int pad_dim(int f);   // 16/32/64 or 0
 
 // Tile pass: out[own] += sum over a BRC's segments of (weighted gathered rows) . B_rel
@@ -139,9 +135,9 @@ struct WGradPass {
 };
 int launch_wgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st);
 // entry-tile variants (etile_kernels.cu): rows gathered straight into MMA fragments
-bool etile_enabled();
 bool etile_vec4_ok(const float* feat, int64_t ldf, int kin, const float* aux);
-int launch_etile_pass(const TilePass& p, int num_sms, cudaStream_t st);
+int launch_etile_pass(const TilePass& p, int num_sms, cudaStream_t st);   // edge tiles only: run launch_selfloop_pass first
+int launch_selfloop_pass(const TilePass& p, int64_t own_lo, int64_t n_own, int R, int num_sms, cudaStream_t st);
 int launch_ewgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st);
 
 int launch_copy_cols(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t n, int cols, cudaStream_t st);

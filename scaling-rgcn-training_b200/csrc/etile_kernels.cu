@@ -424,6 +424,150 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 32) ? 1 : 2) k_ewgrad(con
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// self loop + bias:  out[i] = act(x[i]) . root + bias  with PLAIN vector stores.  Runs before the
+// edge tiles of a pass, so it also replaces the zero fill of the accumulate target; the self-loop
+// tiles (which sort last in every BRC) are then skipped by k_etile.
+// ---------------------------------------------------------------------------------------------
+struct SelfArgs {
+    const float* x;      // row 0 = first OWNED node
+    int64_t ldx;
+    int kin;
+    const float4* rfrag;   // root fragments (slot R of wfrag)
+    const float* bias;
+    int nbias;
+    float* out;
+    int64_t ldo;
+    int nout;
+    int64_t n_own;
+};
+
+template <int KT, int NT, bool RELU, bool V4>
+__global__ void __launch_bounds__(EW * 32, 2) k_selfloop(const SelfArgs a) {
+    constexpr bool BREG = (KT * NT <= 16);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t gw = (int64_t)blockIdx.x * EW + warp, nw = (int64_t)gridDim.x * EW;
+    const float4* wf = a.rfrag + lane;
+    float4 bfrag[BREG ? KT * NT : 1];
+    if constexpr (BREG) {
+#pragma unroll
+        for (int i = 0; i < KT * NT; ++i) bfrag[i] = __ldg(wf + i * 32);
+    }
+    float bx[NT], by[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        const int col = 8 * n + 2 * t;
+        bx[n] = (a.bias && col < a.nbias) ? a.bias[col] : 0.f;
+        by[n] = (a.bias && col + 1 < a.nbias) ? a.bias[col + 1] : 0.f;
+    }
+    constexpr int KOFF = V4 ? 4 : 1;
+    const int64_t n_tiles = (a.n_own + 15) / 16;
+    for (int64_t tile = gw; tile < n_tiles; tile += nw) {
+        const int64_t ig = tile * 16 + g, ih = ig + 8;
+        const bool vg = ig < a.n_own, vh = ih < a.n_own;
+        const float* pg = a.x + (vg ? ig : 0) * a.ldx + KOFF * t;
+        const float* ph = a.x + (vh ? ih : 0) * a.ldx + KOFF * t;
+        float av[KT][4];
+        if constexpr (V4) {
+#pragma unroll
+            for (int j = 0; j < KT / 2; ++j) {
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                if (16 * j + 4 * t < a.kin) {
+                    v0 = __ldg(reinterpret_cast<const float4*>(pg + 16 * j));
+                    v1 = __ldg(reinterpret_cast<const float4*>(ph + 16 * j));
+                }
+                av[2 * j][0] = v0.x;
+                av[2 * j][2] = v0.y;
+                av[2 * j + 1][0] = v0.z;
+                av[2 * j + 1][2] = v0.w;
+                av[2 * j][1] = v1.x;
+                av[2 * j][3] = v1.y;
+                av[2 * j + 1][1] = v1.z;
+                av[2 * j + 1][3] = v1.w;
+            }
+        } else {
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) {
+                const bool c_lo = 8 * kt + t < a.kin, c_hi = 8 * kt + 4 + t < a.kin;
+                av[kt][0] = c_lo ? __ldg(pg + 8 * kt) : 0.f;
+                av[kt][1] = c_lo ? __ldg(ph + 8 * kt) : 0.f;
+                av[kt][2] = c_hi ? __ldg(pg + 8 * kt + 4) : 0.f;
+                av[kt][3] = c_hi ? __ldg(ph + 8 * kt + 4) : 0.f;
+            }
+        }
+        float d[NT][4];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            d[n][0] = bx[n];
+            d[n][1] = by[n];
+            d[n][2] = bx[n];
+            d[n][3] = by[n];
+        }
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+            float x0 = av[kt][0], x1 = av[kt][1], x2 = av[kt][2], x3 = av[kt][3];
+            if (RELU) {
+                x0 = fmaxf(x0, 0.f);
+                x1 = fmaxf(x1, 0.f);
+                x2 = fmaxf(x2, 0.f);
+                x3 = fmaxf(x3, 0.f);
+            }
+            uint32_t ah[4], al[4];
+            split_fast(x0, ah[0], al[0]);
+            split_fast(x1, ah[1], al[1]);
+            split_fast(x2, ah[2], al[2]);
+            split_fast(x3, ah[3], al[3]);
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                float4 bf;
+                if constexpr (BREG) bf = bfrag[kt * NT + n];
+                else bf = __ldg(wf + (kt * NT + n) * 32);
+                const uint32_t bh0 = __float_as_uint(bf.x), bh1 = __float_as_uint(bf.y);
+                const uint32_t bl0 = __float_as_uint(bf.z), bl1 = __float_as_uint(bf.w);
+                mma_tf32(d[n], al[0], al[1], al[2], al[3], bh0, bh1);
+                mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+                mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+            }
+        }
+        const bool odd = (t & 1) != 0;
+#pragma unroll
+        for (int j = 0; j < NT / 2; ++j) {
+            const int col = odd ? 8 * (2 * j + 1) + 2 * (t - 1) : 8 * (2 * j) + 2 * t;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float p0 = d[2 * j][2 * h], p1 = d[2 * j][2 * h + 1];
+                const float q0 = d[2 * j + 1][2 * h], q1 = d[2 * j + 1][2 * h + 1];
+                const float rx = __shfl_xor_sync(FULL, odd ? p0 : q0, 1);
+                const float ry = __shfl_xor_sync(FULL, odd ? p1 : q1, 1);
+                const int64_t row = h ? ih : ig;
+                if ((h ? vh : vg) && col < a.nout) {
+                    float4* p = reinterpret_cast<float4*>(a.out + row * a.ldo + col);
+                    *p = odd ? make_float4(rx, ry, q0, q1) : make_float4(p0, p1, rx, ry);
+                }
+            }
+        }
+    }
+}
+
+template <int KT, int NT>
+int run_selfloop(const SelfArgs& a, bool relu, bool v4, int num_sms, cudaStream_t st) {
+    auto launch = [&](auto kern) -> int {
+        const int64_t tiles = (a.n_own + 15) / 16;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + EW - 1) / EW, (int64_t)num_sms * 2));
+        kern<<<grid, EW * 32, 0, st>>>(a);
+        RGCN_CUDA(cudaGetLastError());
+        return 0;
+    };
+    if (v4) {
+        if (relu) return launch(k_selfloop<KT, NT, true, true>);
+        return launch(k_selfloop<KT, NT, false, true>);
+    }
+    if (relu) return launch(k_selfloop<KT, NT, true, false>);
+    return launch(k_selfloop<KT, NT, false, false>);
+}
+
 template <int KT, int NT>
 int run_etile(const ETileArgs& a, bool relu, bool v4, int num_sms, cudaStream_t st) {
     auto launch = [&](auto kern) -> int {
@@ -505,15 +649,6 @@ bool etile_vec4_ok(const float* feat, int64_t ldf, int kin, const float* aux) {
     return !off && ldf % 4 == 0 && ((kin + 3) & ~3) <= ldf && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)aux & 15) == 0;
 }
 
-bool etile_enabled() {   // RGCN_B200_ETILE=0 selects the staged (shared-memory ring) kernels instead
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("RGCN_B200_ETILE");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v == 1;
-}
-
 int launch_etile_pass(const TilePass& p, int num_sms, cudaStream_t st) {
     const Brc& b = *p.brc;
     if (b.num_tiles == 0) return 0;
@@ -531,9 +666,30 @@ int launch_etile_pass(const TilePass& p, int num_sms, cudaStream_t st) {
     a.out = p.out;
     a.ldo = p.ldo;
     a.nout = p.nout;
+    a.num_tiles = b.num_tiles_noself;   // the self loops were written by launch_selfloop_pass
+    if (a.num_tiles == 0) return 0;
     ProfScope prof(p.transposed ? TAG_TILE_BWD : TAG_TILE_FWD, p.kin, p.tag_out, st);
     note_launch(1);
     RGCN_DISPATCH_E(run_etile, p.kp, p.np, a, p.relu_in, p.vec4, num_sms, st);
+}
+
+// out[i] = act(x[own_lo + i]) . root + bias for every owned row (plain stores: also initialises `out`)
+int launch_selfloop_pass(const TilePass& p, int64_t own_lo, int64_t n_own, int R, int num_sms, cudaStream_t st) {
+    if (n_own == 0) return 0;
+    SelfArgs a{};
+    a.x = p.feat + own_lo * p.ldf;
+    a.ldx = p.ldf;
+    a.kin = p.kin;
+    a.rfrag = p.wfrag + (int64_t)R * (p.kp / 8) * (p.np / 8) * 32;
+    a.bias = p.bias;
+    a.nbias = p.nbias;
+    a.out = p.out;
+    a.ldo = p.ldo;
+    a.nout = p.nout;
+    a.n_own = n_own;
+    ProfScope prof(TAG_SELF, p.kin, p.tag_out, st);
+    note_launch(1);
+    RGCN_DISPATCH_E(run_selfloop, p.kp, p.np, a, p.relu_in, p.vec4, num_sms, st);
 }
 
 int launch_ewgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st) {

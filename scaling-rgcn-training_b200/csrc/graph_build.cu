@@ -15,7 +15,6 @@
 namespace rgcn {
 
 static thread_local std::string g_last_error;
-void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
@@ -125,12 +124,13 @@ __global__ void k_fill_entries(const int32_t* __restrict__ own_g, const int32_t*
     }
 }
 
+// sort key: edges by (owner range, relation, owner); self loops (relation R) after every range, by owner
 __global__ void k_keys(const int32_t* __restrict__ own, const int32_t* __restrict__ rel, int64_t n2, int R, int NR,
-                       uint64_t* __restrict__ key, int32_t* __restrict__ eid) {
+                       uint64_t self_base, uint64_t* __restrict__ key, int32_t* __restrict__ eid) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n2) return;
     uint64_t o = (uint64_t)own[i];
-    key[i] = (o / NR) * ((uint64_t)(R + 1) * NR) + (uint64_t)rel[i] * NR + (o % NR);
+    key[i] = rel[i] == R ? self_base + o : (o / NR) * ((uint64_t)(R + 1) * NR) + (uint64_t)rel[i] * NR + (o % NR);
     eid[i] = (int32_t)i;
 }
 
@@ -142,8 +142,8 @@ __global__ void k_heads(const uint64_t* __restrict__ skey, int64_t n2, int32_t* 
 
 // segid = inclusive_scan(head) - 1 ; at heads record the segment's start / owner / relation
 __global__ void k_seg_fill(const uint64_t* __restrict__ skey, const int32_t* __restrict__ head,
-                           const int32_t* __restrict__ scan, int64_t n2, int R, int NR, int32_t* __restrict__ seg_ptr0,
-                           int32_t* __restrict__ seg_own, int32_t* __restrict__ seg_rel) {
+                           const int32_t* __restrict__ scan, int64_t n2, int R, int NR, uint64_t self_base,
+                           int32_t* __restrict__ seg_ptr0, int32_t* __restrict__ seg_own, int32_t* __restrict__ seg_rel) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n2 || !head[i]) return;
     int32_t s = scan[i] - 1;
@@ -151,8 +151,13 @@ __global__ void k_seg_fill(const uint64_t* __restrict__ skey, const int32_t* __r
     uint64_t span = (uint64_t)(R + 1) * NR;
     uint64_t rng = k / span, rem = k % span;
     seg_ptr0[s] = (int32_t)i;
-    seg_rel[s] = (int32_t)(rem / NR);
-    seg_own[s] = (int32_t)(rng * NR + rem % NR);
+    if (k >= self_base) {
+        seg_rel[s] = R;
+        seg_own[s] = (int32_t)(k - self_base);
+    } else {
+        seg_rel[s] = (int32_t)(rem / NR);
+        seg_own[s] = (int32_t)(rng * NR + rem % NR);
+    }
 }
 
 __global__ void k_raw(const int32_t* __restrict__ perm, const int32_t* __restrict__ gat,
@@ -339,10 +344,11 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const 
     RGCN_CUDA(head.alloc(n2));
     RGCN_CUDA(scan.alloc(n2));
     RGCN_CUDA(cudaMalloc(&b.perm, std::max<int64_t>(n2, 1) * 4));
-    k_keys<<<blocks_for(n2), TPB, 0, st>>>(own, rel, n2, R, NR, key.p, eid.p);
+    const uint64_t nranges = std::max<uint64_t>((uint64_t)((N + NR - 1) / NR), 1);
+    const uint64_t self_base = nranges * (uint64_t)(R + 1) * (uint64_t)NR;
+    k_keys<<<blocks_for(n2), TPB, 0, st>>>(own, rel, n2, R, NR, self_base, key.p, eid.p);
     {
-        uint64_t nranges = (uint64_t)((N + NR - 1) / NR);
-        uint64_t max_key = std::max<uint64_t>(nranges, 1) * (uint64_t)(R + 1) * (uint64_t)NR;
+        uint64_t max_key = self_base + (uint64_t)N;
         int end_bit = std::min(64, bit_length(max_key));
         size_t tmp_bytes = 0;
         RGCN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key.p, skey.p, eid.p, b.perm, (int)n2, 0,
@@ -362,7 +368,8 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const 
     RGCN_CUDA(cudaMalloc(&b.seg_ptr, (size_t)(S + 1) * 4));
     RGCN_CUDA(cudaMalloc(&b.seg_own, std::max(S, 1) * 4));
     RGCN_CUDA(cudaMalloc(&b.seg_rel, std::max(S, 1) * 4));
-    k_seg_fill<<<blocks_for(n2), TPB, 0, st>>>(skey.p, head.p, scan.p, n2, R, NR, b.seg_ptr0, b.seg_own, b.seg_rel);
+    k_seg_fill<<<blocks_for(n2), TPB, 0, st>>>(skey.p, head.p, scan.p, n2, R, NR, self_base, b.seg_ptr0, b.seg_own,
+                                               b.seg_rel);
     k_set_i32<<<1, 1, 0, st>>>(b.seg_ptr0 + S, (int32_t)n2);
     RGCN_CUDA(cudaMalloc(&b.raw_idx, std::max<int64_t>(n2, 1) * 4));
     RGCN_CUDA(cudaMalloc(&b.raw_w, std::max<int64_t>(n2, 1) * 4));
@@ -432,6 +439,13 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const 
             RGCN_CUDA(cudaMemcpy(&NTL, tile_base.p + G, 4, cudaMemcpyDeviceToHost));
         }
         b.num_tiles = NTL;
+        // self loops sort last: their groups (one per owner range) are the tail of the group list
+        b.num_tiles_noself = NTL;
+        if (G > 0) {
+            const int32_t first_self_group = G - (int32_t)nranges;
+            if (first_self_group >= 0)
+                RGCN_CUDA(cudaMemcpy(&b.num_tiles_noself, tile_base.p + first_self_group, 4, cudaMemcpyDeviceToHost));
+        }
         RGCN_CUDA(cudaMalloc(&b.tile_e0, std::max(NTL, 1) * 4));
         RGCN_CUDA(cudaMalloc(&b.tile_info, std::max(NTL, 1) * 4));
         if (NTL > 0)
@@ -647,6 +661,7 @@ extern "C" int rgcn_graph_query(const rgcn_graph* g, int32_t brc, int32_t key, i
         case RGCN_Q_OWN_LO: *out = g->own_lo; break;
         case RGCN_Q_NUM_ENTRIES0: *out = b.num_entries0; break;
         case RGCN_Q_NUM_TILES: *out = b.num_tiles; break;
+        case RGCN_Q_NUM_TILES_NOSELF: *out = b.num_tiles_noself; break;
         case RGCN_Q_DEVICE_BYTES:
             *out = g->brc[0].bytes + g->brc[1].bytes + (g->rel_is_fwd ? 0 : g->brc[2].bytes);
             break;

@@ -21,7 +21,8 @@ EXPORTS = (
 
 BRC_FWD, BRC_BWD, BRC_FWD_REL = 0, 1, 2
 Q_NUM_NODES, Q_NUM_EDGES, Q_NUM_RELATIONS, Q_NUM_SEGMENTS, Q_NUM_ENTRIES, Q_NUM_CHUNKS, Q_NUM_GROUPS, \
-    Q_NUM_BATCHES, Q_RANGE_NODES, Q_DEVICE_BYTES, Q_NUM_OWNED, Q_OWN_LO, Q_NUM_ENTRIES0, Q_NUM_TILES = range(14)
+    Q_NUM_BATCHES, Q_RANGE_NODES, Q_DEVICE_BYTES, Q_NUM_OWNED, Q_OWN_LO, Q_NUM_ENTRIES0, Q_NUM_TILES, \
+    Q_NUM_TILES_NOSELF = range(15)
 A_PERM, A_SEG_PTR, A_SEG_OWN, A_SEG_REL, A_SEG_PTR0, A_E_IDX, A_E_W, A_RAW_IDX, A_RAW_W, A_CHUNK_BEG, \
     A_CHUNK_END, A_BAT_SEG0, A_BAT_INFO, A_E_OWN, A_TILE_E0, A_TILE_INFO = range(16)
 F_RELU_IN, F_FORCE_SIMPLE = 1, 2
@@ -84,7 +85,7 @@ def check(rc: int, what: str = '') -> None:
 
 
 PASS_NAMES = {1: 'wprep', 2: 'chunk_prepass', 3: 'tile_fwd', 4: 'tile_dx', 5: 'wgrad', 6: 'copy_cols', 7: 'relu_mask',
-              8: 'generic', 9: 'map_gather'}
+              8: 'generic', 9: 'map_gather', 10: 'self_loop'}
 
 
 def launch_count() -> int:

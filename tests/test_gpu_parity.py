@@ -30,6 +30,7 @@ def _check_brc(g, which, want):
     assert g.query(_lib.Q_NUM_BATCHES, which) == want['num_batches']
     assert g.query(_lib.Q_NUM_GROUPS, which) == want['num_groups']
     assert g.query(_lib.Q_NUM_TILES, which) == want['num_tiles']
+    assert g.query(_lib.Q_NUM_TILES_NOSELF, which) == want['num_tiles_noself']
     pairs = [(_lib.A_PERM, 'perm'), (_lib.A_SEG_PTR, 'seg_ptr'), (_lib.A_SEG_OWN, 'seg_own'), (_lib.A_SEG_REL, 'seg_rel'),
              (_lib.A_E_IDX, 'e_idx'), (_lib.A_E_W, 'e_w'), (_lib.A_RAW_IDX, 'raw_idx'), (_lib.A_RAW_W, 'raw_w'),
              (_lib.A_CHUNK_BEG, 'chunk_beg'), (_lib.A_CHUNK_END, 'chunk_end'), (_lib.A_BAT_SEG0, 'bat_seg0'),

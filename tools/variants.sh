@@ -1,5 +1,6 @@
 #!/bin/bash
-# tuning helper (GPU box): run bench.py kernel-only under several env variants
+# tuning helper (GPU box): run bench.py kernel-only under several env variants, from the repo root:
+#   tools/variants.sh default relmajor ...
 mkdir -p gpurun_out
 run() { name=$1; shift; env "$@" python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/var_$name.json 2> gpurun_out/var_$name.err; python - <<PY
 import json
