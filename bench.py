@@ -78,7 +78,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -88,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -332,6 +332,29 @@ def run_engine(args):
            'what': 'Trainer.train iteration body (modelTrainer.py:61-69) via Emb_Layers on the drop-in RGCNConv: '
                    'pinned H2D of x_train/y_train, fwd, CE loss, bwd, Adam (incl. the [N,63] embedding), loss.item()'}
 
+    # K5 map gather at this graph's size (3 summaries, sum mode): achieved GB/s, reported beside the layer
+    map_gather = None
+    if not args.no_e2e:
+        from rgcn_b200 import map_gather as mg
+        gen = torch.Generator().manual_seed(3)
+        n_sum = 50_000
+        embs = [torch.randn(n_sum, EMB, generator=gen).to(device) for _ in range(3)]
+        idxs = [torch.randint(-1, n_sum, (n,), generator=gen, dtype=torch.int32).to(device) for _ in range(3)]
+        fbs = [torch.rand(n, EMB, generator=gen).to(device) for _ in range(3)]
+        for _ in range(3):
+            mg(embs, idxs, fbs, 0)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(10):
+            mg(embs, idxs, fbs, 0)
+        ev1.record()
+        torch.cuda.synchronize(device)
+        mg_ms = ev0.elapsed_time(ev1) / 10
+        mg_bytes = 3 * n * (4 * EMB + 4) + n * 4 * EMB        # S x (row + index) read, one row written
+        map_gather = {'ms': mg_ms, 'algorithmic_bytes': mg_bytes, 'gbps': mg_bytes / (mg_ms * 1e-3) / 1e9,
+                      'frac_of_peak': mg_bytes / (mg_ms * 1e-3) / 1e9 / peak, 'mode': 'sum', 'summaries': 3}
+        del embs, idxs, fbs
+
     cpu = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -347,7 +370,7 @@ def run_engine(args):
                    'classes': CLASSES, 'l2_policy': 'inputs larger than L2 (features 420 MB + CSR > 126 MB L2); no flush',
                    'graph_build_ms_once': setup_ms, 'range_nodes': graph.query(_lib.Q_RANGE_NODES),
                    'step_algorithmic_bytes': step_bytes, 'step_roofline_frac': step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
-                   'passes': passes},
+                   'passes': passes, 'map_gather': map_gather},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
     }
     print(json.dumps(line), flush=True)
