@@ -312,25 +312,33 @@ def run_engine(args):
     # labelled batch copied from pinned host memory every step, loss read back every step
     x_train_h, y_train_h = labelled_split(n, CLASSES)
     x_train_h, y_train_h = x_train_h.pin_memory(), y_train_h.pin_memory()
-    opt = make_optimizer(model)
     h2d = x_train_h.numel() * x_train_h.element_size() + y_train_h.numel() * y_train_h.element_size()
 
-    def e2e_step():
-        data.x_train = x_train_h.to(device, non_blocking=True)
-        data.y_train = y_train_h.to(device, non_blocking=True)
-        model.train()
-        opt.zero_grad()
-        out = model(data, identity)
-        loss = ce_loss(out[data.x_train], data.y_train.to(torch.float32))
-        loss.backward()
-        opt.step()
-        return loss.item()
+    def make_e2e_step(opt):
+        def e2e_step():
+            data.x_train = x_train_h.to(device, non_blocking=True)
+            data.y_train = y_train_h.to(device, non_blocking=True)
+            model.train()
+            opt.zero_grad()
+            out = model(data, identity)
+            loss = ce_loss(out[data.x_train], data.y_train.to(torch.float32))
+            loss.backward()
+            opt.step()
+            return loss.item()
+        return e2e_step
 
-    e2e_ms = time_steps(e2e_step, args.steps, args.warmup, world, device) / args.steps if not args.no_e2e else float('nan')
+    e2e_ms = torch_adam_ms = float('nan')
+    if not args.no_e2e:
+        # the package's Trainer step: engine layers + the engine's one-pass Adam (rgcn_b200.trainer.make_optimizer)
+        e2e_ms = time_steps(make_e2e_step(make_optimizer(model)), args.steps, args.warmup, world, device) / args.steps
+        # same step with torch.optim.Adam, i.e. what the unmodified reference Trainer runs on the drop-in layers
+        torch_adam_ms = time_steps(make_e2e_step(make_optimizer(model, fused=False)), args.steps, args.warmup, world,
+                                   device) / args.steps
     e2e = {'value': e / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4,
-           'ms_per_step': e2e_ms,
+           'ms_per_step': e2e_ms, 'ms_per_step_with_torch_adam': torch_adam_ms,
            'what': 'Trainer.train iteration body (modelTrainer.py:61-69) via Emb_Layers on the drop-in RGCNConv: '
-                   'pinned H2D of x_train/y_train, fwd, CE loss, bwd, Adam (incl. the [N,63] embedding), loss.item()'}
+                   'pinned H2D of x_train/y_train, fwd, CE loss, bwd, Adam step (engine FusedAdam, same update rule as '
+                   'torch.optim.Adam(lr, weight_decay); incl. the [N,63] embedding), loss.item()'}
 
     # K5 map gather at this graph's size (3 summaries, sum mode): achieved GB/s, reported beside the layer
     map_gather = None

@@ -134,6 +134,21 @@ int rgcn_map_gather(const float* const* host_emb, const int32_t* const* host_idx
                     const float* const* host_fallback, int32_t num_sums,
                     int64_t num_nodes, int32_t feat, int32_t mode, float* out, void* stream);
 
+/* Device side of `evaluate` (reference model/evaluation.py:14-31).  For the n evaluated rows
+ * pred[idx[r]] (width num_classes): mode 0 = one-hot of the arg-max (the CE path: softmax is
+ * monotone), mode 1 = round() of the already-sigmoided output (BCE path).  Against the int64
+ * multi-hot labels y [n, num_classes] it fills counts[0:C] = true positives per class,
+ * counts[C:2C] = false positives, counts[2C:3C] = false negatives, counts[3C] = rows predicted
+ * exactly — all sklearn's accuracy_score / f1_score(weighted, macro) need. */
+int rgcn_eval_counts(const float* pred, int64_t ldp, int32_t num_classes, const int64_t* idx, int64_t n,
+                     const int64_t* y, int32_t mode, int64_t* counts, void* stream);
+
+/* One Adam step with L2 weight decay on one fp32 tensor, in one pass — the update rule of
+ * torch.optim.Adam(lr, weight_decay) as the reference builds it (model/modelTrainer.py:44;
+ * amsgrad / maximize off).  `step` counts from 1. */
+int rgcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream);
+
 /* Zero-padded, 16-byte addressable mirror of an odd-width feature matrix (e.g. the reference's
  * emb = 63): dst[r][c] = c < cols ? src[r][c] : 0 for c < ldd.  Passing the mirror (ldx = ldd) as x
  * to rgcn_layer_fwd / rgcn_layer_bwd lets the kernels use 128-bit row loads. */

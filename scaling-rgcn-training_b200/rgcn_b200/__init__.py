@@ -10,8 +10,10 @@ from .conv import RGCNConv, rgcn_layer
 from .data import Data
 from .graph import RGCNGraph, cached_graph, clear_cache
 from .layers import Emb_ATT_Layers, Emb_Layers, Emb_MLP_Layers
+from .evaluation import evaluate
+from .optim import FusedAdam
 from .embedding_tricks import (build_map_index, concat_embeddings, map_gather, stack_embeddings, sum_embeddings)
 
 __all__ = ['EngineError', 'RGCNConv', 'rgcn_layer', 'Data', 'RGCNGraph', 'cached_graph', 'clear_cache',
            'Emb_Layers', 'Emb_MLP_Layers', 'Emb_ATT_Layers', 'build_map_index', 'map_gather',
-           'sum_embeddings', 'concat_embeddings', 'stack_embeddings']
+           'sum_embeddings', 'concat_embeddings', 'stack_embeddings', 'evaluate', 'FusedAdam']

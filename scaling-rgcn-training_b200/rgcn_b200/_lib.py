@@ -17,6 +17,7 @@ EXPORTS = (
     'rgcn_last_error', 'rgcn_abi_version', 'rgcn_graph_create', 'rgcn_graph_create_part', 'rgcn_graph_destroy', 'rgcn_graph_query',
     'rgcn_graph_export', 'rgcn_layer_workspace_bytes', 'rgcn_layer_fwd', 'rgcn_layer_bwd', 'rgcn_map_gather',
     'rgcn_kernel_launch_count', 'rgcn_profile_enable', 'rgcn_profile_collect', 'rgcn_pad_rows',
+    'rgcn_eval_counts', 'rgcn_adam_step',
 )
 
 BRC_FWD, BRC_BWD, BRC_FWD_REL = 0, 1, 2
@@ -66,6 +67,10 @@ def load():
     lib.rgcn_layer_bwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, i64, vp, i64, i32, vp, i64, vp, vp, vp, u32, vp, i64, vp]
     lib.rgcn_map_gather.restype = C.c_int
     lib.rgcn_map_gather.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i32, i64, i32, i32, vp, vp]
+    lib.rgcn_eval_counts.restype = C.c_int
+    lib.rgcn_eval_counts.argtypes = [vp, i64, i32, vp, i64, vp, i32, vp, vp]
+    lib.rgcn_adam_step.restype = C.c_int
+    lib.rgcn_adam_step.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, vp]
     lib.rgcn_pad_rows.restype = C.c_int
     lib.rgcn_pad_rows.argtypes = [vp, i64, i32, vp, i64, i64, vp]
     lib.rgcn_kernel_launch_count.restype = i64

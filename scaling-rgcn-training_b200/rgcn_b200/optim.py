@@ -1,0 +1,48 @@
+"""FusedAdam — the optimiser the reference builds at /root/reference/model/modelTrainer.py:44
+(``torch.optim.Adam(model.parameters(), lr, weight_decay)``: L2 decay added to the gradient, bias
+correction, no amsgrad) with the whole update of a tensor in ONE engine kernel
+(``rgcn_adam_step``).  Same constructor defaults and state names
+(``step``, ``exp_avg``, ``exp_avg_sq``) as torch's Adam; CUDA fp32 parameters only."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+        if lr < 0 or eps < 0 or weight_decay < 0 or not (0 <= betas[0] < 1 and 0 <= betas[1] < 1):
+            raise ValueError('FusedAdam: invalid hyper-parameter')
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _lib.load()
+        for group in self.param_groups:
+            b1, b2 = group['betas']
+            for p in group['params']:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda or p.dtype != torch.float32:
+                    raise _lib.EngineError('FusedAdam: CUDA fp32 parameters only (no CPU path)')
+                if not p.is_contiguous():
+                    raise _lib.EngineError('FusedAdam: contiguous parameters only')
+                st = self.state[p]
+                if not st:
+                    st['step'] = 0
+                    st['exp_avg'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st['step'] += 1
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                with torch.cuda.device(p.device):
+                    rc = lib.rgcn_adam_step(p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(),
+                                            st['exp_avg_sq'].data_ptr(), p.numel(), group['lr'], b1, b2, group['eps'],
+                                            group['weight_decay'], st['step'],
+                                            torch.cuda.current_stream(p.device).cuda_stream)
+                _lib.check(rc, 'rgcn_adam_step')
+        return loss

@@ -28,8 +28,12 @@ def get_losst(dataset: str, sumModel: bool = False) -> Tuple[Callable, Callable]
     return ce_loss, identity
 
 
-def make_optimizer(model: nn.Module, lr: float = 0.01, weight_decay: float = 5e-5) -> torch.optim.Optimizer:
-    """Adam exactly as modelTrainer.py:44 builds it (weight_d = 5e-5 from main.py:52)."""
+def make_optimizer(model: nn.Module, lr: float = 0.01, weight_decay: float = 5e-5, fused: bool = True):
+    """Adam as modelTrainer.py:44 builds it (weight_d = 5e-5 from main.py:52): the engine's one-pass
+    FusedAdam (same update rule) by default, torch.optim.Adam with fused=False."""
+    if fused:
+        from .optim import FusedAdam
+        return FusedAdam(model.parameters(), lr=lr, weight_decay=weight_decay)
     return torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
 
 

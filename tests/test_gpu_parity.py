@@ -399,3 +399,58 @@ def test_partitioned_graph_matches_unpartitioned(world):
     assert rel_err(gws, leaves[1].grad.cpu()) < TOL
     assert rel_err(groots, leaves[2].grad.cpu()) < TOL
     assert rel_err(gbiases, leaves[3].grad.cpu()) < TOL
+
+
+# ------------------------------------------------------------------ device-side evaluate
+@pytest.mark.parametrize('sigmoid_path', [False, True])
+def test_eval_counts_match_sklearn(sigmoid_path):
+    """The reference's evaluate (model/evaluation.py:14-31) restated on CPU with sklearn vs the device counts."""
+    from sklearn.metrics import accuracy_score, f1_score
+    from rgcn_b200.evaluation import confusion_counts, metrics_from_counts
+    torch.manual_seed(5)
+    n, c, m = 500, 7, 180
+    logits = torch.randn(n, c)
+    logits[3] = 0.5                      # ties: argmax takes the first index; round(0.5) -> 0 (half to even)
+    x = torch.randperm(n)[:m]
+    if sigmoid_path:
+        out = torch.sigmoid(logits)
+        out[5] = 0.5
+        y = (torch.rand(m, c) < 0.3).long()
+        pred_ref = torch.round(out).type(torch.int64)
+    else:
+        out = logits
+        y = torch.nn.functional.one_hot(torch.randint(0, c, (m,)), c)
+        y[::9, 0] = 1                    # multi-hot rows occur in the reference's labels
+        a = torch.softmax(out, 1).argmax(1)
+        pred_ref = torch.zeros(out.shape).scatter(1, a.unsqueeze(1), 1.0)
+    want = (accuracy_score(y, pred_ref[x]), f1_score(y, pred_ref[x], average='weighted', zero_division=0),
+            f1_score(y, pred_ref[x], average='macro', zero_division=0))
+    counts = confusion_counts(out.to(DEV), x.to(DEV), y.to(DEV), sigmoid_path)
+    got = metrics_from_counts(counts, m)
+    for g_, w_ in zip(got, want):
+        assert abs(g_ - w_) < 1e-12
+
+
+# ------------------------------------------------------------------ fused Adam (SURVEY 8f rank 2)
+def test_fused_adam_matches_torch_adam():
+    from rgcn_b200 import FusedAdam
+    torch.manual_seed(9)
+    shapes = [(1000, 63), (89, 63, 16), (16,), (7,)]
+    pa = [torch.randn(s, device=DEV).requires_grad_() for s in shapes]
+    pb = [p.detach().clone().requires_grad_() for p in pa]
+    oa = torch.optim.Adam(pa, lr=0.01, weight_decay=5e-5)
+    ob = FusedAdam(pb, lr=0.01, weight_decay=5e-5)
+    for step in range(25):
+        gs = [torch.randn_like(p) * (0.1 + step) for p in pa]
+        for p, q, g_ in zip(pa, pb, gs):
+            p.grad = g_.clone()
+            q.grad = g_.clone()
+        oa.step()
+        ob.step()
+    for p, q in zip(pa, pb):
+        assert rel_err(q, p.detach().cpu()) < 1e-6
+    cpu_param = torch.zeros(3, requires_grad=True)       # no CPU path: fails loudly
+    o = FusedAdam([cpu_param])
+    cpu_param.grad = torch.ones(3)
+    with pytest.raises(_lib.EngineError):
+        o.step()
