@@ -127,7 +127,8 @@ def dist_setup(n_gpus: int):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault('NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line (no version banner)
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'          # keep stdout to the one JSON line (no version banner)
         torch.cuda.set_device(local)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     return rank, world, local

@@ -51,32 +51,37 @@ class _RGCNLayerFn(torch.autograd.Function):
             raise _lib.EngineError('RGCNConv: input is not a CUDA tensor; the B200 engine has no CPU path')
         if x.dtype != torch.float32 or weight.dtype != torch.float32:
             raise TypeError('RGCNConv: fp32 features and parameters expected')
+        fin = x.size(1) if x.dim() == 2 else -1
+
+        def pad_rows(t: Tensor) -> Tensor:
+            # odd-width wide rows (the reference's emb = 63): gather from a zero-padded 16-byte
+            # addressable mirror (one streaming copy) so the kernels can use 128-bit row loads;
+            # the mirror is what backward re-gathers, the caller's tensor is not kept
+            if not (_PAD_WIDE and fin > 32 and (t.stride(0) % 4 != 0 or t.data_ptr() % 16 != 0)):
+                return t
+            ldp = (fin + 3) // 4 * 4
+            tp = torch.empty((t.size(0), ldp), dtype=torch.float32, device=t.device)
+            with torch.cuda.device(t.device):
+                _lib.check(lib.rgcn_pad_rows(t.data_ptr(), t.stride(0), fin, tp.data_ptr(), ldp, t.size(0),
+                                             _stream(t.device)), 'rgcn_pad_rows')
+            return tp
+
         if comm is not None:
             if x.dim() != 2 or x.size(0) != graph.num_owned:
                 raise ValueError(f'RGCNConv (partitioned): x must hold the {graph.num_owned} owned rows')
-            x = comm.all_gather_rows(x.contiguous())
+            x = comm.all_gather_rows(pad_rows(x.contiguous()))   # pad the owned shard, gather the mirror
         if x.dim() != 2 or x.size(0) < graph.num_nodes or (comm is None and x.size(0) != graph.num_nodes):
             raise ValueError(f'RGCNConv: x must be [num_nodes={graph.num_nodes}, in_channels]')
         x = x if x.stride(1) == 1 or x.size(1) == 1 else x.contiguous()
         weight = weight.contiguous()
         root_c = root.contiguous() if root is not None else None
         bias_c = bias.contiguous() if bias is not None else None
-        n, fin = x.shape
+        n = x.size(0)
         r, fin_w, fout = weight.shape
         if fin_w != fin or r != graph.num_relations:
             raise ValueError('RGCNConv: weight shape does not match input / num_relations')
-        if fin > 32 and (x.stride(0) % 4 != 0 or x.data_ptr() % 16 != 0) and _PAD_WIDE:
-            # odd-width wide rows (the reference's emb = 63): gather from a zero-padded 16-byte
-            # addressable mirror (one streaming copy) so the kernels can use 128-bit row loads;
-            # the mirror is what backward re-gathers, the caller's tensor is not kept
-            ldp = (fin + 3) // 4 * 4
-            xp = torch.empty((x.size(0), ldp), dtype=torch.float32, device=x.device)
-            with torch.cuda.device(x.device):
-                _lib.check(lib.rgcn_pad_rows(x.data_ptr(), x.stride(0), fin, xp.data_ptr(), ldp, x.size(0),
-                                             _stream(x.device)), 'rgcn_pad_rows')
-            x = xp
-        # rows padded to whole quads so the kernel can accumulate in place with 128-bit atomics; the
-        # caller sees the [:, :fout] view (no column copy)
+        if comm is None:
+            x = pad_rows(x)
         ldo = (fout + 3) // 4 * 4
         out_buf = torch.empty((graph.num_owned, ldo), dtype=torch.float32, device=x.device)
         out = out_buf[:, :fout] if ldo != fout else out_buf

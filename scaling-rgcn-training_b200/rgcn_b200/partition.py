@@ -48,6 +48,7 @@ class RowComm:
         self.chunk, self.ranges = plan_ranges(num_nodes, self.world)
         self.lo, self.hi = self.ranges[self.rank]
         self.bytes_gathered = 0
+        self.events = None        # list of (start, stop) CUDA-event pairs when timing is on (bench)
 
     def all_gather_rows_async(self, t: Tensor):
         """Start the all-gather on the communicator's stream; returns (out, work). The caller runs
@@ -73,9 +74,27 @@ class RowComm:
             pad[:n_own] = t
             t = pad
         out = t.new_empty((self.world * self.chunk, f))
+        ev = self._tic(t)
         dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        self._toc(ev)
         self.bytes_gathered += out.numel() * out.element_size()
         return out
+
+    def _tic(self, t: Tensor):
+        if self.events is None or not t.is_cuda:
+            return None
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+        return ev
+
+    def _toc(self, ev) -> None:
+        if ev is not None:
+            ev[1].record()
+            self.events.append(ev)
+
+    def comm_ms(self) -> float:
+        """Sum of the timed synchronous collectives (call after a device synchronize)."""
+        return sum(a.elapsed_time(b) for a, b in (self.events or []))
 
     def all_reduce_sum_(self, tensors: List[Tensor]) -> None:
         """One flat all-reduce for the (small) parameter gradients."""
@@ -83,7 +102,9 @@ class RowComm:
         if not tensors or self.world == 1:
             return
         flat = torch.cat([t.reshape(-1) for t in tensors])
+        ev = self._tic(flat)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        self._toc(ev)
         off = 0
         for t in tensors:
             t.copy_(flat[off:off + t.numel()].view_as(t))
@@ -145,6 +166,7 @@ def run_partitioned_bench(args, rank: int, world: int, device, metric: str, unit
         step()
     torch.cuda.synchronize(device)
     comm.bytes_gathered = 0
+    comm.events = []
     launches0 = _lib.launch_count()
     if rank == 0:
         sampler.start()
@@ -167,6 +189,7 @@ def run_partitioned_bench(args, rank: int, world: int, device, metric: str, unit
                        'collectives': 'per layer: all_gather(x) fwd, all_gather(gout) bwd; one all_reduce of dW/droot/dbias',
                        'all_gather_bytes_per_step_per_rank': comm.bytes_gathered // max(args.steps, 1),
                        'max_rank_in_edges': int(mx.item()), 'mean_rank_in_edges': e / world,
+                       'sync_collectives_ms_per_step_rank0': comm.comm_ms() / max(args.steps, 1),
                        'graph_build_ms_once': setup_ms,
                        'l2_policy': 'inputs larger than L2; no flush'},
             'clocks': clocks, 'gpu_launches': int(launches),
