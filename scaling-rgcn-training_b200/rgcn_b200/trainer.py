@@ -46,3 +46,69 @@ def train_step(model: nn.Module, training_data, optimizer, loss_f: Callable, act
     loss.backward()
     optimizer.step()
     return loss.item()
+
+
+class Trainer:
+    """Mirror of the reference's ``Trainer`` (/root/reference/model/modelTrainer.py:14-116) on the
+    engine: sequential summary pre-training with carried R-GCN weights (:76-82),
+    weight transfer (:26-39), embedding transfer (:94-96) and full-graph training with per-epoch
+    validation (:41-74), everything on the device.  ``data`` needs ``sumGraphs``, ``orgGraph`` and
+    ``num_classes`` exactly like the reference's ``Dataset``; a graph needs ``training_data``,
+    ``num_nodes``, ``relations``, ``node_to_enum`` (and ``orgNode2sumNode_dict`` for summaries).
+    """
+
+    def __init__(self, data, hidden_l: int, epochs: int, emb_dim: int, lr: float, weight_d: float,
+                 device='cuda:0', fused_adam: bool = True) -> None:
+        self.data, self.hidden_l, self.epochs, self.emb_dim = data, hidden_l, epochs, emb_dim
+        self.lr, self.weight_d = lr, weight_d
+        self.device = torch.device(device)
+        self.fused_adam = fused_adam
+        self.sumModel = None
+
+    def transfer_weights(self, orgModel: nn.Module, grad: bool) -> None:
+        s = self.sumModel
+        orgModel.override_params(s.rgcn1.weight.clone(), s.rgcn1.bias.clone(), s.rgcn1.root.clone(),
+                                 s.rgcn2.weight.clone(), s.rgcn2.bias.clone(), s.rgcn2.root.clone(), grad)
+
+    def train(self, model: nn.Module, graph, loss_f: Callable, activation: Callable, sum_graph: bool = True):
+        from .evaluation import evaluate
+        model = model.to(self.device)
+        td = graph.training_data.to(self.device)
+        opt = make_optimizer(model, self.lr, self.weight_d, fused=self.fused_adam)
+        accuracies, losses, f1_ws, f1_ms = [], [], [], []
+        for _ in range(self.epochs):
+            if not sum_graph:
+                model.eval()
+                acc, f1_w, f1_m = evaluate(model, activation, td, td.x_val, td.y_val)
+                accuracies.append(acc)
+                f1_ws.append(f1_w)
+                f1_ms.append(f1_m)
+            losses.append(train_step(model, td, opt, loss_f, activation))
+        return accuracies, losses, f1_ws, f1_ms
+
+    def train_summaries(self, dataset: str = 'AIFB') -> None:
+        from .layers import Emb_Layers
+        loss_f, activation = get_losst(dataset, sumModel=True)
+        first = self.data.sumGraphs[0]
+        self.sumModel = Emb_Layers(2 * len(first.relations) + 1, self.hidden_l, self.data.num_classes, first.num_nodes,
+                                   self.emb_dim, len(self.data.sumGraphs))
+        for sg in self.data.sumGraphs:
+            self.sumModel.reset_embedding(sg.num_nodes, self.emb_dim)
+            self.train(self.sumModel, sg, loss_f, activation, sum_graph=True)
+            sg.embedding = self.sumModel.embedding.weight.clone()
+
+    def train_original(self, org_layers, embedding_trick, configs: dict, exp: str):
+        from .evaluation import evaluate
+        org = self.data.orgGraph
+        model = org_layers(2 * len(org.relations) + 1, self.hidden_l, self.data.num_classes, org.num_nodes,
+                           self.emb_dim, configs['num_sums'])
+        if exp != 'baseline' and configs['e_trans']:
+            emb = embedding_trick(org, self.data.sumGraphs, self.emb_dim, device=self.device)
+            model.load_embedding(emb, freeze=configs['e_freeze'])
+        if exp != 'baseline' and configs['w_trans']:
+            self.transfer_weights(model, configs['w_grad'])
+        loss_f, activation = get_losst(configs['dataset'], sumModel=False)
+        acc, loss, f1_w, f1_m = self.train(model, org, loss_f, activation, sum_graph=False)
+        td = org.training_data
+        test = evaluate(model, activation, td, td.x_test, td.y_test)
+        return acc, loss, f1_w, f1_m, test[0], test[1], test[2], model

@@ -352,9 +352,10 @@ class _LocalComm:
         self.table[key_rows] = full
 
     def all_gather_rows(self, t):
-        full = self.table[t.size(1)]
-        out = full.new_zeros((self.world * self.chunk, full.size(1)))
-        out[:full.size(0)] = full
+        # the layer gathers the zero-padded 16-byte aligned mirror of odd-width rows (63 -> 64)
+        full = self.table.get(t.size(1), self.table.get(t.size(1) - 1))
+        out = full.new_zeros((self.world * self.chunk, t.size(1)))
+        out[:full.size(0), :full.size(1)] = full
         return out
 
     def all_reduce_sum_(self, tensors):
