@@ -291,11 +291,13 @@ def run_engine(args):
     for name, dims, ms in recs:
         agg.setdefault((name, dims[0], dims[1]), []).append(ms)
     # the self-loop (root + bias) launch belongs to the pass whose bytes include the N x (Fin + Fout) term
+    self_ms = {}
     for (name, d0, d1), v in list(agg.items()):
         if name == 'self_loop':
             for host in ('tile_fwd', 'tile_dx'):
                 if (host, d0, d1) in agg and len(agg[(host, d0, d1)]) == len(v):
                     agg[(host, d0, d1)] = [x + y for x, y in zip(agg[(host, d0, d1)], v)]
+                    self_ms[(host, d0, d1)] = statistics.mean(v)
                     del agg[(name, d0, d1)]
                     break
     tot = {k: sum(v) for k, v in agg.items()}
@@ -317,7 +319,8 @@ def run_engine(args):
     f2, b2 = algorithmic_bytes(n, e, HIDDEN, CLASSES)
     step_bytes = f1 + b1 + f2 + b2
     passes = {f'{k[0]}_{k[1]}x{k[2]}': {'avg_ms': statistics.mean(v), 'launches': len(v),
-                                        'gbps_algorithmic': (pb[k] / (statistics.mean(v) * 1e-3) / 1e9) if k in pb else None}
+                                        'gbps_algorithmic': (pb[k] / (statistics.mean(v) * 1e-3) / 1e9) if k in pb else None,
+                                        **({'of_which_self_loop_ms': self_ms[k]} if k in self_ms else {})}
               for k, v in sorted(agg.items())}
 
     # end to end: the reference's Trainer.train iteration body through the public (drop-in) API,
@@ -339,18 +342,33 @@ def run_engine(args):
             return loss.item()
         return e2e_step
 
-    e2e_ms = torch_adam_ms = float('nan')
+    e2e_ms = torch_adam_ms = eager_ms = float('nan')
     if not args.no_e2e:
         # the package's Trainer step: engine layers + the engine's one-pass Adam (rgcn_b200.trainer.make_optimizer)
-        e2e_ms = time_steps(make_e2e_step(make_optimizer(model)), args.steps, args.warmup, world, device) / args.steps
+        eager_ms = time_steps(make_e2e_step(make_optimizer(model)), args.steps, args.warmup, world, device) / args.steps
+        # the same step captured once in a CUDA graph (rgcn_b200.trainer.GraphedTrainStep) and replayed:
+        # the labelled batch is still copied from pinned host memory and the loss read back every step
+        from rgcn_b200.trainer import GraphedTrainStep
+        data.x_train, data.y_train = x_train_h.to(device), y_train_h.to(device)
+        graphed = GraphedTrainStep(model, data, make_optimizer(model, capturable=True), ce_loss, identity)
+
+        graphed.prefetch(x_train_h, y_train_h)
+
+        def graphed_step():
+            loss = graphed()                              # consumes the batch prefetched during the previous step
+            graphed.prefetch(x_train_h, y_train_h)        # next step's H2D overlaps this step's kernels
+            return loss.item()
+        e2e_ms = time_steps(graphed_step, args.steps, args.warmup, world, device) / args.steps
         # same step with torch.optim.Adam, i.e. what the unmodified reference Trainer runs on the drop-in layers
         torch_adam_ms = time_steps(make_e2e_step(make_optimizer(model, fused=False)), args.steps, args.warmup, world,
                                    device) / args.steps
     e2e = {'value': e / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4,
-           'ms_per_step': e2e_ms, 'ms_per_step_with_torch_adam': torch_adam_ms,
-           'what': 'Trainer.train iteration body (modelTrainer.py:61-69) via Emb_Layers on the drop-in RGCNConv: '
-                   'pinned H2D of x_train/y_train, fwd, CE loss, bwd, Adam step (engine FusedAdam, same update rule as '
-                   'torch.optim.Adam(lr, weight_decay); incl. the [N,63] embedding), loss.item()'}
+           'ms_per_step': e2e_ms, 'ms_per_step_eager': eager_ms, 'ms_per_step_eager_torch_adam': torch_adam_ms,
+           'what': 'Trainer.train iteration body (modelTrainer.py:61-69) via Emb_Layers on the drop-in RGCNConv, captured '
+                   'in a CUDA graph (GraphedTrainStep): pinned H2D of x_train/y_train every step (copy stream, overlapping the previous step), fwd, CE loss, bwd, Adam step '
+                   '(engine FusedAdam, same update rule as torch.optim.Adam(lr, weight_decay); incl. the [N,63] '
+                   'embedding), loss.item(); ms_per_step_eager = the same step launched eagerly, '
+                   '..._torch_adam = eagerly with torch.optim.Adam'}
 
     # K5 map gather at this graph's size (3 summaries, sum mode): achieved GB/s, reported beside the layer
     map_gather = None

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RGCN_B200_ABI_VERSION 2
+#define RGCN_B200_ABI_VERSION 3
 
 typedef enum {
     RGCN_OK = 0,
@@ -148,6 +148,13 @@ int rgcn_eval_counts(const float* pred, int64_t ldp, int32_t num_classes, const 
  * amsgrad / maximize off).  `step` counts from 1. */
 int rgcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream);
+
+/* Same update with the step count read from DEVICE memory (*step_dev >= 1, incremented by the caller
+ * on the same stream before the call): nothing step-dependent is baked into the launch, so a
+ * training step that contains it can be captured once in a CUDA graph and replayed. */
+int rgcn_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, const int64_t* step_dev,
+                       void* stream);
 
 /* Zero-padded, 16-byte addressable mirror of an odd-width feature matrix (e.g. the reference's
  * emb = 63): dst[r][c] = c < cols ? src[r][c] : 0 for c < ldd.  Passing the mirror (ldx = ldd) as x

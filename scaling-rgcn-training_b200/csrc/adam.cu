@@ -13,7 +13,13 @@ namespace {
 
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, int64_t n, float lr_over_bc1, float beta1,
-                                              float beta2, float eps, float wd, float inv_sqrt_bc2) {
+                                              float beta2, float eps, float wd, float inv_sqrt_bc2,
+                                              const int64_t* __restrict__ step_dev, float lr) {
+    if (step_dev) {   // graph-replayable form: the step count lives on the device, same double-precision formulas
+        const double t = (double)*step_dev;
+        lr_over_bc1 = (float)((double)lr / (1.0 - pow((double)beta1, t)));
+        inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)beta2, t)));
+    }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
         const float pi = p[i];
@@ -41,7 +47,22 @@ extern "C" int rgcn_adam_step(float* param, const float* grad, float* exp_avg, f
     note_launch(1);
     const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
     k_adam<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(lr / bc1), beta1, beta2, eps,
-                                                   weight_decay, (float)(1.0 / sqrt(bc2)));
+                                                   weight_decay, (float)(1.0 / sqrt(bc2)), nullptr, lr);
+    RGCN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int rgcn_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                  float beta1, float beta2, float eps, float weight_decay, const int64_t* step_dev,
+                                  void* stream) {
+    using namespace rgcn;
+    if (!param || !grad || !exp_avg || !exp_avg_sq || n < 0 || !step_dev)
+        return fail(RGCN_ERR_INVALID_ARG, "rgcn_adam_step_dev: bad argument");
+    if (n == 0) return 0;
+    note_launch(1);
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    k_adam<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, 0.f, beta1, beta2, eps,
+                                                   weight_decay, 0.f, step_dev, lr);
     RGCN_CUDA(cudaGetLastError());
     return 0;
 }

@@ -131,6 +131,7 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     p.kp = kp; p.np = np;
     p.relu_in = relu;
     p.vec4 = v4;
+    p.out_rows = g->n_own;
     if ((rc = launch_chunk_prepass(p, st))) return rc;
     if (et) {   // root + bias with plain stores (initialises the target), then the edge tiles accumulate
         if ((rc = launch_selfloop_pass(p, g->own_lo, g->n_own, g->R, g->num_sms, st))) return rc;
@@ -197,7 +198,12 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     float4* wtfrag = (float4*)ws.take<float>((int64_t)(g->R + 1) * kp * np * 2);
     float2* wtfrag2 = (float2*)ws.take<float>((int64_t)(g->R + 1) * kp * np);
     float* gaux = ws.take<float>((int64_t)g->brc[RGCN_BRC_BWD].num_chunks * np);
-    const bool direct = gx && direct_target(gx, ldgx, fin);
+    // dx target: gx itself when its rows are whole aligned quads, or tightly packed odd-width rows that
+    // the bulk-reduce scatter can address (Fin = 63); else a padded buffer + column copy
+    const bool dx_v4ok = gx && etile_vec4_ok(gout_gather, ldgg, fout, nullptr);
+    const bool packed = gx && !direct_target(gx, ldgx, fin) && dx_v4ok && etile_choice(np, dx_v4ok) &&
+                        etile_packed_ok(gx, ldgx, fin, kp);
+    const bool direct = gx && (packed || direct_target(gx, ldgx, fin));
     float* target = gx ? (direct ? gx : ws.take<float>((int64_t)g->n_own * kp)) : nullptr;
     if (!ws.ok) return fail(RGCN_ERR_WORKSPACE, "rgcn_layer_bwd: workspace too small (see rgcn_layer_workspace_bytes)");
     if (need_w) {
@@ -239,6 +245,8 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
         p.relu_in = false;
         p.transposed = true;
         p.vec4 = v4;
+        p.packed = packed && v4;
+        p.out_rows = g->n_own;
         if ((rc = launch_chunk_prepass(p, st))) return rc;
         if (et) {
             if ((rc = launch_selfloop_pass(p, g->own_lo, g->n_own, g->R, g->num_sms, st))) return rc;

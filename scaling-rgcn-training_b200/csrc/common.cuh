@@ -103,7 +103,11 @@ struct TilePass {
     bool transposed;                                // dL/dx pass (profiling tag only)
     bool vec4;                                      // entry-tile kernel: 16-byte row loads, wfrag prepared with perm
     int tag_out;                                    // logical output width (profiling tag)
+    bool packed;                                    // out rows are tightly packed with an odd width (ldo == nout,
+                                                    // not a multiple of 4): bulk-reduce scatter into shifted windows
+    int64_t out_rows;                               // rows of `out` (packed mode: bound of the last window)
 };
+bool etile_packed_ok(const float* out, int64_t ldo, int nout, int np);
 int launch_chunk_prepass(const TilePass& p, cudaStream_t st);
 int launch_tile_pass(const TilePass& p, int num_sms, cudaStream_t st);
 

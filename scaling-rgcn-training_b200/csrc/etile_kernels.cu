@@ -50,6 +50,7 @@ struct ETileArgs {
     float* out;
     int64_t ldo;
     int nout;
+    int64_t out_elems;   // packed mode: floats in `out`
     // dL/dW only
     const float* gout;
     int64_t ldg;
@@ -71,6 +72,8 @@ __device__ __forceinline__ void split_rn(float x, uint32_t& hi, uint32_t& lo) {
     hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 struct RowRef {   // one gathered row of a lane
     const float* p;   // row pointer + lane's k offset
@@ -102,9 +105,28 @@ __device__ __forceinline__ RowRef make_ref(const ETileArgs& a, int e, bool valid
 // columns 16j+4t..+3, which serve K slots (t, t+4) of steps 2j and 2j+1; the B fragments are
 // prepared with the matching row permutation (k_wprep perm).  K is a contraction index, so any
 // consistent permutation is exact.
-template <int KT, int NT, bool RELU, bool V4>
+//
+// BULK: the scatter goes through shared memory and the bulk-copy engine instead of the LSU: the
+// warp parks its 16 x (8 NT) result tile in a (double-buffered, bank-skewed) shared tile and 16
+// lanes each issue ONE cp.reduce.async.bulk (f32 add) of a whole row to out[owner].  A vector RED
+// costs ~1.3 LSU cycles per LANE whatever its width, so a 64-column row is 16 lane-slots; as a
+// bulk reduce it is one request to the copy engine.
+template <int NT>
+struct BulkTile {
+    static constexpr int ROWW = NT * 8 + 8;        // words per staged row: +8 skews rows over the banks
+    static constexpr int WARP_WORDS = 2 * 16 * ROWW;   // two buffers
+    static constexpr int CTA_BYTES = EW * WARP_WORDS * 4;
+};
+
+//
+// BULK == 2 (packed odd-width rows, e.g. the [N, 63] embedding gradient): row i starts at float
+// 63 i, which is 16-byte aligned only for i % 4 == 0.  The row is staged shifted by f = (63 i) % 4
+// with zeros around it and the reduce covers the aligned window [63 i - f, +8 NT + 4): the
+// neighbours receive +0.0f.  No padded target, no column copy afterwards.
+template <int KT, int NT, bool RELU, bool V4, int BULK = 0>
 __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(const ETileArgs a) {
     constexpr int KP = KT * 8;
+    extern __shared__ __align__(16) float bulk_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int gw = blockIdx.x * EW + warp, nw = gridDim.x * EW;
@@ -160,6 +182,14 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
     const int num_units = (a.num_tiles + UT - 1) / UT;
     for (int unit = gw; unit < num_units; unit += nw) {
         const int t0 = unit * UT, t1 = min(a.num_tiles, t0 + UT);
+        // this warp's NEXT unit: its tile list and entry streams are pulled into L2 while this one runs
+        // (pays only where a tile is long enough to cover the L2 trip: wide gathered rows)
+        const int tn0 = (unit + nw) * UT;
+        int pf_e0 = -1;
+        if (KT >= 4 && tn0 < a.num_tiles) {
+            pf_e0 = a.tile_e0[tn0];
+            if (lane < 2) prefetch_l2(lane ? (const void*)(a.tile_info + tn0) : (const void*)(a.tile_e0 + tn0));
+        }
         // pipeline: indices two tiles ahead, rows one tile ahead of the tensor-pipe work
         TileRef cur = load_meta(t0), nxt = cur;
         if (t0 + 1 < t1) nxt = load_meta(t0 + 1);
@@ -230,6 +260,61 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
                     d[n][3] += by;
                 }
             }
+            if constexpr (BULK != 0) {
+                using BT = BulkTile<NT>;
+                float* buf = bulk_smem + warp * BT::WARP_WORDS + ((ti - t0) & 1) * (16 * BT::ROWW);
+                // the bulk reads of this buffer (issued two tiles ago) must be over before it is rewritten
+                if (lane < 16) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                if constexpr (BULK == 2) {
+                    const int fg = cg.own >= 0 ? (int)(((int64_t)cg.own * a.ldo) & 3) : 0;
+                    const int fh = ch.own >= 0 ? (int)(((int64_t)ch.own * a.ldo) & 3) : 0;
+                    float* rg = buf + g * BT::ROWW;
+                    float* rh = buf + (g + 8) * BT::ROWW;
+                    rg[t < fg ? t : NT * 8 + t] = 0.f;   // the 4 window cells outside [f, f + 8 NT)
+                    rh[t < fh ? t : NT * 8 + t] = 0.f;
+                    rg += fg + 2 * t;
+                    rh += fh + 2 * t;
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) {
+                        rg[8 * n] = d[n][0];
+                        rg[8 * n + 1] = d[n][1];
+                        rh[8 * n] = d[n][2];
+                        rh[8 * n + 1] = d[n][3];
+                    }
+                } else {
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) {
+                        *reinterpret_cast<float2*>(buf + g * BT::ROWW + 8 * n + 2 * t) = make_float2(d[n][0], d[n][1]);
+                        *reinterpret_cast<float2*>(buf + (g + 8) * BT::ROWW + 8 * n + 2 * t) = make_float2(d[n][2], d[n][3]);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                const int o1 = __shfl_sync(FULL, cg.own, (lane & 7) * 4);
+                const int o2 = __shfl_sync(FULL, ch.own, (lane & 7) * 4);
+                const int own = lane < 8 ? o1 : o2;
+                if (lane < 16) {
+                    if (own >= 0) {
+                        const uint32_t src = (uint32_t)__cvta_generic_to_shared(buf + lane * BT::ROWW);
+                        if constexpr (BULK == 2) {
+                            const int64_t off = (int64_t)own * a.ldo, w0 = off & ~(int64_t)3;
+                            if (w0 + NT * 8 + 4 <= a.out_elems) {
+                                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                             ::"l"(a.out + w0), "r"(src), "n"(NT * 32 + 16) : "memory");
+                            } else {   // the window of the very last rows would pass the end of the buffer
+                                const float* srow = buf + lane * BT::ROWW + (int)(off & 3);
+                                for (int c = 0; c < a.nout; ++c) atomicAdd(a.out + off + c, srow[c]);
+                            }
+                        } else {
+                            float* dst = a.out + (int64_t)own * a.ldo;
+                            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                         ::"l"(dst), "r"(src), "n"(NT * 32) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else {
             const bool odd = (t & 1) != 0;
 #pragma unroll
             for (int j = 0; j < NT / 2; ++j) {
@@ -248,13 +333,26 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
                     }
                 }
             }
+            }
             cur = nxt;
             nxt = nn;
 #pragma unroll
             for (int kt = 0; kt < KT; ++kt)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) av[kt][i] = avn[kt][i];
+            if (ti == t0 + 1 && pf_e0 >= 0 && lane < 24) {   // UT*16 entries = 8 lines per stream
+                const int e = pf_e0 + (lane & 7) * 32;
+                const void* p = lane < 8 ? (const void*)(a.e_idx + e) : lane < 16 ? (const void*)(a.e_w + e) : (const void*)(a.e_own + e);
+                prefetch_l2(p);
+            }
         }
+        if constexpr (BULK != 0) {   // the next unit restarts the buffer parity
+            if (lane < 16) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+        }
+    }
+    if constexpr (BULK != 0) {
+        if (lane < 16) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
 
@@ -443,9 +541,12 @@ struct SelfArgs {
     int64_t n_own;
 };
 
-template <int KT, int NT, bool RELU, bool V4>
+// PACK: `out` rows are tightly packed with a width that is not a multiple of 4 (ldo == nout): the
+// warp's 16 rows are one contiguous, 64-byte aligned span, staged in shared memory and written flat.
+template <int KT, int NT, bool RELU, bool V4, bool PACK = false>
 __global__ void __launch_bounds__(EW * 32, 2) k_selfloop(const SelfArgs a) {
     constexpr bool BREG = (KT * NT <= 16);
+    __shared__ __align__(16) float pack_stage[PACK ? EW * 16 * NT * 8 : 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int64_t gw = (int64_t)blockIdx.x * EW + warp, nw = (int64_t)gridDim.x * EW;
@@ -531,6 +632,34 @@ __global__ void __launch_bounds__(EW * 32, 2) k_selfloop(const SelfArgs a) {
                 mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
             }
         }
+        if constexpr (PACK) {
+            float* sb = pack_stage + warp * (16 * NT * 8);
+            const int w = a.nout;
+            __syncwarp();
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                const int col = 8 * n + 2 * t;
+                if (col < w) {
+                    sb[g * w + col] = d[n][0];
+                    sb[(g + 8) * w + col] = d[n][2];
+                }
+                if (col + 1 < w) {
+                    sb[g * w + col + 1] = d[n][1];
+                    sb[(g + 8) * w + col + 1] = d[n][3];
+                }
+            }
+            __syncwarp();
+            const int rows = (int)min((int64_t)16, a.n_own - tile * 16);
+            const int total = rows * w;
+            float* base = a.out + tile * 16 * w;   // 16 w floats per tile: 64-byte aligned
+            for (int i = lane * 4; i < total; i += 128) {
+                if (i + 4 <= total) {
+                    *reinterpret_cast<float4*>(base + i) = *reinterpret_cast<const float4*>(sb + i);
+                } else {
+                    for (int c = i; c < total; ++c) base[c] = sb[c];
+                }
+            }
+        } else {
         const bool odd = (t & 1) != 0;
 #pragma unroll
         for (int j = 0; j < NT / 2; ++j) {
@@ -548,11 +677,12 @@ __global__ void __launch_bounds__(EW * 32, 2) k_selfloop(const SelfArgs a) {
                 }
             }
         }
+        }
     }
 }
 
 template <int KT, int NT>
-int run_selfloop(const SelfArgs& a, bool relu, bool v4, int num_sms, cudaStream_t st) {
+int run_selfloop(const SelfArgs& a, bool relu, bool v4, bool packed, int num_sms, cudaStream_t st) {
     auto launch = [&](auto kern) -> int {
         const int64_t tiles = (a.n_own + 15) / 16;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + EW - 1) / EW, (int64_t)num_sms * 2));
@@ -560,6 +690,13 @@ int run_selfloop(const SelfArgs& a, bool relu, bool v4, int num_sms, cudaStream_
         RGCN_CUDA(cudaGetLastError());
         return 0;
     };
+    if constexpr (NT == 8) {
+        if (packed) {
+            if (!v4) return fail(RGCN_ERR_UNSUPPORTED, "packed self-loop pass needs 16-byte addressable gathered rows");
+            if (relu) return launch(k_selfloop<KT, NT, true, true, true>);
+            return launch(k_selfloop<KT, NT, false, true, true>);
+        }
+    }
     if (v4) {
         if (relu) return launch(k_selfloop<KT, NT, true, true>);
         return launch(k_selfloop<KT, NT, false, true>);
@@ -568,18 +705,44 @@ int run_selfloop(const SelfArgs& a, bool relu, bool v4, int num_sms, cudaStream_
     return launch(k_selfloop<KT, NT, false, false>);
 }
 
+// rows of at least this many 8-column steps are scattered by the bulk-copy engine (0 = never)
+int bulk_min_nt() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RGCN_B200_BULK");
+        v = e ? atoi(e) : 8;
+    }
+    return v;
+}
+
 template <int KT, int NT>
-int run_etile(const ETileArgs& a, bool relu, bool v4, int num_sms, cudaStream_t st) {
-    auto launch = [&](auto kern) -> int {
+int run_etile(const ETileArgs& a, bool relu, bool v4, bool packed, int num_sms, cudaStream_t st) {
+    auto launch = [&](auto kern, int smem = 0) -> int {
         int per_sm = 1;
-        RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EW * 32, 0));
+        if (smem > 48 * 1024) RGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EW * 32, smem));
         per_sm = std::max(per_sm, 1);
         const int64_t units = ((int64_t)a.num_tiles + UT - 1) / UT;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + EW - 1) / EW, (int64_t)num_sms * per_sm));
-        kern<<<grid, EW * 32, 0, st>>>(a);
+        kern<<<grid, EW * 32, smem, st>>>(a);
         RGCN_CUDA(cudaGetLastError());
         return 0;
     };
+    // bulk scatter: whole padded rows (8 NT floats) are added, so the target row must hold them
+    if constexpr (NT == 8) {
+        if (packed) {
+            if (!v4) return fail(RGCN_ERR_UNSUPPORTED, "packed scatter needs 16-byte addressable gathered rows");
+            if (relu) return launch(k_etile<KT, NT, true, true, 2>, BulkTile<NT>::CTA_BYTES);
+            return launch(k_etile<KT, NT, false, true, 2>, BulkTile<NT>::CTA_BYTES);
+        }
+    }
+    if (packed) return fail(RGCN_ERR_UNSUPPORTED, "packed scatter is built for 64-column rows only");
+    const bool bulk = v4 && bulk_min_nt() > 0 && NT >= bulk_min_nt() && a.ldo >= 8 * NT && a.ldo % 4 == 0 &&
+                      ((uintptr_t)a.out & 15) == 0;
+    if (bulk) {
+        if (relu) return launch(k_etile<KT, NT, true, true, 1>, BulkTile<NT>::CTA_BYTES);
+        return launch(k_etile<KT, NT, false, true, 1>, BulkTile<NT>::CTA_BYTES);
+    }
     if (v4) {
         if (relu) return launch(k_etile<KT, NT, true, true>);
         return launch(k_etile<KT, NT, false, true>);
@@ -649,6 +812,17 @@ bool etile_vec4_ok(const float* feat, int64_t ldf, int kin, const float* aux) {
     return !off && ldf % 4 == 0 && ((kin + 3) & ~3) <= ldf && ((uintptr_t)feat & 15) == 0 && ((uintptr_t)aux & 15) == 0;
 }
 
+// tightly packed odd-width target rows (the [N, 63] gradient): bulk-reduce scatter into shifted windows
+bool etile_packed_ok(const float* out, int64_t ldo, int nout, int np) {
+    static int off = -1;
+    if (off < 0) {
+        const char* e = getenv("RGCN_B200_PACKED");
+        off = (e && e[0] == '0') ? 1 : 0;
+    }
+    return !off && bulk_min_nt() > 0 && bulk_min_nt() <= 8 && np == 64 && ldo == nout && nout % 4 != 0 && nout > 56 &&
+           ((uintptr_t)out & 15) == 0;
+}
+
 int launch_etile_pass(const TilePass& p, int num_sms, cudaStream_t st) {
     const Brc& b = *p.brc;
     if (b.num_tiles == 0) return 0;
@@ -667,10 +841,11 @@ int launch_etile_pass(const TilePass& p, int num_sms, cudaStream_t st) {
     a.ldo = p.ldo;
     a.nout = p.nout;
     a.num_tiles = b.num_tiles_noself;   // the self loops were written by launch_selfloop_pass
+    a.out_elems = p.out_rows * p.ldo;
     if (a.num_tiles == 0) return 0;
     ProfScope prof(p.transposed ? TAG_TILE_BWD : TAG_TILE_FWD, p.kin, p.tag_out, st);
     note_launch(1);
-    RGCN_DISPATCH_E(run_etile, p.kp, p.np, a, p.relu_in, p.vec4, num_sms, st);
+    RGCN_DISPATCH_E(run_etile, p.kp, p.np, a, p.relu_in, p.vec4, p.packed, num_sms, st);
 }
 
 // out[i] = act(x[own_lo + i]) . root + bias for every owned row (plain stores: also initialises `out`)
@@ -689,7 +864,7 @@ int launch_selfloop_pass(const TilePass& p, int64_t own_lo, int64_t n_own, int R
     a.n_own = n_own;
     ProfScope prof(TAG_SELF, p.kin, p.tag_out, st);
     note_launch(1);
-    RGCN_DISPATCH_E(run_selfloop, p.kp, p.np, a, p.relu_in, p.vec4, num_sms, st);
+    RGCN_DISPATCH_E(run_selfloop, p.kp, p.np, a, p.relu_in, p.vec4, p.packed, num_sms, st);
 }
 
 int launch_ewgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st) {

@@ -17,7 +17,7 @@ EXPORTS = (
     'rgcn_last_error', 'rgcn_abi_version', 'rgcn_graph_create', 'rgcn_graph_create_part', 'rgcn_graph_destroy', 'rgcn_graph_query',
     'rgcn_graph_export', 'rgcn_layer_workspace_bytes', 'rgcn_layer_fwd', 'rgcn_layer_bwd', 'rgcn_map_gather',
     'rgcn_kernel_launch_count', 'rgcn_profile_enable', 'rgcn_profile_collect', 'rgcn_pad_rows',
-    'rgcn_eval_counts', 'rgcn_adam_step',
+    'rgcn_eval_counts', 'rgcn_adam_step', 'rgcn_adam_step_dev',
 )
 
 BRC_FWD, BRC_BWD, BRC_FWD_REL = 0, 1, 2
@@ -71,6 +71,8 @@ def load():
     lib.rgcn_eval_counts.argtypes = [vp, i64, i32, vp, i64, vp, i32, vp, vp]
     lib.rgcn_adam_step.restype = C.c_int
     lib.rgcn_adam_step.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, vp]
+    lib.rgcn_adam_step_dev.restype = C.c_int
+    lib.rgcn_adam_step_dev.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
     lib.rgcn_pad_rows.restype = C.c_int
     lib.rgcn_pad_rows.argtypes = [vp, i64, i32, vp, i64, i64, vp]
     lib.rgcn_kernel_launch_count.restype = i64

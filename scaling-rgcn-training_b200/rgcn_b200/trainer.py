@@ -3,6 +3,7 @@
 mirrored so bench.py and the tests can drive the engine the way the reference does."""
 from __future__ import annotations
 
+import copy
 from typing import Callable, Tuple
 
 import torch
@@ -28,12 +29,13 @@ def get_losst(dataset: str, sumModel: bool = False) -> Tuple[Callable, Callable]
     return ce_loss, identity
 
 
-def make_optimizer(model: nn.Module, lr: float = 0.01, weight_decay: float = 5e-5, fused: bool = True):
+def make_optimizer(model: nn.Module, lr: float = 0.01, weight_decay: float = 5e-5, fused: bool = True,
+                   capturable: bool = False):
     """Adam as modelTrainer.py:44 builds it (weight_d = 5e-5 from main.py:52): the engine's one-pass
     FusedAdam (same update rule) by default, torch.optim.Adam with fused=False."""
     if fused:
         from .optim import FusedAdam
-        return FusedAdam(model.parameters(), lr=lr, weight_decay=weight_decay)
+        return FusedAdam(model.parameters(), lr=lr, weight_decay=weight_decay, capturable=capturable)
     return torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
 
 
@@ -46,6 +48,98 @@ def train_step(model: nn.Module, training_data, optimizer, loss_f: Callable, act
     loss.backward()
     optimizer.step()
     return loss.item()
+
+
+class GraphedTrainStep:
+    """The same iteration body (modelTrainer.py:61-69) captured ONCE in a CUDA graph and replayed:
+    one graph launch per step instead of ~60 kernel launches plus the Python between them.
+
+    ``x_train`` / ``y_train`` live in static device buffers that ``__call__`` refills (from pinned
+    host memory or device tensors) before each replay; the loss comes back as a device scalar.
+    Capture needs one eager step (lazy initialisation, CSR build, optimiser state); the parameters
+    and optimiser state are restored afterwards, so step k of the graphed loop equals step k of the
+    eager loop.  The optimiser must be a ``FusedAdam(capturable=True)``
+    (``make_optimizer(..., capturable=True)``)."""
+
+    def __init__(self, model: nn.Module, training_data, optimizer, loss_f: Callable, activation: Callable) -> None:
+        if not getattr(optimizer, 'capturable', False):
+            raise ValueError('GraphedTrainStep needs make_optimizer(..., capturable=True)')
+        self.model, self.td, self.opt = model, training_data, optimizer
+        self.loss_f, self.activation = loss_f, activation
+        dev = training_data.x_train.device
+        if dev.type != 'cuda':
+            raise ValueError('GraphedTrainStep: training data must be on the GPU')
+        self._copy_stream, self._next_slot, self._pending = None, 0, []
+        self.x_static = training_data.x_train.clone()
+        self.y_static = training_data.y_train.clone()
+        self._td = copy.copy(training_data)     # shallow: same edge tensors (the CSR cache is keyed on them)
+        self._td.x_train, self._td.y_train = self.x_static, self.y_static
+        params = [p for p in model.parameters()]
+        snapshot = [p.detach().clone() for p in params]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._body()                                   # eager warm-up on the capture stream
+            with torch.no_grad():
+                for p, s in zip(params, snapshot):
+                    p.copy_(s)
+            optimizer.reset_state()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss_static = self._body()
+
+    def _body(self) -> Tensor:
+        self.model.train()
+        self.opt.zero_grad(set_to_none=True)
+        out = self.model(self._td, self.activation)
+        targets = self.y_static.to(torch.float32)
+        loss = self.loss_f(out[self.x_static], targets)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def prefetch(self, x_train: Tensor, y_train: Tensor) -> None:
+        """Starts the host->device copy of the NEXT step's labelled batch on a copy stream (double-
+        buffered staging), so it overlaps the step that is running; the next ``__call__()`` without
+        arguments consumes it."""
+        dev = self.x_static.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staging = [(torch.empty_like(self.x_static), torch.empty_like(self.y_static)) for _ in range(2)]
+            self._events = [torch.cuda.Event(), torch.cuda.Event()]
+            self._consumed = [None, None]
+        k = self._next_slot
+        self._next_slot ^= 1
+        if self._consumed[k] is not None:                  # the D2D that last read this slot must be over
+            self._copy_stream.wait_event(self._consumed[k])
+        with torch.cuda.stream(self._copy_stream):
+            self._staging[k][0].copy_(x_train, non_blocking=True)
+            self._staging[k][1].copy_(y_train, non_blocking=True)
+            self._events[k].record(self._copy_stream)
+        self._pending.append(k)
+
+    def __call__(self, x_train: Tensor = None, y_train: Tensor = None) -> Tensor:
+        """Replays one step; returns the loss as a device scalar (``.item()`` to read it).  With
+        arguments the batch is copied on the current stream first; without, a prefetched batch (if
+        any) is used, else the batch already in the static buffers."""
+        cur = torch.cuda.current_stream(self.x_static.device)
+        if x_train is not None or y_train is not None:
+            if x_train is not None:
+                self.x_static.copy_(x_train, non_blocking=True)
+            if y_train is not None:
+                self.y_static.copy_(y_train, non_blocking=True)
+        elif self._pending:
+            k = self._pending.pop(0)
+            cur.wait_event(self._events[k])
+            self.x_static.copy_(self._staging[k][0], non_blocking=True)
+            self.y_static.copy_(self._staging[k][1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._consumed[k] = ev
+        self.graph.replay()
+        return self.loss_static
 
 
 class Trainer:
