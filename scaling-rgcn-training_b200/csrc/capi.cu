@@ -85,7 +85,8 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     const bool relu = (flags & RGCN_F_RELU_IN) != 0;
     const int kp = pad_dim(fin), np = pad_dim(fout);
     // tile kernels address gathered rows with 32-bit element offsets
-    const bool big = (uint64_t)g->N * (uint64_t)ldx >= (1ull << 32);
+    const bool big = (uint64_t)g->N * (uint64_t)ldx >= (1ull << 32) ||
+                     (uint64_t)g->n_own * (uint64_t)std::max<int64_t>(ldo, np) >= (1ull << 32);
     if ((flags & RGCN_F_FORCE_SIMPLE) || !kp || !np || big) {
         RGCN_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)fout * 4, (size_t)g->n_own, st));
         SimplePass p{};
@@ -163,7 +164,8 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     const bool relu = (flags & RGCN_F_RELU_IN) != 0;
     const int kp = pad_dim(fin), np = pad_dim(fout);
     const bool big = (uint64_t)g->N * (uint64_t)ldx >= (1ull << 32) ||
-                     (uint64_t)g->N * (uint64_t)(gout_gather ? ldgg : ldg) >= (1ull << 32);
+                     (uint64_t)g->N * (uint64_t)(gout_gather ? ldgg : ldg) >= (1ull << 32) ||
+                     (uint64_t)g->n_own * (uint64_t)std::max<int64_t>(ldgx, kp) >= (1ull << 32);
     const bool simple = (flags & RGCN_F_FORCE_SIMPLE) || !kp || !np || big;
     const bool need_w = gweight || groot || gbias;
     int rc;

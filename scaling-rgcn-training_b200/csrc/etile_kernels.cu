@@ -123,14 +123,35 @@ struct BulkTile {
 // 63 i, which is 16-byte aligned only for i % 4 == 0.  The row is staged shifted by f = (63 i) % 4
 // with zeros around it and the reduce covers the aligned window [63 i - f, +8 NT + 4): the
 // neighbours receive +0.0f.  No padded target, no column copy afterwards.
+// Metadata staging: a warp's unit is UTU consecutive tiles = one contiguous span of <= 16 UTU entries.
+// The unit's e_idx / e_w / e_own slices and its tile list are copied global -> shared with 16-byte
+// cp.async ONE UNIT AHEAD (double buffered), so the tile loop reads its indices from shared memory:
+// no per-tile index loads from global, no exposed index latency, no deep register pipeline.
+template <int BULK>
+struct MetaStage {
+    static constexpr int UTU = (BULK != 0) ? 8 : UT;   // bulk kernels also park result tiles in shared memory
+    static constexpr int SPAN = UTU * 16 + 4;          // entries staged per unit (start rounded down to a quad)
+    static constexpr int MW = 3 * SPAN + 2 * UTU;      // words per buffer: idx, w, own, tile_e0, tile_info
+    static constexpr int WARP_WORDS = 2 * MW;
+    static constexpr int CTA_BYTES = EW * WARP_WORDS * 4;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+
 template <int KT, int NT, bool RELU, bool V4, int BULK = 0>
 __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(const ETileArgs a) {
     constexpr int KP = KT * 8;
-    extern __shared__ __align__(16) float bulk_smem[];
+    using MS = MetaStage<BULK>;
+    constexpr int UTU = MS::UTU, SPAN = MS::SPAN, MW = MS::MW;
+    extern __shared__ __align__(16) uint32_t dyn_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int gw = blockIdx.x * EW + warp, nw = gridDim.x * EW;
-    const uint64_t pol_s = policy_evict_first();
+    uint32_t* meta = dyn_smem + warp * MS::WARP_WORDS;
+    [[maybe_unused]] float* bulk_smem = reinterpret_cast<float*>(dyn_smem + EW * MS::WARP_WORDS);
     const uint64_t pol_f =
         (uint64_t)a.n_rows * (uint64_t)a.ldf * 4ull <= (112ull << 20) ? policy_evict_last() : policy_evict_normal();
     constexpr bool BREG = (KT * NT <= 4);
@@ -141,12 +162,51 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
         RowRef g8, h8;
         int rel;
     };
-    auto load_meta = [&](int ti) {
+    const int num_units = (a.num_tiles + UTU - 1) / UTU;
+
+    // entry span [first, end) of a unit, read straight from the tile list (one unit ahead of its use)
+    auto unit_span = [&](int u, int& first, int& end) {
+        const int t0 = u * UTU, t1 = min(a.num_tiles, t0 + UTU);
+        first = a.tile_e0[t0];
+        end = a.tile_e0[t1 - 1] + (a.tile_info[t1 - 1] & 0xff);
+    };
+    auto stage_unit = [&](int u, int first, int end, uint32_t* m) {
+        const int eb = first & ~3;
+        const int nchunk = (end - eb + 3) >> 2;
+        for (int c = lane; c < nchunk; c += 32) {
+            cp_async16(m + 4 * c, a.e_idx + eb + 4 * c);
+            cp_async16(m + SPAN + 4 * c, a.e_w + eb + 4 * c);
+            cp_async16(m + 2 * SPAN + 4 * c, a.e_own + eb + 4 * c);
+        }
+        const int t0 = u * UTU;
+        if (lane < UTU / 4) cp_async16(m + 3 * SPAN + 4 * lane, a.tile_e0 + t0 + 4 * lane);
+        else if (lane < UTU / 2) cp_async16(m + 3 * SPAN + UTU + 4 * (lane - UTU / 4), a.tile_info + t0 + 4 * (lane - UTU / 4));
+    };
+    const float* const feat_t = a.feat + KOFF * t;   // lane bases: feature rows / chunk rows
+    const float* const aux_t = a.aux + KOFF * t;
+    const uint32_t n_rows = (uint32_t)a.n_rows, ldf = (uint32_t)a.ldf;
+    auto make_row = [&](const uint32_t* m, int o, bool valid) {
+        RowRef r;
+        uint32_t idx = 0;
+        r.w = 0.f;
+        r.own = -1;
+        if (valid) {
+            idx = m[o] & IDX_MASK;
+            r.w = __uint_as_float(m[SPAN + o]);
+            r.own = (int)m[2 * SPAN + o];
+        }
+        r.real = idx < n_rows;
+        const uint32_t off = r.real ? idx * ldf : (idx - n_rows) * (uint32_t)KP;   // < 2^32 elements (checked by the caller)
+        r.p = (r.real ? feat_t : aux_t) + off;
+        return r;
+    };
+    auto tile_ref = [&](const uint32_t* m, int i, int eb) {
         TileRef r;
-        const int e0 = a.tile_e0[ti], info = a.tile_info[ti];
+        const int e0 = (int)m[3 * SPAN + i], info = (int)m[3 * SPAN + UTU + i];
         r.rel = info >> 8;
-        r.g8 = make_ref<KP>(a, e0 + g, g < (info & 0xff), KOFF * t, pol_s);
-        r.h8 = make_ref<KP>(a, e0 + g + 8, g + 8 < (info & 0xff), KOFF * t, pol_s);
+        const int o = e0 - eb + g, cnt = info & 0xff;
+        r.g8 = make_row(m, o, g < cnt);
+        r.h8 = make_row(m, o + 8, g + 8 < cnt);
         return r;
     };
     // A fragments: raw loads (all independent); the arithmetic happens one tile later
@@ -179,34 +239,37 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
             }
         }
     };
-    const int num_units = (a.num_tiles + UT - 1) / UT;
-    for (int unit = gw; unit < num_units; unit += nw) {
-        const int t0 = unit * UT, t1 = min(a.num_tiles, t0 + UT);
-        // this warp's NEXT unit: its tile list and entry streams are pulled into L2 while this one runs
-        // (pays only where a tile is long enough to cover the L2 trip: wide gathered rows)
-        const int tn0 = (unit + nw) * UT;
-        int pf_e0 = -1;
-        if (KT >= 4 && tn0 < a.num_tiles) {
-            pf_e0 = a.tile_e0[tn0];
-            if (lane < 2) prefetch_l2(lane ? (const void*)(a.tile_info + tn0) : (const void*)(a.tile_e0 + tn0));
-        }
-        // pipeline: indices two tiles ahead, rows one tile ahead of the tensor-pipe work
-        TileRef cur = load_meta(t0), nxt = cur;
-        if (t0 + 1 < t1) nxt = load_meta(t0 + 1);
-        float av[KT][4], avn[KT][4];
-        load_rows(cur, av);
-        for (int ti = t0; ti < t1; ++ti) {
+
+    if (gw >= num_units) return;
+    int cur_first, cur_end, nxt_first = 0, nxt_end = 0;
+    unit_span(gw, cur_first, cur_end);
+    stage_unit(gw, cur_first, cur_end, meta);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (gw + nw < num_units) unit_span(gw + nw, nxt_first, nxt_end);
+    int buf = 0;
+    [[maybe_unused]] int bulk_par = 0;
+    for (int unit = gw; unit < num_units; unit += nw, buf ^= 1) {
+        const uint32_t* m = meta + buf * MW;
+        const int eb = cur_first & ~3;
+        const int nt = min(a.num_tiles, unit * UTU + UTU) - unit * UTU;
+        // next unit: its metadata goes to the other buffer while this one is processed
+        if (unit + nw < num_units) stage_unit(unit + nw, nxt_first, nxt_end, meta + (buf ^ 1) * MW);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        cur_first = nxt_first;
+        cur_end = nxt_end;
+        if (unit + 2 * nw < num_units) unit_span(unit + 2 * nw, nxt_first, nxt_end);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+
+        auto process = [&](const TileRef& cur, const float (&av)[KT][4]) {
             const int rel = cur.rel;
             const RowRef cg = cur.g8, ch = cur.h8;
-            if (ti + 1 < t1) load_rows(nxt, avn);
-            TileRef nn = nxt;
-            if (ti + 2 < t1) nn = load_meta(ti + 2);
             const float4* wf = a.wfrag + (int64_t)rel * (KT * NT * 32) + lane;
             const float2* wf2 = a.wfrag2 + (int64_t)rel * (KT * NT * 32) + lane;
             if constexpr (BREG) {   // few fragments: keep the current relation's in registers
                 if (rel != breg_rel) {
 #pragma unroll
-                    for (int i = 0; i < KT * NT; ++i) bfrag[i] = __ldg(wf + i * 32);
+                    for (int q = 0; q < KT * NT; ++q) bfrag[q] = __ldg(wf + q * 32);
                     breg_rel = rel;
                 }
             }
@@ -248,29 +311,18 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
                     mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
                 }
             }
-            if (rel == a.self_rel && a.bias != nullptr) {   // one self loop per owner: bias exactly once
-#pragma unroll
-                for (int n = 0; n < NT; ++n) {
-                    const int col = 8 * n + 2 * t;
-                    const float bx = col < a.nbias ? a.bias[col] : 0.f;
-                    const float by = col + 1 < a.nbias ? a.bias[col + 1] : 0.f;
-                    d[n][0] += bx;
-                    d[n][1] += by;
-                    d[n][2] += bx;
-                    d[n][3] += by;
-                }
-            }
             if constexpr (BULK != 0) {
                 using BT = BulkTile<NT>;
-                float* buf = bulk_smem + warp * BT::WARP_WORDS + ((ti - t0) & 1) * (16 * BT::ROWW);
+                float* bt = bulk_smem + warp * BT::WARP_WORDS + bulk_par * (16 * BT::ROWW);
+                bulk_par ^= 1;
                 // the bulk reads of this buffer (issued two tiles ago) must be over before it is rewritten
                 if (lane < 16) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 __syncwarp();
                 if constexpr (BULK == 2) {
                     const int fg = cg.own >= 0 ? (int)(((int64_t)cg.own * a.ldo) & 3) : 0;
                     const int fh = ch.own >= 0 ? (int)(((int64_t)ch.own * a.ldo) & 3) : 0;
-                    float* rg = buf + g * BT::ROWW;
-                    float* rh = buf + (g + 8) * BT::ROWW;
+                    float* rg = bt + g * BT::ROWW;
+                    float* rh = bt + (g + 8) * BT::ROWW;
                     rg[t < fg ? t : NT * 8 + t] = 0.f;   // the 4 window cells outside [f, f + 8 NT)
                     rh[t < fh ? t : NT * 8 + t] = 0.f;
                     rg += fg + 2 * t;
@@ -285,8 +337,8 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
                 } else {
 #pragma unroll
                     for (int n = 0; n < NT; ++n) {
-                        *reinterpret_cast<float2*>(buf + g * BT::ROWW + 8 * n + 2 * t) = make_float2(d[n][0], d[n][1]);
-                        *reinterpret_cast<float2*>(buf + (g + 8) * BT::ROWW + 8 * n + 2 * t) = make_float2(d[n][2], d[n][3]);
+                        *reinterpret_cast<float2*>(bt + g * BT::ROWW + 8 * n + 2 * t) = make_float2(d[n][0], d[n][1]);
+                        *reinterpret_cast<float2*>(bt + (g + 8) * BT::ROWW + 8 * n + 2 * t) = make_float2(d[n][2], d[n][3]);
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -296,14 +348,14 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
                 const int own = lane < 8 ? o1 : o2;
                 if (lane < 16) {
                     if (own >= 0) {
-                        const uint32_t src = (uint32_t)__cvta_generic_to_shared(buf + lane * BT::ROWW);
+                        const uint32_t src = (uint32_t)__cvta_generic_to_shared(bt + lane * BT::ROWW);
                         if constexpr (BULK == 2) {
                             const int64_t off = (int64_t)own * a.ldo, w0 = off & ~(int64_t)3;
                             if (w0 + NT * 8 + 4 <= a.out_elems) {
                                 asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
                                              ::"l"(a.out + w0), "r"(src), "n"(NT * 32 + 16) : "memory");
                             } else {   // the window of the very last rows would pass the end of the buffer
-                                const float* srow = buf + lane * BT::ROWW + (int)(off & 3);
+                                const float* srow = bt + lane * BT::ROWW + (int)(off & 3);
                                 for (int c = 0; c < a.nout; ++c) atomicAdd(a.out + off + c, srow[c]);
                             }
                         } else {
@@ -315,42 +367,47 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             } else {
-            const bool odd = (t & 1) != 0;
+                // lanes t, t^1 swap halves so that each holds 4 consecutive columns of one n-tile pair
+                const bool odd = (t & 1) != 0;
+                const uint32_t ldo = (uint32_t)a.ldo;
 #pragma unroll
-            for (int j = 0; j < NT / 2; ++j) {
-                const int col = odd ? 8 * (2 * j + 1) + 2 * (t - 1) : 8 * (2 * j) + 2 * t;
+                for (int j = 0; j < NT / 2; ++j) {
+                    const int col = 16 * j + (odd ? 6 : 0) + 2 * t;   // odd: 8(2j+1) + 2(t-1)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {   // h = 0: entry g ; h = 1: entry g + 8
-                    const float p0 = d[2 * j][2 * h], p1 = d[2 * j][2 * h + 1];
-                    const float q0 = d[2 * j + 1][2 * h], q1 = d[2 * j + 1][2 * h + 1];
-                    const float rx = __shfl_xor_sync(FULL, odd ? p0 : q0, 1);
-                    const float ry = __shfl_xor_sync(FULL, odd ? p1 : q1, 1);
-                    const int own = h ? ch.own : cg.own;
-                    if (own >= 0 && col < a.nout) {
-                        float* p = a.out + (int64_t)own * a.ldo + col;
-                        if (odd) red_add_v4(p, rx, ry, q0, q1);
-                        else red_add_v4(p, p0, p1, rx, ry);
+                    for (int h = 0; h < 2; ++h) {   // h = 0: entry g ; h = 1: entry g + 8
+                        const float p0 = d[2 * j][2 * h], p1 = d[2 * j][2 * h + 1];
+                        const float q0 = d[2 * j + 1][2 * h], q1 = d[2 * j + 1][2 * h + 1];
+                        const float rx = __shfl_xor_sync(FULL, odd ? p0 : q0, 1);
+                        const float ry = __shfl_xor_sync(FULL, odd ? p1 : q1, 1);
+                        const int own = h ? ch.own : cg.own;
+                        if (own >= 0 && col < a.nout)   // row offsets fit 32 bits (checked by the caller)
+                            red_add_v4(a.out + ((uint32_t)own * ldo + (uint32_t)col), odd ? rx : p0, odd ? ry : p1,
+                                       odd ? q0 : rx, odd ? q1 : ry);
                     }
                 }
             }
+        };
+        // rows one tile ahead of the tensor-pipe work; two tiles per trip with swapped roles, so the
+        // pipeline registers are never copied
+        TileRef rA = tile_ref(m, 0, eb), rB = rA;
+        float aA[KT][4], aB[KT][4];
+        load_rows(rA, aA);
+        for (int i = 0; i < nt; i += 2) {
+            if (i + 1 < nt) {
+                rB = tile_ref(m, i + 1, eb);
+                load_rows(rB, aB);
             }
-            cur = nxt;
-            nxt = nn;
-#pragma unroll
-            for (int kt = 0; kt < KT; ++kt)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) av[kt][i] = avn[kt][i];
-            if (ti == t0 + 1 && pf_e0 >= 0 && lane < 24) {   // UT*16 entries = 8 lines per stream
-                const int e = pf_e0 + (lane & 7) * 32;
-                const void* p = lane < 8 ? (const void*)(a.e_idx + e) : lane < 16 ? (const void*)(a.e_w + e) : (const void*)(a.e_own + e);
-                prefetch_l2(p);
+            process(rA, aA);
+            if (i + 1 >= nt) break;
+            if (i + 2 < nt) {
+                rA = tile_ref(m, i + 2, eb);
+                load_rows(rA, aA);
             }
+            process(rB, aB);
         }
-        if constexpr (BULK != 0) {   // the next unit restarts the buffer parity
-            if (lane < 16) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncwarp();
-        }
+        __syncwarp();   // every lane is done with this metadata buffer before it is staged again
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if constexpr (BULK != 0) {
         if (lane < 16) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -717,12 +774,14 @@ int bulk_min_nt() {
 
 template <int KT, int NT>
 int run_etile(const ETileArgs& a, bool relu, bool v4, bool packed, int num_sms, cudaStream_t st) {
-    auto launch = [&](auto kern, int smem = 0) -> int {
+    auto launch = [&](auto kern, int bulk_bytes = 0) -> int {
         int per_sm = 1;
+        const int smem = (bulk_bytes ? MetaStage<1>::CTA_BYTES : MetaStage<0>::CTA_BYTES) + bulk_bytes;
+        const int utu = bulk_bytes ? MetaStage<1>::UTU : MetaStage<0>::UTU;
         if (smem > 48 * 1024) RGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EW * 32, smem));
         per_sm = std::max(per_sm, 1);
-        const int64_t units = ((int64_t)a.num_tiles + UT - 1) / UT;
+        const int64_t units = ((int64_t)a.num_tiles + utu - 1) / utu;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + EW - 1) / EW, (int64_t)num_sms * per_sm));
         kern<<<grid, EW * 32, smem, st>>>(a);
         RGCN_CUDA(cudaGetLastError());

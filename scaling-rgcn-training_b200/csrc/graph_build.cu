@@ -390,11 +390,11 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const 
     RGCN_CUDA(cudaMemcpy(&NC, chunk_base.p + S, 4, cudaMemcpyDeviceToHost));
     b.num_entries = E3;
     b.num_chunks = NC;
-    RGCN_CUDA(cudaMalloc(&b.e_idx, std::max(E3, 1) * 4));
-    RGCN_CUDA(cudaMalloc(&b.e_w, std::max(E3, 1) * 4));
+    RGCN_CUDA(cudaMalloc(&b.e_idx, ((size_t)std::max(E3, 1) + 16) * 4));   // +16: whole 16-byte chunks are staged
+    RGCN_CUDA(cudaMalloc(&b.e_w, ((size_t)std::max(E3, 1) + 16) * 4));
     RGCN_CUDA(cudaMalloc(&b.chunk_beg, std::max(NC, 1) * 4));
     RGCN_CUDA(cudaMalloc(&b.chunk_end, std::max(NC, 1) * 4));
-    RGCN_CUDA(cudaMalloc(&b.e_own, std::max(E3, 1) * 4));
+    RGCN_CUDA(cudaMalloc(&b.e_own, ((size_t)std::max(E3, 1) + 16) * 4));
     k_compact<<<blocks_for(n2), TPB, 0, st>>>(scan.p, b.seg_ptr0, b.seg_ptr, chunk_base.p, b.raw_idx, b.raw_w, n2, n_gat, T,
                                               CH, b.e_idx, b.e_w, b.chunk_beg, b.chunk_end, b.seg_own, b.e_own);
 
@@ -446,8 +446,8 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const 
             if (first_self_group >= 0)
                 RGCN_CUDA(cudaMemcpy(&b.num_tiles_noself, tile_base.p + first_self_group, 4, cudaMemcpyDeviceToHost));
         }
-        RGCN_CUDA(cudaMalloc(&b.tile_e0, std::max(NTL, 1) * 4));
-        RGCN_CUDA(cudaMalloc(&b.tile_info, std::max(NTL, 1) * 4));
+        RGCN_CUDA(cudaMalloc(&b.tile_e0, ((size_t)std::max(NTL, 1) + 16) * 4));
+        RGCN_CUDA(cudaMalloc(&b.tile_info, ((size_t)std::max(NTL, 1) + 16) * 4));
         if (NTL > 0)
             k_tile_fill<<<blocks_for(NTL), TPB, 0, st>>>(tile_base.p, grp_seg.p, b.seg_ptr, b.seg_rel, G, NTL, b.tile_e0,
                                                          b.tile_info);
