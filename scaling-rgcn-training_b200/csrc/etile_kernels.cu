@@ -73,7 +73,22 @@ __device__ __forceinline__ void split_rn(float x, uint32_t& hi, uint32_t& lo) {
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// Kernel parameters used inside the load sequences are pinned in registers: left alone, ptxas
+// re-reads them from the constant bank (LDC) between the row loads, and an LDC that shares a
+// scoreboard slot with an outstanding LDG waits for DRAM — the loads of one tile then go out in
+// three or four round trips instead of one (ncu: half of all stall samples on those sites).
+__device__ __forceinline__ const float* pin(const float* p) {
+    asm volatile("" : "+l"(p));
+    return p;
+}
+__device__ __forceinline__ uint32_t pin(uint32_t v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+__device__ __forceinline__ int pin(int v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
 
 struct RowRef {   // one gathered row of a lane
     const float* p;   // row pointer + lane's k offset
@@ -185,6 +200,7 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
     const float* const feat_t = a.feat + KOFF * t;   // lane bases: feature rows / chunk rows
     const float* const aux_t = a.aux + KOFF * t;
     const uint32_t n_rows = (uint32_t)a.n_rows, ldf = (uint32_t)a.ldf;
+    const int kin = a.kin;   // (pinning these costs spills here and measured slower)
     auto make_row = [&](const uint32_t* m, int o, bool valid) {
         RowRef r;
         uint32_t idx = 0;
@@ -215,7 +231,7 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
 #pragma unroll
             for (int j = 0; j < KT / 2; ++j) {
                 float4 vg = make_float4(0.f, 0.f, 0.f, 0.f), vh = vg;
-                if (16 * j + 4 * t < a.kin) {
+                if (16 * j + 4 * t < kin) {
                     vg = ldg128_hint(reinterpret_cast<const float4*>(r.g8.p + 16 * j), pol_f);
                     vh = ldg128_hint(reinterpret_cast<const float4*>(r.h8.p + 16 * j), pol_f);
                 }
@@ -231,7 +247,7 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
         } else {
 #pragma unroll
             for (int kt = 0; kt < KT; ++kt) {
-                const bool c_lo = 8 * kt + t < a.kin, c_hi = 8 * kt + 4 + t < a.kin;
+                const bool c_lo = 8 * kt + t < kin, c_hi = 8 * kt + 4 + t < kin;
                 av[kt][0] = c_lo ? ldg_hint(r.g8.p + 8 * kt, pol_f) : 0.f;
                 av[kt][1] = c_lo ? ldg_hint(r.h8.p + 8 * kt, pol_f) : 0.f;
                 av[kt][2] = c_hi ? ldg_hint(r.g8.p + 8 * kt + 4, pol_f) : 0.f;
@@ -425,10 +441,13 @@ template <int KT, int NT, bool RELU, bool V4>
 __global__ void __launch_bounds__(EW * 32, (KT * NT >= 32) ? 1 : 2) k_ewgrad(const ETileArgs a) {
     constexpr int KP = KT * 8, MT = KP / 16;
     static_assert(!V4 || KP >= 32, "vector loads need at least 32 columns");
+    using MS = MetaStage<(KT >= 4) ? 1 : 0>;   // wide rows: smaller staging units leave more L1 for the gout rows
+    constexpr int UTU = MS::UTU, SPAN = MS::SPAN, MW = MS::MW;
+    extern __shared__ __align__(16) uint32_t dyn_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int gw = blockIdx.x * EW + warp, nw = gridDim.x * EW;
-    const uint64_t pol_s = policy_evict_first();
+    uint32_t* meta = dyn_smem + warp * MS::WARP_WORDS;
     const uint64_t pol_f =
         (uint64_t)a.n_rows * (uint64_t)a.ldf * 4ull <= (112ull << 20) ? policy_evict_last() : policy_evict_normal();
     float d[MT][NT][4];
@@ -459,122 +478,214 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 32) ? 1 : 2) k_ewgrad(con
     };
 
     constexpr int KOFF = V4 ? 4 : 1;
-    // contiguous span of tiles per warp (tiles cost the same): D stays in registers across the whole
-    // span and is flushed only where the relation changes -> a few atomics per warp, not per unit
-    const int per = (a.num_tiles + nw - 1) / nw;
-    {
-        const int t0 = min(a.num_tiles, gw * per), t1 = min(a.num_tiles, gw * per + per);
-        if (t0 >= t1) return;
-        int e0 = a.tile_e0[t0], info = a.tile_info[t0];
+    const float* const feat_g = pin(a.feat + KOFF * g);   // lane bases: feature rows / chunk rows / gout rows
+    const float* const aux_g = pin(a.aux + KOFF * g);
+    const float* const gout_g = pin(a.gout + g);
+    const uint32_t n_rows = pin((uint32_t)a.n_rows), ldf = pin((uint32_t)a.ldf), ldg = pin((uint32_t)a.ldg);
+    const int kin = pin(a.kin), nout = pin(a.nout);
+    // contiguous span of tiles per warp (tiles cost the same), a multiple of the staging unit: D stays
+    // in registers across the whole span and is flushed only where the relation changes
+    const int per = ((a.num_tiles + nw - 1) / nw + UTU - 1) / UTU * UTU;
+    const int t0 = min(a.num_tiles, gw * per), t1 = min(a.num_tiles, gw * per + per);
+    if (t0 >= t1) return;
+    const int num_units = (t1 - t0 + UTU - 1) / UTU;
+
+    auto unit_span = [&](int u, int& first, int& end) {
+        const int u0 = t0 + u * UTU, u1 = min(t1, u0 + UTU);
+        first = a.tile_e0[u0];
+        end = a.tile_e0[u1 - 1] + (a.tile_info[u1 - 1] & 0xff);
+    };
+    auto stage_unit = [&](int u, int first, int end, uint32_t* m) {
+        const int eb = first & ~3;
+        const int nchunk = (end - eb + 3) >> 2;
+        for (int c = lane; c < nchunk; c += 32) {
+            cp_async16(m + 4 * c, a.e_idx + eb + 4 * c);
+            cp_async16(m + SPAN + 4 * c, a.e_w + eb + 4 * c);
+            cp_async16(m + 2 * SPAN + 4 * c, a.e_own + eb + 4 * c);
+        }
+        const int u0 = t0 + u * UTU;
+        if (lane < UTU / 4) cp_async16(m + 3 * SPAN + 4 * lane, a.tile_e0 + u0 + 4 * lane);
+        else if (lane < UTU / 2) cp_async16(m + 3 * SPAN + UTU + 4 * (lane - UTU / 4), a.tile_info + u0 + 4 * (lane - UTU / 4));
+    };
+    struct Tile {
         RowRef r[4];   // entries t, t+4, 8+t, 12+t ; feature offset of lane g folded in
+        int rel;
+    };
+    auto tile_ref = [&](const uint32_t* m, int i, int eb) {
+        Tile tl;
+        const int e0 = (int)m[3 * SPAN + i], info = (int)m[3 * SPAN + UTU + i];
+        tl.rel = info >> 8;
+        const int cnt = info & 0xff;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) r[i] = make_ref<KP>(a, e0 + t + 4 * i, t + 4 * i < (info & 0xff), KOFF * g, pol_s);
-        for (int ti = t0; ti < t1; ++ti) {
-            const int rel = info >> 8;
-            if (rel != cur_rel) {
-                if (cur_rel >= 0) flush(cur_rel);
-                cur_rel = rel;
+        for (int q = 0; q < 4; ++q) {
+            RowRef r;
+            const int o = e0 - eb + t + 4 * q;
+            uint32_t idx = 0;
+            r.w = 0.f;
+            r.own = -1;
+            if (t + 4 * q < cnt) {
+                idx = m[o] & IDX_MASK;
+                r.w = __uint_as_float(m[SPAN + o]);
+                r.own = (int)m[2 * SPAN + o];
             }
-            const bool wanted = rel == a.self_rel ? (a.groot != nullptr || a.gbias != nullptr) : a.gweight != nullptr;
-            float av[2][MT][4], bv[2][NT][2];
-            if (wanted) {
+            r.real = idx < n_rows;
+            const uint32_t off = r.real ? idx * ldf : (idx - n_rows) * (uint32_t)KP;
+            r.p = (r.real ? feat_g : aux_g) + off;
+            tl.r[q] = r;
+        }
+        return tl;
+    };
+    auto load_tile = [&](const Tile& tl, float (&av)[2][MT][4], float (&bv)[2][NT][2]) {
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    const RowRef& ra = r[2 * ks];       // K slot t
-                    const RowRef& rb = r[2 * ks + 1];   // K slot t + 4
-                    if constexpr (V4) {
+        for (int ks = 0; ks < 2; ++ks) {
+            const RowRef& ra = tl.r[2 * ks];       // K slot t
+            const RowRef& rb = tl.r[2 * ks + 1];   // K slot t + 4
+            if constexpr (V4) {
 #pragma unroll
-                        for (int jb = 0; jb < MT / 2; ++jb) {
-                            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-                            if (32 * jb + 4 * g < a.kin) {
-                                va = ldg128_hint(reinterpret_cast<const float4*>(ra.p + 32 * jb), pol_f);
-                                vb = ldg128_hint(reinterpret_cast<const float4*>(rb.p + 32 * jb), pol_f);
-                            }
-                            av[ks][2 * jb][0] = va.x;       // m-tile 2jb  : row g   (K slot t)
-                            av[ks][2 * jb][1] = va.y;       //               row g+8
-                            av[ks][2 * jb + 1][0] = va.z;   // m-tile 2jb+1: row g
-                            av[ks][2 * jb + 1][1] = va.w;   //               row g+8
-                            av[ks][2 * jb][2] = vb.x;       // same rows, K slot t+4
-                            av[ks][2 * jb][3] = vb.y;
-                            av[ks][2 * jb + 1][2] = vb.z;
-                            av[ks][2 * jb + 1][3] = vb.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int m = 0; m < MT; ++m) {
-                            const bool c_lo = 16 * m + g < a.kin, c_hi = 16 * m + 8 + g < a.kin;
-                            av[ks][m][0] = c_lo ? ldg_hint(ra.p + 16 * m, pol_f) : 0.f;
-                            av[ks][m][1] = c_hi ? ldg_hint(ra.p + 16 * m + 8, pol_f) : 0.f;
-                            av[ks][m][2] = c_lo ? ldg_hint(rb.p + 16 * m, pol_f) : 0.f;
-                            av[ks][m][3] = c_hi ? ldg_hint(rb.p + 16 * m + 8, pol_f) : 0.f;
-                        }
+                for (int jb = 0; jb < MT / 2; ++jb) {
+                    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+                    if (32 * jb + 4 * g < kin) {
+                        va = ldg128_hint(reinterpret_cast<const float4*>(ra.p + 32 * jb), pol_f);
+                        vb = ldg128_hint(reinterpret_cast<const float4*>(rb.p + 32 * jb), pol_f);
                     }
-#pragma unroll
-                    for (int n = 0; n < NT; ++n) {
-                        const bool cn = 8 * n + g < a.nout;
-                        bv[ks][n][0] = (cn && ra.own >= 0) ? __ldg(a.gout + (int64_t)ra.own * a.ldg + 8 * n + g) : 0.f;
-                        bv[ks][n][1] = (cn && rb.own >= 0) ? __ldg(a.gout + (int64_t)rb.own * a.ldg + 8 * n + g) : 0.f;
-                    }
+                    av[ks][2 * jb][0] = va.x;       // m-tile 2jb  : row g   (K slot t)
+                    av[ks][2 * jb][1] = va.y;       //               row g+8
+                    av[ks][2 * jb + 1][0] = va.z;   // m-tile 2jb+1: row g
+                    av[ks][2 * jb + 1][1] = va.w;   //               row g+8
+                    av[ks][2 * jb][2] = vb.x;       // same rows, K slot t+4
+                    av[ks][2 * jb][3] = vb.y;
+                    av[ks][2 * jb + 1][2] = vb.z;
+                    av[ks][2 * jb + 1][3] = vb.w;
                 }
-            }
-            RowRef c[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) c[i] = r[i];
-            if (ti + 1 < t1) {
-                e0 = a.tile_e0[ti + 1];
-                info = a.tile_info[ti + 1];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    r[i] = make_ref<KP>(a, e0 + t + 4 * i, t + 4 * i < (info & 0xff), KOFF * g, pol_s);
-            }
-            if (!wanted) continue;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                const RowRef& ra = c[2 * ks];
-                const RowRef& rb = c[2 * ks + 1];
-                uint32_t bh[NT][2], bl[NT][2];
-#pragma unroll
-                for (int n = 0; n < NT; ++n) {
-                    split_rn(bv[ks][n][0], bh[n][0], bl[n][0]);
-                    split_rn(bv[ks][n][1], bh[n][1], bl[n][1]);
-                    if (rel == a.self_rel) bsum[n] += bv[ks][n][0] + bv[ks][n][1];
-                }
+            } else {
 #pragma unroll
                 for (int m = 0; m < MT; ++m) {
-                    float x0 = av[ks][m][0], x1 = av[ks][m][1], x2 = av[ks][m][2], x3 = av[ks][m][3];
-                    if (RELU) {
-                        if (ra.real) {
-                            x0 = fmaxf(x0, 0.f);
-                            x1 = fmaxf(x1, 0.f);
-                        }
-                        if (rb.real) {
-                            x2 = fmaxf(x2, 0.f);
-                            x3 = fmaxf(x3, 0.f);
-                        }
-                    }
-                    uint32_t ah[4], al[4];
-                    split_fast(x0 * ra.w, ah[0], al[0]);
-                    split_fast(x1 * ra.w, ah[1], al[1]);
-                    split_fast(x2 * rb.w, ah[2], al[2]);
-                    split_fast(x3 * rb.w, ah[3], al[3]);
+                    const bool c_lo = 16 * m + g < kin, c_hi = 16 * m + 8 + g < kin;
+                    av[ks][m][0] = c_lo ? ldg_hint(ra.p + 16 * m, pol_f) : 0.f;
+                    av[ks][m][1] = c_hi ? ldg_hint(ra.p + 16 * m + 8, pol_f) : 0.f;
+                    av[ks][m][2] = c_lo ? ldg_hint(rb.p + 16 * m, pol_f) : 0.f;
+                    av[ks][m][3] = c_hi ? ldg_hint(rb.p + 16 * m + 8, pol_f) : 0.f;
+                }
+            }
+            const float* ga = gout_g + (uint32_t)max(ra.own, 0) * ldg;   // row offsets fit 32 bits (caller)
+            const float* gb = gout_g + (uint32_t)max(rb.own, 0) * ldg;
 #pragma unroll
-                    for (int n = 0; n < NT; ++n) {
-                        mma_tf32(d[m][n], al[0], al[1], al[2], al[3], bh[n][0], bh[n][1]);
-                        mma_tf32(d[m][n], ah[0], ah[1], ah[2], ah[3], bl[n][0], bl[n][1]);
-                        mma_tf32(d[m][n], ah[0], ah[1], ah[2], ah[3], bh[n][0], bh[n][1]);
+            for (int n = 0; n < NT; ++n) {
+                const bool cn = 8 * n + g < nout;
+                bv[ks][n][0] = (cn && ra.own >= 0) ? __ldg(ga + 8 * n) : 0.f;
+                bv[ks][n][1] = (cn && rb.own >= 0) ? __ldg(gb + 8 * n) : 0.f;
+            }
+        }
+    };
+    auto compute = [&](const Tile& tl, const float (&av)[2][MT][4], const float (&bv)[2][NT][2]) {
+        const int rel = tl.rel;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const RowRef& ra = tl.r[2 * ks];
+            const RowRef& rb = tl.r[2 * ks + 1];
+            uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                split_rn(bv[ks][n][0], bh[n][0], bl[n][0]);
+                split_rn(bv[ks][n][1], bh[n][1], bl[n][1]);
+                if (rel == a.self_rel) bsum[n] += bv[ks][n][0] + bv[ks][n][1];
+            }
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                float x0 = av[ks][m][0], x1 = av[ks][m][1], x2 = av[ks][m][2], x3 = av[ks][m][3];
+                if (RELU) {
+                    if (ra.real) {
+                        x0 = fmaxf(x0, 0.f);
+                        x1 = fmaxf(x1, 0.f);
                     }
+                    if (rb.real) {
+                        x2 = fmaxf(x2, 0.f);
+                        x3 = fmaxf(x3, 0.f);
+                    }
+                }
+                uint32_t ah[4], al[4];
+                split_fast(x0 * ra.w, ah[0], al[0]);
+                split_fast(x1 * ra.w, ah[1], al[1]);
+                split_fast(x2 * rb.w, ah[2], al[2]);
+                split_fast(x3 * rb.w, ah[3], al[3]);
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    mma_tf32(d[m][n], al[0], al[1], al[2], al[3], bh[n][0], bh[n][1]);
+                    mma_tf32(d[m][n], ah[0], ah[1], ah[2], ah[3], bl[n][0], bl[n][1]);
+                    mma_tf32(d[m][n], ah[0], ah[1], ah[2], ah[3], bh[n][0], bh[n][1]);
                 }
             }
         }
+    };
+    auto wanted = [&](int rel) {
+        return rel == a.self_rel ? (a.groot != nullptr || a.gbias != nullptr) : a.gweight != nullptr;
+    };
+    auto enter = [&](int rel) {   // D belongs to one relation at a time
+        if (rel != cur_rel) {
+            if (cur_rel >= 0) flush(cur_rel);
+            cur_rel = rel;
+        }
+    };
+
+    int cur_first, cur_end, nxt_first = 0, nxt_end = 0;
+    unit_span(0, cur_first, cur_end);
+    stage_unit(0, cur_first, cur_end, meta);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (1 < num_units) unit_span(1, nxt_first, nxt_end);
+    for (int u = 0, buf = 0; u < num_units; ++u, buf ^= 1) {
+        const uint32_t* m = meta + buf * MW;
+        const int eb = cur_first & ~3;
+        const int nt = min(t1, t0 + u * UTU + UTU) - (t0 + u * UTU);
+        if (u + 1 < num_units) stage_unit(u + 1, nxt_first, nxt_end, meta + (buf ^ 1) * MW);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        cur_first = nxt_first;
+        cur_end = nxt_end;
+        if (u + 2 < num_units) unit_span(u + 2, nxt_first, nxt_end);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        if constexpr (MT <= 2) {   // narrow rows: the next tile's rows are loaded before this tile's MMAs
+            Tile tA = tile_ref(m, 0, eb), tB = tA;
+            float aA[2][MT][4], bA[2][NT][2], aB[2][MT][4], bB[2][NT][2];
+            bool wA = wanted(tA.rel), wB = false;
+            if (wA) load_tile(tA, aA, bA);
+            for (int i = 0; i < nt; i += 2) {
+                if (i + 1 < nt) {
+                    tB = tile_ref(m, i + 1, eb);
+                    wB = wanted(tB.rel);
+                    if (wB) load_tile(tB, aB, bB);
+                }
+                enter(tA.rel);
+                if (wA) compute(tA, aA, bA);
+                if (i + 1 >= nt) break;
+                if (i + 2 < nt) {
+                    tA = tile_ref(m, i + 2, eb);
+                    wA = wanted(tA.rel);
+                    if (wA) load_tile(tA, aA, bA);
+                }
+                enter(tB.rel);
+                if (wB) compute(tB, aB, bB);
+            }
+        } else {
+            for (int i = 0; i < nt; ++i) {
+                const Tile tl = tile_ref(m, i, eb);
+                enter(tl.rel);
+                if (!wanted(tl.rel)) continue;
+                float av[2][MT][4], bv[2][NT][2];
+                load_tile(tl, av, bv);
+                compute(tl, av, bv);
+            }
+        }
+        __syncwarp();
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (cur_rel >= 0) flush(cur_rel);
     if (a.gbias) {   // column 8n+g summed over this lane's K slots; fold the 4 t-lanes, then one atomic
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
-            float s = bsum[n];
-            s += __shfl_xor_sync(FULL, s, 1);
-            s += __shfl_xor_sync(FULL, s, 2);
-            if (t == 0 && 8 * n + g < a.nout && s != 0.f) atomicAdd(a.gbias + 8 * n + g, s);
+            float sacc = bsum[n];
+            sacc += __shfl_xor_sync(FULL, sacc, 1);
+            sacc += __shfl_xor_sync(FULL, sacc, 2);
+            if (t == 0 && 8 * n + g < a.nout && sacc != 0.f) atomicAdd(a.gbias + 8 * n + g, sacc);
         }
     }
 }
@@ -814,11 +925,13 @@ template <int KT, int NT>
 int run_ewgrad(const ETileArgs& a, bool relu, bool v4, int num_sms, cudaStream_t st) {
     auto launch = [&](auto kern) -> int {
         int per_sm = 1;
-        RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EW * 32, 0));
+        const int smem = (KT >= 4) ? MetaStage<1>::CTA_BYTES : MetaStage<0>::CTA_BYTES;
+        if (smem > 48 * 1024) RGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EW * 32, smem));
         per_sm = std::max(per_sm, 1);
         const int64_t units = ((int64_t)a.num_tiles + UT - 1) / UT;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + EW - 1) / EW, (int64_t)num_sms * per_sm));
-        kern<<<grid, EW * 32, 0, st>>>(a);
+        kern<<<grid, EW * 32, smem, st>>>(a);
         RGCN_CUDA(cudaGetLastError());
         return 0;
     };
