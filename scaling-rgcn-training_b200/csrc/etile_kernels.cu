@@ -66,6 +66,8 @@ __device__ __forceinline__ float4 ldg128_hint(const float4* p, uint64_t pol) {
                  : "l"(p), "l"(pol));
     return v;
 }
+// (row gathers keep their L1 allocation: with L1::no_allocate the two 64-byte halves of a 128-byte
+// line become separate L2 requests and the 256-byte-row forward pass ran 40 % slower)
 // round-to-nearest split (unbiased): used for ONE operand when both are activations, so that the
 // dropped lo*lo term has no systematic sign over long sums
 __device__ __forceinline__ void split_rn(float x, uint32_t& hi, uint32_t& lo) {
@@ -197,10 +199,14 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
         if (lane < UTU / 4) cp_async16(m + 3 * SPAN + 4 * lane, a.tile_e0 + t0 + 4 * lane);
         else if (lane < UTU / 2) cp_async16(m + 3 * SPAN + UTU + 4 * (lane - UTU / 4), a.tile_info + t0 + 4 * (lane - UTU / 4));
     };
-    const float* const feat_t = a.feat + KOFF * t;   // lane bases: feature rows / chunk rows
-    const float* const aux_t = a.aux + KOFF * t;
-    const uint32_t n_rows = (uint32_t)a.n_rows, ldf = (uint32_t)a.ldf;
-    const int kin = a.kin;   // (pinning these costs spills here and measured slower)
+    // lane bases: feature rows / chunk rows.  Pinned (see pin()) where registers allow: the wide-row
+    // instances are at the 128-register cap and pinning them spills (measured slower)
+    constexpr bool PIN = (KT <= 2);
+    const float* const feat_t = PIN ? pin(a.feat + KOFF * t) : a.feat + KOFF * t;
+    const float* const aux_t = PIN ? pin(a.aux + KOFF * t) : a.aux + KOFF * t;
+    const uint32_t n_rows = PIN ? pin((uint32_t)a.n_rows) : (uint32_t)a.n_rows;
+    const uint32_t ldf = PIN ? pin((uint32_t)a.ldf) : (uint32_t)a.ldf;
+    const int kin = PIN ? pin(a.kin) : a.kin;
     auto make_row = [&](const uint32_t* m, int o, bool valid) {
         RowRef r;
         uint32_t idx = 0;
@@ -714,7 +720,7 @@ struct SelfArgs {
 template <int KT, int NT, bool RELU, bool V4, bool PACK = false>
 __global__ void __launch_bounds__(EW * 32, 2) k_selfloop(const SelfArgs a) {
     constexpr bool BREG = (KT * NT <= 16);
-    __shared__ __align__(16) float pack_stage[PACK ? EW * 16 * NT * 8 : 4];
+    __shared__ __align__(16) float pack_stage[PACK ? EW * 16 * (NT * 8 + 8) : 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int64_t gw = (int64_t)blockIdx.x * EW + warp, nw = (int64_t)gridDim.x * EW;
@@ -801,31 +807,21 @@ __global__ void __launch_bounds__(EW * 32, 2) k_selfloop(const SelfArgs a) {
             }
         }
         if constexpr (PACK) {
-            float* sb = pack_stage + warp * (16 * NT * 8);
+            constexpr int SW = NT * 8 + 8;   // staged row stride: 64-bit stores of 8 rows hit 32 distinct banks
+            float* sb = pack_stage + warp * (16 * SW);
             const int w = a.nout;
             __syncwarp();
 #pragma unroll
             for (int n = 0; n < NT; ++n) {
-                const int col = 8 * n + 2 * t;
-                if (col < w) {
-                    sb[g * w + col] = d[n][0];
-                    sb[(g + 8) * w + col] = d[n][2];
-                }
-                if (col + 1 < w) {
-                    sb[g * w + col + 1] = d[n][1];
-                    sb[(g + 8) * w + col + 1] = d[n][3];
-                }
+                *reinterpret_cast<float2*>(sb + g * SW + 8 * n + 2 * t) = make_float2(d[n][0], d[n][1]);
+                *reinterpret_cast<float2*>(sb + (g + 8) * SW + 8 * n + 2 * t) = make_float2(d[n][2], d[n][3]);
             }
             __syncwarp();
             const int rows = (int)min((int64_t)16, a.n_own - tile * 16);
-            const int total = rows * w;
-            float* base = a.out + tile * 16 * w;   // 16 w floats per tile: 64-byte aligned
-            for (int i = lane * 4; i < total; i += 128) {
-                if (i + 4 <= total) {
-                    *reinterpret_cast<float4*>(base + i) = *reinterpret_cast<const float4*>(sb + i);
-                } else {
-                    for (int c = i; c < total; ++c) base[c] = sb[c];
-                }
+            float* base = a.out + tile * 16 * w;   // the tile's rows are one contiguous span of `out`
+            for (int r = 0; r < rows; ++r) {
+                if (lane < w) base[r * w + lane] = sb[r * SW + lane];
+                if (lane + 32 < w) base[r * w + lane + 32] = sb[r * SW + lane + 32];
             }
         } else {
         const bool odd = (t & 1) != 0;
