@@ -131,7 +131,8 @@ __device__ __forceinline__ RowRef make_ref(const ETileArgs& a, int e, bool valid
 template <int NT>
 struct BulkTile {
     static constexpr int ROWW = NT * 8 + 8;        // words per staged row: +8 skews rows over the banks
-    static constexpr int WARP_WORDS = 2 * 16 * ROWW;   // two buffers
+    static constexpr int NBUF = 1;                      // result-tile buffers per warp
+    static constexpr int WARP_WORDS = NBUF * 16 * ROWW;
     static constexpr int CTA_BYTES = EW * WARP_WORDS * 4;
 };
 
@@ -336,9 +337,13 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
             if constexpr (BULK != 0) {
                 using BT = BulkTile<NT>;
                 float* bt = bulk_smem + warp * BT::WARP_WORDS + bulk_par * (16 * BT::ROWW);
-                bulk_par ^= 1;
-                // the bulk reads of this buffer (issued two tiles ago) must be over before it is rewritten
-                if (lane < 16) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                // the bulk reads of this buffer must be over before it is rewritten
+                if constexpr (BT::NBUF == 2) {
+                    bulk_par ^= 1;
+                    if (lane < 16) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                } else {
+                    if (lane < 16) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
                 __syncwarp();
                 if constexpr (BULK == 2) {
                     const int fg = cg.own >= 0 ? (int)(((int64_t)cg.own * a.ldo) & 3) : 0;
@@ -883,8 +888,9 @@ template <int KT, int NT>
 int run_etile(const ETileArgs& a, bool relu, bool v4, bool packed, int num_sms, cudaStream_t st) {
     auto launch = [&](auto kern, int bulk_bytes = 0) -> int {
         int per_sm = 1;
-        const int smem = (bulk_bytes ? MetaStage<1>::CTA_BYTES : MetaStage<0>::CTA_BYTES) + bulk_bytes;
-        const int utu = bulk_bytes ? MetaStage<1>::UTU : MetaStage<0>::UTU;
+        const bool small_units = bulk_bytes != 0;
+        const int smem = (small_units ? MetaStage<1>::CTA_BYTES : MetaStage<0>::CTA_BYTES) + bulk_bytes;
+        const int utu = small_units ? MetaStage<1>::UTU : MetaStage<0>::UTU;
         if (smem > 48 * 1024) RGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EW * 32, smem));
         per_sm = std::max(per_sm, 1);
