@@ -122,6 +122,16 @@ def test_layer_shapes_on_random_multigraph(fin, fout):
     _layer_case(ei, et, 257, 7, fin, fout, seed=1)
 
 
+@pytest.mark.parametrize('n', [1, 15, 16, 17, 1003])
+@pytest.mark.parametrize('fin', [57, 61, 62, 63, 64])
+def test_dx_bulk_scatter_paths(n, fin):
+    """dL/dx with 64 padded columns is scattered by the bulk-copy engine: whole rows for fin = 64, the
+    shifted 16-byte windows of tightly packed odd-width rows otherwise (every row phase 63 i mod 4, the
+    scalar fallback of the last rows, graphs smaller than one tile)."""
+    ei, et = random_multigraph(n, 40 * n, 9, seed=n + fin, hub_frac=0.3, dup_frac=0.2)
+    _layer_case(ei, et, n, 9, fin, 16, seed=3)
+
+
 @pytest.mark.parametrize('fin,fout', [(100, 70), (65, 3), (5, 130)])
 def test_layer_wide_shapes_use_generic_kernels(fin, fout):
     ei, et = random_multigraph(90, 800, 5, seed=7, hub_frac=0.2, dup_frac=0.1)
