@@ -242,6 +242,10 @@ def run_engine(args):
 
     ei, et, n, r = am_shape(scale=args.scale)
     e = et.numel()
+    # CUDA context + lazy module load (seconds on a fresh box) are not part of the graph build time
+    _wi, _wt = torch.zeros((2, 4), dtype=torch.int64, device=device), torch.zeros(4, dtype=torch.int64, device=device)
+    RGCNGraph(_wi, _wt, 2, 3)
+    torch.cuda.synchronize(device)
     t_setup = time.perf_counter()
     data = Data(edge_index=ei)
     data.edge_type = et

@@ -707,6 +707,23 @@ __global__ void k_relu_mask(float* __restrict__ gr, int64_t ldg, const float* __
     if (!(pre[r * ldp + c] > 0.f)) gr[r * ldg + c] = 0.f;
 }
 
+// rows of whole aligned quads (the 16-wide hidden layer): one float4 of each matrix per thread
+__global__ void __launch_bounds__(256) k_relu_mask4(float4* __restrict__ gr, int64_t ldg4, const float4* __restrict__ pre,
+                                                    int64_t ldp4, int64_t n, int cols4) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, total = n * cols4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t r = i / cols4;
+        const int c = (int)(i - r * cols4);
+        const float4 p = __ldg(pre + r * ldp4 + c);
+        float4 g = gr[r * ldg4 + c];
+        g.x = p.x > 0.f ? g.x : 0.f;
+        g.y = p.y > 0.f ? g.y : 0.f;
+        g.z = p.z > 0.f ? g.z : 0.f;
+        g.w = p.w > 0.f ? g.w : 0.f;
+        gr[r * ldg4 + c] = g;
+    }
+}
+
 template <int KT, int NT, bool RELU, bool BREG>
 int run_tile_v(const TileArgs& a, int num_sms, cudaStream_t st) {
     constexpr int LDH = KT * 8 + 4;
@@ -932,6 +949,14 @@ int launch_relu_mask(float* g, int64_t ldg, const float* pre, int64_t ldp, int64
     if (total == 0) return 0;
     ProfScope prof(TAG_MASK, cols, 0, st);
     note_launch(1);
+    if (cols % 4 == 0 && ldg % 4 == 0 && ldp % 4 == 0 && (((uintptr_t)g | (uintptr_t)pre) & 15) == 0) {
+        const int64_t quads = total / 4;
+        const int grid = (int)std::min<int64_t>((quads + 255) / 256, 148 * 16);
+        k_relu_mask4<<<grid, 256, 0, st>>>(reinterpret_cast<float4*>(g), ldg / 4, reinterpret_cast<const float4*>(pre),
+                                           ldp / 4, n, cols / 4);
+        RGCN_CUDA(cudaGetLastError());
+        return 0;
+    }
     k_relu_mask<<<(int)((total + 255) / 256), 256, 0, st>>>(g, ldg, pre, ldp, n, cols);
     RGCN_CUDA(cudaGetLastError());
     return 0;
