@@ -226,6 +226,46 @@ __global__ void __launch_bounds__(256) k_chunk_sum(const int32_t* __restrict__ r
     if (KP > 32) aux[(int64_t)c * KP + lane + 32] = acc1;          // v1 is zero past the width
 }
 
+// 16-column rows that are 16-byte addressable: 4 lanes per row, 8 rows per load instruction (the
+// column-per-lane kernel above leaves half the warp idle and loads one row per instruction)
+template <bool RELU>
+__global__ void __launch_bounds__(256) k_chunk_sum16(const int32_t* __restrict__ raw_idx, const float* __restrict__ raw_w,
+                                                     const int32_t* __restrict__ chunk_beg,
+                                                     const int32_t* __restrict__ chunk_end, int num_chunks,
+                                                     const float* __restrict__ feat, int64_t ldf, int kin,
+                                                     float* __restrict__ aux) {
+    const int lane = threadIdx.x & 31, q = lane & 3, r = lane >> 2;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= num_chunks) return;
+    const int e0 = chunk_beg[c], e1 = chunk_end[c];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool col_ok = 4 * q < kin;   // kin is a multiple of 4 here (whole quads inside the row)
+    for (int pos = e0 + r; pos < e1; pos += 8) {
+        const uint32_t idx = (uint32_t)raw_idx[pos];
+        const float w = raw_w[pos];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok) v = __ldg(reinterpret_cast<const float4*>(feat + (uint64_t)idx * (uint64_t)ldf) + q);
+        if (RELU) {
+            v.x = fmaxf(v.x, 0.f);
+            v.y = fmaxf(v.y, 0.f);
+            v.z = fmaxf(v.z, 0.f);
+            v.w = fmaxf(v.w, 0.f);
+        }
+        acc.x = fmaf(w, v.x, acc.x);
+        acc.y = fmaf(w, v.y, acc.y);
+        acc.z = fmaf(w, v.z, acc.z);
+        acc.w = fmaf(w, v.w, acc.w);
+    }
+#pragma unroll
+    for (int sh = 4; sh < 32; sh <<= 1) {
+        acc.x += __shfl_xor_sync(FULL, acc.x, sh);
+        acc.y += __shfl_xor_sync(FULL, acc.y, sh);
+        acc.z += __shfl_xor_sync(FULL, acc.z, sh);
+        acc.w += __shfl_xor_sync(FULL, acc.w, sh);
+    }
+    if (r == 0) reinterpret_cast<float4*>(aux + (int64_t)c * 16)[q] = acc;
+}
+
 // ---------------------------------------------------------------------------------------------
 // B-operand preparation: fragment-ordered, pre-split into tf32 hi/lo.
 //   wfrag[((rel*KT + kt)*NT + nt)*32 + lane] = (b0.hi, b1.hi, b0.lo, b1.lo)
@@ -839,6 +879,19 @@ int launch_chunk_prepass(const TilePass& p, cudaStream_t st) {
     const int grid = (b.num_chunks + wpb - 1) / wpb;
     ProfScope prof(TAG_PREPASS, p.kin, b.num_chunks, st);
     note_launch(1);
+    // (kin < 16 with whole quads, e.g. the 12 used columns of a caller-padded 11-wide row, is fine too)
+    const bool quad16 = p.kp == 16 && p.ldf % 4 == 0 && p.kin % 4 == 0 && ((uintptr_t)p.feat & 15) == 0 &&
+                        ((uintptr_t)p.aux & 15) == 0;
+    if (quad16) {
+        if (p.relu_in)
+            k_chunk_sum16<true><<<grid, wpb * 32, 0, st>>>(b.raw_idx, b.raw_w, b.chunk_beg, b.chunk_end, b.num_chunks, p.feat,
+                                                           p.ldf, p.kin, p.aux);
+        else
+            k_chunk_sum16<false><<<grid, wpb * 32, 0, st>>>(b.raw_idx, b.raw_w, b.chunk_beg, b.chunk_end, b.num_chunks, p.feat,
+                                                            p.ldf, p.kin, p.aux);
+        RGCN_CUDA(cudaGetLastError());
+        return 0;
+    }
     switch (p.kp) {
         case 16: run_chunk<16>(b, p, grid, wpb, st); break;
         case 32: run_chunk<32>(b, p, grid, wpb, st); break;
