@@ -175,6 +175,44 @@ def run_partitioned_bench(args, rank: int, world: int, device, metric: str, unit
     launches = _lib.launch_count() - launches0
     ms = total_ms / args.steps
     value = e / (ms * 1e-3)
+    sync_ms = comm.comm_ms() / max(args.steps, 1)
+    gathered = comm.bytes_gathered // max(args.steps, 1)
+    # end to end: the Trainer.train iteration body on the partitioned model — this rank's share of the
+    # labelled batch copied from pinned host memory every step, forward, CE loss (global mean: local
+    # sum / total count), backward (weight gradients all-reduced inside the layer), Adam on the local
+    # embedding shard and the replicated weights, loss all-reduced and read back
+    e2e = None
+    if not getattr(args, 'no_e2e', False):
+        from .synthetic import labelled_split
+        from .trainer import make_optimizer
+        x_all, y_all = labelled_split(n, B.CLASSES)
+        mine = (x_all >= comm.lo) & (x_all < comm.hi)
+        x_h = (x_all[mine] - comm.lo).contiguous().pin_memory()
+        y_h = y_all[mine].contiguous().pin_memory()
+        m_total = float(x_all.numel())
+        opt = make_optimizer(model)
+
+        def e2e_step():
+            xs, ys = x_h.to(device, non_blocking=True), y_h.to(device, non_blocking=True)
+            opt.zero_grad()
+            out = model()[xs]
+            picked = out.gather(1, ys.to(torch.float32).argmax(-1, keepdim=True)).squeeze(1)
+            local = (torch.logsumexp(out, dim=1) - picked).sum() / m_total
+            local.backward()
+            opt.step()
+            tot = local.detach().clone()
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            return tot.item()
+
+        e2e_ms = B.time_steps(e2e_step, args.steps, args.warmup, world, device) / args.steps
+        h2d = torch.tensor([x_h.numel() * x_h.element_size() + y_h.numel() * y_h.element_size()], device=device,
+                           dtype=torch.float64)
+        dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
+        e2e = {'value': e / (e2e_ms * 1e-3), 'unit': unit, 'h2d_bytes_per_step': int(h2d.item()),
+               'd2h_bytes_per_step': 4 * world, 'ms_per_step': e2e_ms,
+               'what': 'Trainer.train iteration body on the partitioned model (eager): per-rank share of x_train/y_train '
+                       'from pinned host memory, fwd, CE loss (global mean), bwd, FusedAdam on the embedding shard and '
+                       'the replicated weights, all-reduced loss .item(); bytes summed over ranks'}
     own_edges = torch.tensor([graph.query(_lib.Q_NUM_ENTRIES0, _lib.BRC_FWD) - graph.num_owned], device=device,
                              dtype=torch.float64)
     mx = own_edges.clone()
@@ -187,13 +225,13 @@ def run_partitioned_bench(args, rank: int, world: int, device, metric: str, unit
             'config': {'workload': 'am_shape_full_graph_rgcn_63_16_11_all_grads', 'scale': args.scale, 'nodes': n,
                        'directed_edges': e, 'relations': r, 'partition': f'dst-partitioned x{world}, equal node ranges',
                        'collectives': 'per layer: all_gather(x) fwd, all_gather(gout) bwd; one all_reduce of dW/droot/dbias',
-                       'all_gather_bytes_per_step_per_rank': comm.bytes_gathered // max(args.steps, 1),
+                       'all_gather_bytes_per_step_per_rank': gathered,
                        'max_rank_in_edges': int(mx.item()), 'mean_rank_in_edges': e / world,
-                       'sync_collectives_ms_per_step_rank0': comm.comm_ms() / max(args.steps, 1),
+                       'sync_collectives_ms_per_step_rank0': sync_ms,
                        'graph_build_ms_once': setup_ms,
                        'l2_policy': 'inputs larger than L2; no flush'},
             'clocks': clocks, 'gpu_launches': int(launches),
-            'e2e': None, 'roofline': None, 'cpu_baseline': None,
+            'e2e': e2e, 'roofline': None, 'cpu_baseline': None,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()
