@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RGCN_B200_ABI_VERSION 3
+#define RGCN_B200_ABI_VERSION 4
 
 typedef enum {
     RGCN_OK = 0,
@@ -62,7 +62,8 @@ enum {
     RGCN_A_E_W = 6 /*f32[E3]*/, RGCN_A_RAW_IDX = 7 /*i32[E+N]*/, RGCN_A_RAW_W = 8 /*f32[E+N]*/,
     RGCN_A_CHUNK_BEG = 9 /*i32[NC]*/, RGCN_A_CHUNK_END = 10 /*i32[NC]*/,
     RGCN_A_BAT_SEG0 = 11 /*i32[NB]*/, RGCN_A_BAT_INFO = 12 /*i32[NB]*/,
-    RGCN_A_E_OWN = 13 /*i32[E3]*/, RGCN_A_TILE_E0 = 14 /*i32[NT]*/, RGCN_A_TILE_INFO = 15 /*i32[NT]*/
+    RGCN_A_E_OWN = 13 /*i32[E3]*/, RGCN_A_TILE_E0 = 14 /*i32[NT]*/, RGCN_A_TILE_INFO = 15 /*i32[NT]*/,
+    RGCN_A_CHUNK_OUT = 16 /*i32[NC]: chunk-matrix row of each chunk; FWD_REL only (it shares FWD's numbering), else empty*/
 };
 
 /* layer flags */
@@ -125,6 +126,23 @@ int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin
                    const float* gout, int64_t ldg, const float* gout_gather, int64_t ldgg, int32_t fout,
                    float* gx, int64_t ldgx, float* gweight, float* groot, float* gbias,
                    uint32_t flags, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Chunk-row reuse between forward and backward.  Long (relation, dst) segments are pre-reduced into
+ * "chunk rows" ([num_chunks, pad(fin)] floats, pad = 16/32/64); dL/dW needs exactly the rows the
+ * forward pass computed (same x, same flags).  rgcn_layer_fwd_keep writes them to the caller's
+ * `chunk_rows` buffer (rgcn_layer_chunk_rows_bytes(g, fin) bytes, 16-byte aligned) instead of its
+ * workspace; rgcn_layer_bwd_reuse takes them back (null = recompute, i.e. plain rgcn_layer_bwd). */
+int64_t rgcn_layer_chunk_rows_bytes(const rgcn_graph* g, int32_t fin);
+int rgcn_layer_fwd_keep(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin,
+                        const float* weight, const float* root, const float* bias,
+                        float* out, int64_t ldo, int32_t fout, uint32_t flags,
+                        void* workspace, int64_t workspace_bytes, float* chunk_rows, void* stream);
+int rgcn_layer_bwd_reuse(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin,
+                         const float* weight, const float* root,
+                         const float* gout, int64_t ldg, const float* gout_gather, int64_t ldgg, int32_t fout,
+                         float* gx, int64_t ldgx, float* gweight, float* groot, float* gbias,
+                         uint32_t flags, void* workspace, int64_t workspace_bytes, const float* x_chunk_rows,
+                         void* stream);
 
 /* K5 — get_tensor_list + sum/concat/stack (reference model/embeddingTricks.py:8-49).
  * For summary s: row i of T_s = emb[s][idx[s][i]] if idx[s][i] >= 0 else fallback[s][i]

@@ -138,6 +138,34 @@ def build_brc(own, gat, rel, n, r, nr, t, ch, w_edge=None, lo=0, hi=None):
                 num_groups=g, num_batches=nb, bat_seg0=bat_seg0, bat_info=bat_info)
 
 
+def share_chunks(fwd, fwd_rel, n_gat):
+    """FWD_REL shares FWD's chunk numbering (graph_build.cu share_chunks): both chunk the same
+    (relation, dst) segments into the same pieces; FWD_REL's chunk c is the c-th chunk in
+    (relation, dst, piece) order, and a stable sort of FWD's chunks by (relation, dst) gives FWD's id
+    of it.  Returns a copy of fwd_rel with the chunk entries renumbered and ``chunk_out`` = that map."""
+    nc = fwd['num_chunks']
+    out = dict(fwd_rel)
+    if nc == 0 or nc != fwd_rel['num_chunks']:
+        out['chunk_out'] = np.zeros(0, dtype=np.int32)
+        return out
+    n_own = int(max(fwd['seg_own'].max(), fwd_rel['seg_own'].max())) + 1
+    key = np.zeros(nc, dtype=np.int64)
+    idx = fwd['e_idx'] & np.uint32(0x7fffffff)
+    for s in range(fwd['num_seg']):
+        a, b = int(fwd['seg_ptr'][s]), int(fwd['seg_ptr'][s + 1])
+        if a < b and idx[a] >= n_gat:
+            for o in range(a, b):
+                key[int(idx[o]) - n_gat] = int(fwd['seg_rel'][s]) * n_own + int(fwd['seg_own'][s])
+    order = np.argsort(key, kind='stable').astype(np.int32)
+    e = fwd_rel['e_idx'].copy()
+    ridx = e & np.uint32(0x7fffffff)
+    is_chunk = ridx >= n_gat
+    e[is_chunk] = (np.uint32(n_gat) + order[(ridx[is_chunk] - n_gat).astype(np.int64)].astype(np.uint32)) | (e[is_chunk] & LAST_FLAG)
+    out['e_idx'] = e
+    out['chunk_out'] = order
+    return out
+
+
 def build_graph(src, dst, rel, n, r, nr, t, ch, lo=0, hi=None):
     """Forward (owner = dst) and transposed (owner = src) BRCs as the engine builds them."""
     w = edge_weights(dst, rel, n)

@@ -76,10 +76,19 @@ extern "C" int64_t rgcn_layer_workspace_bytes(const rgcn_graph* g, int32_t fin, 
     return backward ? bwd_ws(g, fin, fout) : fwd_ws(g, fin, fout);
 }
 
-extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, const float* weight,
-                              const float* root, const float* bias, float* out, int64_t ldo, int32_t fout,
-                              uint32_t flags, void* workspace, int64_t workspace_bytes, void* stream) {
-    if (!g || !x || !weight || !out || fin <= 0 || fout <= 0 || ldx < fin || ldo < fout)
+extern "C" int64_t rgcn_layer_chunk_rows_bytes(const rgcn_graph* g, int32_t fin) {
+    if (!g || fin <= 0) return -1;
+    const int kp = pad_dim(fin);
+    if (!kp) return 0;   // generic kernels: no chunk rows
+    return ws_take((int64_t)g->brc[RGCN_BRC_FWD].num_chunks * kp, 4);
+}
+
+namespace {
+int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, const float* weight, const float* root,
+              const float* bias, float* out, int64_t ldo, int32_t fout, uint32_t flags, void* workspace,
+              int64_t workspace_bytes, float* chunk_rows, void* stream) {
+    if (!g || !x || !weight || !out || fin <= 0 || fout <= 0 || ldx < fin || ldo < fout ||
+        ((uintptr_t)chunk_rows & 15) != 0)
         return fail(RGCN_ERR_INVALID_ARG, "rgcn_layer_fwd: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     const bool relu = (flags & RGCN_F_RELU_IN) != 0;
@@ -102,6 +111,7 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     float4* wfrag = (float4*)ws.take<float>((int64_t)(g->R + 1) * kp * np * 2);
     float2* wfrag2 = (float2*)ws.take<float>((int64_t)(g->R + 1) * kp * np);
     float* aux = ws.take<float>((int64_t)g->brc[RGCN_BRC_FWD].num_chunks * kp);
+    if (chunk_rows) aux = chunk_rows;   // kept by the caller for rgcn_layer_bwd_reuse
     // accumulate straight into `out` when its rows are 16-byte addressable and hold whole quads
     // (ldo == fout % 4 == 0, or a caller-padded row: ldo % 4 == 0 and ldo >= ceil4(fout); the pad
     // columns then receive zeros); otherwise through a padded buffer + column copy
@@ -144,12 +154,29 @@ extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, 
     if (!direct) return launch_copy_cols(target, tld, out, ldo, g->n_own, fout, st);
     return 0;
 }
+}  // namespace
 
-extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, const float* weight,
-                              const float* root, const float* gout, int64_t ldg, const float* gout_gather,
-                              int64_t ldgg, int32_t fout, float* gx, int64_t ldgx, float* gweight, float* groot,
-                              float* gbias, uint32_t flags, void* workspace, int64_t workspace_bytes, void* stream) {
-    if (!g || !x || !weight || !gout || fin <= 0 || fout <= 0 || ldx < fin || ldg < fout || (gx && ldgx < fin))
+extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, const float* weight,
+                              const float* root, const float* bias, float* out, int64_t ldo, int32_t fout,
+                              uint32_t flags, void* workspace, int64_t workspace_bytes, void* stream) {
+    return layer_fwd(g, x, ldx, fin, weight, root, bias, out, ldo, fout, flags, workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" int rgcn_layer_fwd_keep(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, const float* weight,
+                                   const float* root, const float* bias, float* out, int64_t ldo, int32_t fout,
+                                   uint32_t flags, void* workspace, int64_t workspace_bytes, float* chunk_rows,
+                                   void* stream) {
+    return layer_fwd(g, x, ldx, fin, weight, root, bias, out, ldo, fout, flags, workspace, workspace_bytes, chunk_rows,
+                     stream);
+}
+
+namespace {
+int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, const float* weight, const float* root,
+              const float* gout, int64_t ldg, const float* gout_gather, int64_t ldgg, int32_t fout, float* gx,
+              int64_t ldgx, float* gweight, float* groot, float* gbias, uint32_t flags, void* workspace,
+              int64_t workspace_bytes, const float* x_chunk_rows, void* stream) {
+    if (!g || !x || !weight || !gout || fin <= 0 || fout <= 0 || ldx < fin || ldg < fout || (gx && ldgx < fin) ||
+        ((uintptr_t)x_chunk_rows & 15) != 0)
         return fail(RGCN_ERR_INVALID_ARG, "rgcn_layer_bwd: bad argument");
     if (!gout_gather) {
         if (gx && g->n_own != g->N)
@@ -214,7 +241,9 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
         pre.brc = &g->brc[RGCN_BRC_FWD_REL];
         pre.n_nodes = g->N;
         pre.feat = x; pre.ldf = ldx; pre.kin = fin; pre.aux = xaux; pre.kp = kp; pre.relu_in = relu;
-        if ((rc = launch_chunk_prepass(pre, st))) return rc;
+        // FWD_REL shares FWD's chunk numbering: the rows the forward pass kept are these rows
+        if (x_chunk_rows) xaux = const_cast<float*>(x_chunk_rows);
+        else if ((rc = launch_chunk_prepass(pre, st))) return rc;
         WGradPass p{};
         p.brc = &g->brc[RGCN_BRC_FWD_REL];
         p.n_nodes = g->N; p.self_rel = g->R;
@@ -261,6 +290,24 @@ extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, 
         if (relu && (rc = launch_relu_mask(gx, ldgx, x_own, ldx, g->n_own, fin, st))) return rc;
     }
     return 0;
+}
+}  // namespace
+
+extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, const float* weight,
+                              const float* root, const float* gout, int64_t ldg, const float* gout_gather,
+                              int64_t ldgg, int32_t fout, float* gx, int64_t ldgx, float* gweight, float* groot,
+                              float* gbias, uint32_t flags, void* workspace, int64_t workspace_bytes, void* stream) {
+    return layer_bwd(g, x, ldx, fin, weight, root, gout, ldg, gout_gather, ldgg, fout, gx, ldgx, gweight, groot, gbias, flags,
+                     workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" int rgcn_layer_bwd_reuse(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, const float* weight,
+                                    const float* root, const float* gout, int64_t ldg, const float* gout_gather,
+                                    int64_t ldgg, int32_t fout, float* gx, int64_t ldgx, float* gweight, float* groot,
+                                    float* gbias, uint32_t flags, void* workspace, int64_t workspace_bytes,
+                                    const float* x_chunk_rows, void* stream) {
+    return layer_bwd(g, x, ldx, fin, weight, root, gout, ldg, gout_gather, ldgg, fout, gx, ldgx, gweight, groot, gbias, flags,
+                     workspace, workspace_bytes, x_chunk_rows, stream);
 }
 
 extern "C" int rgcn_pad_rows(const float* src, int64_t lds, int32_t cols, float* dst, int64_t ldd, int64_t n,

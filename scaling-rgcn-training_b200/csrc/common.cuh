@@ -55,6 +55,8 @@ struct Brc {
     float* raw_w = nullptr;        // [E+N]
     int32_t* chunk_beg = nullptr;  // [NC] into raw_*
     int32_t* chunk_end = nullptr;  // [NC]
+    int32_t* chunk_out = nullptr;  // [NC] row of the chunk matrix this chunk is written to (null: its own id).
+                                   // FWD_REL shares FWD's numbering, so backward can reuse forward's chunk rows
     int32_t* bat_seg0 = nullptr;   // [NB]
     int32_t* bat_info = nullptr;   // [NB] rel << 8 | nseg
     int4* units = nullptr;         // [NU+1] equal-cost work units: (first batch, first segment, first entry, 0)

@@ -23,7 +23,7 @@ const char* last_error_cstr() { return g_last_error.c_str(); }
 
 void Brc::release() {
     void* ptrs[] = {perm, seg_ptr0, seg_ptr, seg_own, seg_rel, e_idx, e_w, raw_idx, raw_w,
-                    chunk_beg, chunk_end, bat_seg0, bat_info, units, e_own, tile_e0, tile_info};
+                    chunk_beg, chunk_end, chunk_out, bat_seg0, bat_info, units, e_own, tile_e0, tile_info};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     *this = Brc();
@@ -328,6 +328,56 @@ int bit_length(uint64_t v) {
     return std::max(b, 1);
 }
 
+// ---- chunk numbering shared between FWD and FWD_REL -------------------------------------------
+// Both structures chunk the same (relation, dst) segments into the same pieces (same T / CH, entries
+// of a segment in input order), only the ORDER of the segments differs.  FWD_REL's chunk c is the
+// c-th chunk in (relation, dst, piece) order; a stable sort of FWD's chunks by (relation, dst) gives
+// FWD's id of that chunk.  FWD_REL's chunk entries are rewritten to FWD ids, so the chunk rows the
+// forward pass computed serve dL/dW unchanged (spec: oracle/csr_oracle.py share_chunks).
+__global__ void k_chunk_keys(const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_own,
+                             const int32_t* __restrict__ seg_rel, const uint32_t* __restrict__ e_idx, int32_t S,
+                             uint32_t n_gat, uint64_t n_own, uint64_t* __restrict__ key, int32_t* __restrict__ id) {
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const int32_t a = seg_ptr[s], b = seg_ptr[s + 1];
+    if (a >= b || (e_idx[a] & IDX_MASK) < n_gat) return;   // not a chunked segment
+    for (int32_t o = a; o < b; ++o) {
+        const uint32_t c = (e_idx[o] & IDX_MASK) - n_gat;
+        key[c] = (uint64_t)seg_rel[s] * n_own + (uint64_t)seg_own[s];
+        id[c] = (int32_t)c;
+    }
+}
+__global__ void k_chunk_renumber(uint32_t* __restrict__ e_idx, int64_t E3, uint32_t n_gat,
+                                 const int32_t* __restrict__ order) {
+    int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (o >= E3) return;
+    const uint32_t v = e_idx[o], idx = v & IDX_MASK;
+    if (idx >= n_gat) e_idx[o] = (n_gat + (uint32_t)order[idx - n_gat]) | (v & LAST_FLAG);
+}
+
+int share_chunks(const Brc& fwd, Brc& rel, int64_t n_own, int64_t n_gat, int R, cudaStream_t st) {
+    const int32_t NC = fwd.num_chunks;
+    if (NC == 0 || NC != rel.num_chunks) return 0;
+    Dev<uint64_t> key, skey;
+    Dev<int32_t> id, tmp_order;
+    Dev<char> tmp;
+    RGCN_CUDA(key.alloc(NC));
+    RGCN_CUDA(skey.alloc(NC));
+    RGCN_CUDA(id.alloc(NC));
+    RGCN_CUDA(cudaMalloc(&rel.chunk_out, (size_t)NC * 4));
+    k_chunk_keys<<<blocks_for(fwd.num_seg), TPB, 0, st>>>(fwd.seg_ptr, fwd.seg_own, fwd.seg_rel, fwd.e_idx, fwd.num_seg,
+                                                         (uint32_t)n_gat, (uint64_t)n_own, key.p, id.p);
+    const int end_bit = bit_length((uint64_t)(R + 1) * (uint64_t)n_own);
+    size_t tmp_bytes = 0;
+    RGCN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key.p, skey.p, id.p, rel.chunk_out, (int)NC, 0, end_bit, st));
+    RGCN_CUDA(tmp.alloc(tmp_bytes));
+    RGCN_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key.p, skey.p, id.p, rel.chunk_out, (int)NC, 0, end_bit, st));
+    k_chunk_renumber<<<blocks_for(rel.num_entries), TPB, 0, st>>>(rel.e_idx, rel.num_entries, (uint32_t)n_gat, rel.chunk_out);
+    RGCN_CUDA(cudaGetLastError());
+    RGCN_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 // Build one BRC from an entry list (owner local id, gather global id, relation, weight).
 // n_own owners (ranges of NR), chunk rows are numbered from n_gat (the gather row count).
 int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const float* w_entry, int64_t n2,
@@ -626,6 +676,8 @@ extern "C" int rgcn_graph_create_part(const int64_t* src, int64_t src_stride, co
     if (one_range) {
         g->brc[RGCN_BRC_FWD_REL] = g->brc[RGCN_BRC_FWD];
         g->rel_is_fwd = true;
+    } else if ((rc = share_chunks(g->brc[RGCN_BRC_FWD], g->brc[RGCN_BRC_FWD_REL], g->n_own, num_nodes, num_relations, st))) {
+        return bail(rc);
     }
     // transposed: owner = src, gather = dst, same per-edge weights
     if ((rc = build_side(src32.p, dst32.p, rel32.p, w_edge.p, E, num_nodes, num_relations, own_lo, own_hi, (int)nr, T,
@@ -693,6 +745,7 @@ extern "C" int rgcn_graph_export(const rgcn_graph* g, int32_t brc, int32_t array
         case RGCN_A_E_OWN: p = b.e_own; n = b.num_entries; break;
         case RGCN_A_TILE_E0: p = b.tile_e0; n = b.num_tiles; break;
         case RGCN_A_TILE_INFO: p = b.tile_info; n = b.num_tiles; break;
+        case RGCN_A_CHUNK_OUT: p = b.chunk_out; n = b.chunk_out ? b.num_chunks : 0; break;
         default: return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_export: unknown array");
     }
     if (bytes != n * 4) return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_export: byte count mismatch");

@@ -195,10 +195,12 @@ __global__ void __launch_bounds__(256) k_chunk_sum(const int32_t* __restrict__ r
                                                    const int32_t* __restrict__ chunk_beg,
                                                    const int32_t* __restrict__ chunk_end, int num_chunks,
                                                    const float* __restrict__ feat, int64_t ldf, int kin,
-                                                   int64_t n_rows, float* __restrict__ aux) {
+                                                   int64_t n_rows, float* __restrict__ aux,
+                                                   const int32_t* __restrict__ chunk_out) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= num_chunks) return;
+    const int64_t row = chunk_out ? chunk_out[c] : c;   // FWD_REL writes FWD's numbering
     const LanePtrs q = lane_ptrs<KP>(feat, ldf, kin, nullptr, n_rows, lane);
     const int e0 = chunk_beg[c], e1 = chunk_end[c];
     float acc0 = 0.f, acc1 = 0.f;
@@ -221,9 +223,9 @@ __global__ void __launch_bounds__(256) k_chunk_sum(const int32_t* __restrict__ r
             }
         }
     }
-    if (lane < min(KP, kin)) aux[(int64_t)c * KP + lane] = acc0;   // pad columns stay zero
-    else if (lane < KP) aux[(int64_t)c * KP + lane] = 0.f;
-    if (KP > 32) aux[(int64_t)c * KP + lane + 32] = acc1;          // v1 is zero past the width
+    if (lane < min(KP, kin)) aux[row * KP + lane] = acc0;   // pad columns stay zero
+    else if (lane < KP) aux[row * KP + lane] = 0.f;
+    if (KP > 32) aux[row * KP + lane + 32] = acc1;          // v1 is zero past the width
 }
 
 // 16-column rows that are 16-byte addressable: 4 lanes per row, 8 rows per load instruction (the
@@ -233,10 +235,11 @@ __global__ void __launch_bounds__(256) k_chunk_sum16(const int32_t* __restrict__
                                                      const int32_t* __restrict__ chunk_beg,
                                                      const int32_t* __restrict__ chunk_end, int num_chunks,
                                                      const float* __restrict__ feat, int64_t ldf, int kin,
-                                                     float* __restrict__ aux) {
+                                                     float* __restrict__ aux, const int32_t* __restrict__ chunk_out) {
     const int lane = threadIdx.x & 31, q = lane & 3, r = lane >> 2;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= num_chunks) return;
+    const int64_t row = chunk_out ? chunk_out[c] : c;
     const int e0 = chunk_beg[c], e1 = chunk_end[c];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool col_ok = 4 * q < kin;   // kin is a multiple of 4 here (whole quads inside the row)
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(256) k_chunk_sum16(const int32_t* __restrict__
         acc.z += __shfl_xor_sync(FULL, acc.z, sh);
         acc.w += __shfl_xor_sync(FULL, acc.w, sh);
     }
-    if (r == 0) reinterpret_cast<float4*>(aux + (int64_t)c * 16)[q] = acc;
+    if (r == 0) reinterpret_cast<float4*>(aux + row * 16)[q] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -865,10 +868,10 @@ template <int KP>
 void run_chunk(const Brc& b, const TilePass& p, int grid, int wpb, cudaStream_t st) {
     if (p.relu_in)
         k_chunk_sum<KP, true><<<grid, wpb * 32, 0, st>>>(b.raw_idx, b.raw_w, b.chunk_beg, b.chunk_end, b.num_chunks, p.feat,
-                                                         p.ldf, p.kin, p.n_nodes, p.aux);
+                                                         p.ldf, p.kin, p.n_nodes, p.aux, b.chunk_out);
     else
         k_chunk_sum<KP, false><<<grid, wpb * 32, 0, st>>>(b.raw_idx, b.raw_w, b.chunk_beg, b.chunk_end, b.num_chunks, p.feat,
-                                                          p.ldf, p.kin, p.n_nodes, p.aux);
+                                                          p.ldf, p.kin, p.n_nodes, p.aux, b.chunk_out);
 }
 }  // namespace
 
@@ -885,10 +888,10 @@ int launch_chunk_prepass(const TilePass& p, cudaStream_t st) {
     if (quad16) {
         if (p.relu_in)
             k_chunk_sum16<true><<<grid, wpb * 32, 0, st>>>(b.raw_idx, b.raw_w, b.chunk_beg, b.chunk_end, b.num_chunks, p.feat,
-                                                           p.ldf, p.kin, p.aux);
+                                                           p.ldf, p.kin, p.aux, b.chunk_out);
         else
             k_chunk_sum16<false><<<grid, wpb * 32, 0, st>>>(b.raw_idx, b.raw_w, b.chunk_beg, b.chunk_end, b.num_chunks, p.feat,
-                                                            p.ldf, p.kin, p.aux);
+                                                            p.ldf, p.kin, p.aux, b.chunk_out);
         RGCN_CUDA(cudaGetLastError());
         return 0;
     }

@@ -17,7 +17,8 @@ EXPORTS = (
     'rgcn_last_error', 'rgcn_abi_version', 'rgcn_graph_create', 'rgcn_graph_create_part', 'rgcn_graph_destroy', 'rgcn_graph_query',
     'rgcn_graph_export', 'rgcn_layer_workspace_bytes', 'rgcn_layer_fwd', 'rgcn_layer_bwd', 'rgcn_map_gather',
     'rgcn_kernel_launch_count', 'rgcn_profile_enable', 'rgcn_profile_collect', 'rgcn_pad_rows',
-    'rgcn_eval_counts', 'rgcn_adam_step', 'rgcn_adam_step_dev',
+    'rgcn_eval_counts', 'rgcn_adam_step', 'rgcn_adam_step_dev', 'rgcn_layer_chunk_rows_bytes', 'rgcn_layer_fwd_keep',
+    'rgcn_layer_bwd_reuse',
 )
 
 BRC_FWD, BRC_BWD, BRC_FWD_REL = 0, 1, 2
@@ -25,7 +26,7 @@ Q_NUM_NODES, Q_NUM_EDGES, Q_NUM_RELATIONS, Q_NUM_SEGMENTS, Q_NUM_ENTRIES, Q_NUM_
     Q_NUM_BATCHES, Q_RANGE_NODES, Q_DEVICE_BYTES, Q_NUM_OWNED, Q_OWN_LO, Q_NUM_ENTRIES0, Q_NUM_TILES, \
     Q_NUM_TILES_NOSELF = range(15)
 A_PERM, A_SEG_PTR, A_SEG_OWN, A_SEG_REL, A_SEG_PTR0, A_E_IDX, A_E_W, A_RAW_IDX, A_RAW_W, A_CHUNK_BEG, \
-    A_CHUNK_END, A_BAT_SEG0, A_BAT_INFO, A_E_OWN, A_TILE_E0, A_TILE_INFO = range(16)
+    A_CHUNK_END, A_BAT_SEG0, A_BAT_INFO, A_E_OWN, A_TILE_E0, A_TILE_INFO, A_CHUNK_OUT = range(17)
 F_RELU_IN, F_FORCE_SIMPLE = 1, 2
 
 _lib = None
@@ -65,6 +66,13 @@ def load():
     lib.rgcn_layer_fwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, i64, i32, u32, vp, i64, vp]
     lib.rgcn_layer_bwd.restype = C.c_int
     lib.rgcn_layer_bwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, i64, vp, i64, i32, vp, i64, vp, vp, vp, u32, vp, i64, vp]
+    lib.rgcn_layer_chunk_rows_bytes.restype = i64
+    lib.rgcn_layer_chunk_rows_bytes.argtypes = [vp, i32]
+    lib.rgcn_layer_fwd_keep.restype = C.c_int
+    lib.rgcn_layer_fwd_keep.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, i64, i32, u32, vp, i64, vp, vp]
+    lib.rgcn_layer_bwd_reuse.restype = C.c_int
+    lib.rgcn_layer_bwd_reuse.argtypes = [vp, vp, i64, i32, vp, vp, vp, i64, vp, i64, i32, vp, i64, vp, vp, vp, u32, vp, i64,
+                                         vp, vp]
     lib.rgcn_map_gather.restype = C.c_int
     lib.rgcn_map_gather.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i32, i64, i32, i32, vp, vp]
     lib.rgcn_eval_counts.restype = C.c_int

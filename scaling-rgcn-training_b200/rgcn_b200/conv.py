@@ -28,6 +28,7 @@ def _glorot_(t: Tensor) -> None:   # PyG inits.glorot
 
 
 _PAD_WIDE = os.environ.get('RGCN_B200_PAD', '1') != '0'
+_KEEP_CHUNKS = os.environ.get('RGCN_B200_KEEP_CHUNKS', '1') != '0'
 
 
 def _ptr(t: Optional[Tensor]) -> int:
@@ -87,12 +88,18 @@ class _RGCNLayerFn(torch.autograd.Function):
         out = out_buf[:, :fout] if ldo != fout else out_buf
         ws_bytes = graph.workspace_bytes(fin, fout, False)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        # the pre-reduced rows of long (relation, dst) segments are kept for dL/dW when a weight
+        # gradient will be asked for (a few MB; saves recomputing them in backward)
+        keep = _KEEP_CHUNKS and any(ctx.needs_input_grad[1:4]) and not (flags & _lib.F_FORCE_SIMPLE)
+        xc_bytes = lib.rgcn_layer_chunk_rows_bytes(graph.handle, fin) if keep else 0
+        xc = torch.empty(xc_bytes, dtype=torch.uint8, device=x.device) if xc_bytes > 0 else None
         with torch.cuda.device(x.device):
-            rc = lib.rgcn_layer_fwd(graph.handle, x.data_ptr(), x.stride(0), fin, weight.data_ptr(), _ptr(root_c),
-                                    _ptr(bias_c), out_buf.data_ptr(), ldo, fout, flags, ws.data_ptr(), ws_bytes,
-                                    _stream(x.device))
+            rc = lib.rgcn_layer_fwd_keep(graph.handle, x.data_ptr(), x.stride(0), fin, weight.data_ptr(), _ptr(root_c),
+                                         _ptr(bias_c), out_buf.data_ptr(), ldo, fout, flags, ws.data_ptr(), ws_bytes,
+                                         _ptr(xc), _stream(x.device))
         _lib.check(rc, 'rgcn_layer_fwd')
         ctx.graph, ctx.flags, ctx.comm, ctx.fin = graph, flags, comm, fin
+        ctx.x_chunk_rows = xc
         ctx.has_root, ctx.has_bias = root is not None, bias is not None
         ctx.save_for_backward(x, weight, root_c if root_c is not None else x.new_empty(0))
         return out
@@ -128,11 +135,11 @@ class _RGCNLayerFn(torch.autograd.Function):
             ws_bytes = graph.workspace_bytes(fin, fout, True)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             with torch.cuda.device(dev):
-                rc = lib.rgcn_layer_bwd(graph.handle, x.data_ptr(), x.stride(0), fin, weight.data_ptr(), _ptr(root),
-                                        gout.data_ptr(), gout.stride(0), _ptr(gout_all),
-                                        gout_all.stride(0) if gout_all is not None else 0, fout, _ptr(gx_t), fin,
-                                        _ptr(gw_t), _ptr(groot_t), _ptr(gbias_t), ctx.flags, ws.data_ptr(), ws_bytes,
-                                        _stream(dev))
+                rc = lib.rgcn_layer_bwd_reuse(graph.handle, x.data_ptr(), x.stride(0), fin, weight.data_ptr(), _ptr(root),
+                                              gout.data_ptr(), gout.stride(0), _ptr(gout_all),
+                                              gout_all.stride(0) if gout_all is not None else 0, fout, _ptr(gx_t), fin,
+                                              _ptr(gw_t), _ptr(groot_t), _ptr(gbias_t), ctx.flags, ws.data_ptr(),
+                                              ws_bytes, _ptr(ctx.x_chunk_rows), _stream(dev))
             _lib.check(rc, 'rgcn_layer_bwd')
 
         if work is not None and (need_w or need_root or need_bias):

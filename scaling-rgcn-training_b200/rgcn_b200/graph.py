@@ -75,6 +75,9 @@ class RGCNGraph:
             _lib.A_BAT_SEG0: self.query(_lib.Q_NUM_BATCHES, brc), _lib.A_BAT_INFO: self.query(_lib.Q_NUM_BATCHES, brc),
             _lib.A_E_OWN: self.query(_lib.Q_NUM_ENTRIES, brc), _lib.A_TILE_E0: self.query(_lib.Q_NUM_TILES, brc),
             _lib.A_TILE_INFO: self.query(_lib.Q_NUM_TILES, brc),
+            # only a FWD_REL structure of its own (several ranges) carries the map onto FWD's chunk numbering
+            _lib.A_CHUNK_OUT: (self.query(_lib.Q_NUM_CHUNKS, brc)
+                               if brc == _lib.BRC_FWD_REL and self.query(_lib.Q_RANGE_NODES) < self.num_owned else 0),
         }[array]
         out = np.empty(n, dtype=_ARRAY_DTYPES.get(array, np.int32))
         with torch.cuda.device(self.device):

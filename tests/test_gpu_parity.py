@@ -54,6 +54,9 @@ def test_graph_build_bit_exact(name, nr, t, ch):
     _check_brc(g, _lib.BRC_FWD, fwd)
     _check_brc(g, _lib.BRC_BWD, bwd)
     fwd_rel = csr_oracle.build_brc(dst, src, rel, n, r, n, t_eff, ch_eff, w_edge=csr_oracle.edge_weights(dst, rel, n))
+    if nr_eff < n:      # several ranges: FWD_REL is its own structure and shares FWD's chunk numbering
+        fwd_rel = csr_oracle.share_chunks(fwd, fwd_rel, n)
+        assert np.array_equal(g.export(_lib.A_CHUNK_OUT, _lib.BRC_FWD_REL), fwd_rel['chunk_out'])
     _check_brc(g, _lib.BRC_FWD_REL, fwd_rel)
 
 
