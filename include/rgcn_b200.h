@@ -131,12 +131,17 @@ int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin
  * "chunk rows" ([num_chunks, pad(fin)] floats, pad = 16/32/64); dL/dW needs exactly the rows the
  * forward pass computed (same x, same flags).  rgcn_layer_fwd_keep writes them to the caller's
  * `chunk_rows` buffer (rgcn_layer_chunk_rows_bytes(g, fin) bytes, 16-byte aligned) instead of its
- * workspace; rgcn_layer_bwd_reuse takes them back (null = recompute, i.e. plain rgcn_layer_bwd). */
+ * workspace; rgcn_layer_bwd_reuse takes them back (null = recompute, i.e. plain rgcn_layer_bwd).
+ * x_mirror (nullable, [num_nodes, ld_mirror], ld_mirror % 4 == 0, 16-byte aligned): when the rows of x are
+ * not 16-byte addressable (emb = 63) the engine gathers from this zero-padded copy instead, which it
+ * writes itself — fused with the root/self-loop pass where the shape allows, so x is read once.  The
+ * caller then passes the mirror (ldx = ld_mirror) as x to the backward call. */
 int64_t rgcn_layer_chunk_rows_bytes(const rgcn_graph* g, int32_t fin);
 int rgcn_layer_fwd_keep(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin,
                         const float* weight, const float* root, const float* bias,
                         float* out, int64_t ldo, int32_t fout, uint32_t flags,
-                        void* workspace, int64_t workspace_bytes, float* chunk_rows, void* stream);
+                        void* workspace, int64_t workspace_bytes, float* chunk_rows,
+                        float* x_mirror, int64_t ld_mirror, void* stream);
 int rgcn_layer_bwd_reuse(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin,
                          const float* weight, const float* root,
                          const float* gout, int64_t ldg, const float* gout_gather, int64_t ldgg, int32_t fout,

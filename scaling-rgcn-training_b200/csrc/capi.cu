@@ -86,9 +86,10 @@ extern "C" int64_t rgcn_layer_chunk_rows_bytes(const rgcn_graph* g, int32_t fin)
 namespace {
 int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, const float* weight, const float* root,
               const float* bias, float* out, int64_t ldo, int32_t fout, uint32_t flags, void* workspace,
-              int64_t workspace_bytes, float* chunk_rows, void* stream) {
+              int64_t workspace_bytes, float* chunk_rows, float* x_mirror, int64_t ld_mirror, void* stream) {
     if (!g || !x || !weight || !out || fin <= 0 || fout <= 0 || ldx < fin || ldo < fout ||
-        ((uintptr_t)chunk_rows & 15) != 0)
+        ((uintptr_t)chunk_rows & 15) != 0 ||
+        (x_mirror && (((uintptr_t)x_mirror & 15) != 0 || ld_mirror % 4 != 0 || ld_mirror < ((fin + 3) & ~3))))
         return fail(RGCN_ERR_INVALID_ARG, "rgcn_layer_fwd: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     const bool relu = (flags & RGCN_F_RELU_IN) != 0;
@@ -97,6 +98,11 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
     const bool big = (uint64_t)g->N * (uint64_t)ldx >= (1ull << 32) ||
                      (uint64_t)g->n_own * (uint64_t)std::max<int64_t>(ldo, np) >= (1ull << 32);
     if ((flags & RGCN_F_FORCE_SIMPLE) || !kp || !np || big) {
+        // (the mirror is always written when one is given: the caller hands it to backward as x)
+        if (x_mirror) {
+            int prc = launch_pad_rows(x, ldx, fin, x_mirror, ld_mirror, g->N, st);
+            if (prc) return prc;
+        }
         RGCN_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)fout * 4, (size_t)g->n_own, st));
         SimplePass p{};
         p.brc = &g->brc[RGCN_BRC_FWD];
@@ -121,9 +127,21 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
     if (!ws.ok) return fail(RGCN_ERR_WORKSPACE, "rgcn_layer_fwd: workspace too small (see rgcn_layer_workspace_bytes)");
     const int64_t tld = direct ? ldo : np;
     const int tn = direct ? fout4 : np;
-    int rc;
+    int rc = 0;
     // wide rows that are not 16-byte addressable (Fin = 63) go through the staged kernels; everything
     // else is gathered straight into MMA fragments
+    // rows that are not 16-byte addressable (emb = 63) and a caller-provided mirror: the gathers read the
+    // zero-padded mirror; it is written by the fused pad + self-loop pass when the shape allows, else by
+    // a plain padding copy
+    const float* x_raw = x;
+    const int64_t ld_raw = ldx;
+    bool fused_pad = false;
+    if (x_mirror) {
+        fused_pad = !etile_vec4_ok(x, ldx, fin, aux) && selfloop_pad_ok(kp, np) && g->n_own == g->N && etile_choice(kp, true);
+        if (!fused_pad && (rc = launch_pad_rows(x, ldx, fin, x_mirror, ld_mirror, g->N, st))) return rc;
+        x = x_mirror;
+        ldx = ld_mirror;
+    }
     const bool v4ok = etile_vec4_ok(x, ldx, fin, aux);
     const bool et = etile_choice(kp, v4ok);
     const bool v4 = et && v4ok;
@@ -143,9 +161,12 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
     p.relu_in = relu;
     p.vec4 = v4;
     p.out_rows = g->n_own;
+    if (fused_pad) {   // writes the mirror (which the pre-pass and the edge tiles then gather) and root + bias
+        if ((rc = launch_selfloop_pad(p, x_raw, ld_raw, x_mirror, ld_mirror, g->n_own, g->R, g->num_sms, st))) return rc;
+    }
     if ((rc = launch_chunk_prepass(p, st))) return rc;
     if (et) {   // root + bias with plain stores (initialises the target), then the edge tiles accumulate
-        if ((rc = launch_selfloop_pass(p, g->own_lo, g->n_own, g->R, g->num_sms, st))) return rc;
+        if (!fused_pad && (rc = launch_selfloop_pass(p, g->own_lo, g->n_own, g->R, g->num_sms, st))) return rc;
         if ((rc = launch_etile_pass(p, g->num_sms, st))) return rc;
     } else {
         RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->n_own * tld * 4, st));
@@ -159,15 +180,16 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
 extern "C" int rgcn_layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, const float* weight,
                               const float* root, const float* bias, float* out, int64_t ldo, int32_t fout,
                               uint32_t flags, void* workspace, int64_t workspace_bytes, void* stream) {
-    return layer_fwd(g, x, ldx, fin, weight, root, bias, out, ldo, fout, flags, workspace, workspace_bytes, nullptr, stream);
+    return layer_fwd(g, x, ldx, fin, weight, root, bias, out, ldo, fout, flags, workspace, workspace_bytes, nullptr, nullptr,
+                     0, stream);
 }
 
 extern "C" int rgcn_layer_fwd_keep(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, const float* weight,
                                    const float* root, const float* bias, float* out, int64_t ldo, int32_t fout,
                                    uint32_t flags, void* workspace, int64_t workspace_bytes, float* chunk_rows,
-                                   void* stream) {
+                                   float* x_mirror, int64_t ld_mirror, void* stream) {
     return layer_fwd(g, x, ldx, fin, weight, root, bias, out, ldo, fout, flags, workspace, workspace_bytes, chunk_rows,
-                     stream);
+                     x_mirror, ld_mirror, stream);
 }
 
 namespace {

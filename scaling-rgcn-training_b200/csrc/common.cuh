@@ -145,6 +145,9 @@ bool etile_vec4_ok(const float* feat, int64_t ldf, int kin, const float* aux);
 int launch_etile_pass(const TilePass& p, int num_sms, cudaStream_t st);   // edge tiles only: run launch_selfloop_pass first
 int launch_selfloop_pass(const TilePass& p, int64_t own_lo, int64_t n_own, int R, int num_sms, cudaStream_t st);
 int launch_ewgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st);
+bool selfloop_pad_ok(int kp, int np);
+int launch_selfloop_pad(const TilePass& p, const float* x_raw, int64_t ld_raw, float* mirror, int64_t ldm, int64_t n_own,
+                        int R, int num_sms, cudaStream_t st);
 
 int launch_copy_cols(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t n, int cols, cudaStream_t st);
 int launch_pad_rows(const float* src, int64_t lds, int cols, float* dst, int64_t ldd, int64_t n, cudaStream_t st);

@@ -718,6 +718,8 @@ struct SelfArgs {
     int64_t ldo;
     int nout;
     int64_t n_own;
+    float* mirror;       // k_selfloop_pad: zero-padded 16-byte addressable copy of x, written on the way
+    int64_t ldm;
 };
 
 // PACK: `out` rows are tightly packed with a width that is not a multiple of 4 (ldo == nout): the
@@ -846,6 +848,110 @@ __global__ void __launch_bounds__(EW * 32, 2) k_selfloop(const SelfArgs a) {
                 }
             }
         }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// self loop fused with the padding copy (rows of 33..64 floats that are NOT 16-byte addressable, the
+// reference's emb = 63): the pass that makes the zero-padded mirror reads every row of x anyway, so
+// it also multiplies it by root.  Row-wise coalesced 4-byte loads -> shared tile -> (a) the mirror
+// rows as 16-byte stores, (b) the A fragments.  Replaces k_pad_rows + k_selfloop<8, NT>: x is read
+// once instead of x once and the mirror once.
+// ---------------------------------------------------------------------------------------------
+template <int NT, bool RELU>
+__global__ void __launch_bounds__(EW * 32, 2) k_selfloop_pad(const SelfArgs a) {
+    constexpr int KT = 8, SW = 80;   // staged row stride: the 8 lanes of a 128-bit phase hit distinct banks
+    static_assert(KT * NT <= 16, "fragments are kept in registers");
+    __shared__ __align__(16) float stage[EW * 16 * SW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t gw = (int64_t)blockIdx.x * EW + warp, nw = (int64_t)gridDim.x * EW;
+    float* sb = stage + warp * (16 * SW);
+    const float4* wf = a.rfrag + lane;
+    float4 bfrag[KT * NT];
+#pragma unroll
+    for (int i = 0; i < KT * NT; ++i) bfrag[i] = __ldg(wf + i * 32);
+    float bx[NT], by[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        const int col = 8 * n + 2 * t;
+        bx[n] = (a.bias && col < a.nbias) ? a.bias[col] : 0.f;
+        by[n] = (a.bias && col + 1 < a.nbias) ? a.bias[col + 1] : 0.f;
+    }
+    const bool c0 = lane < a.kin, c1 = lane + 32 < a.kin;
+    const int64_t n_tiles = (a.n_own + 15) / 16;
+    for (int64_t tile = gw; tile < n_tiles; tile += nw) {
+        const int rows = (int)min((int64_t)16, a.n_own - tile * 16);
+        const float* src = a.x + tile * 16 * a.ldx + lane;
+        float v0[16], v1[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            v0[r] = (r < rows && c0) ? __ldg(src + r * a.ldx) : 0.f;
+            v1[r] = (r < rows && c1) ? __ldg(src + r * a.ldx + 32) : 0.f;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            sb[r * SW + lane] = v0[r];          // columns >= kin are the zero padding
+            sb[r * SW + lane + 32] = v1[r];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // the mirror: 16 rows x 16 quads, 512 contiguous bytes per instruction
+            const int i = lane + 32 * k, r = i >> 4, q = i & 15;
+            if (r < rows && 4 * q < a.ldm)
+                *reinterpret_cast<float4*>(a.mirror + (tile * 16 + r) * a.ldm + 4 * q) =
+                    *reinterpret_cast<const float4*>(sb + r * SW + 4 * q);
+        }
+        float d[NT][4];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            d[n][0] = bx[n];
+            d[n][1] = by[n];
+            d[n][2] = bx[n];
+            d[n][3] = by[n];
+        }
+#pragma unroll
+        for (int j = 0; j < KT / 2; ++j) {
+            const float4 vg = *reinterpret_cast<const float4*>(sb + g * SW + 16 * j + 4 * t);
+            const float4 vh = *reinterpret_cast<const float4*>(sb + (g + 8) * SW + 16 * j + 4 * t);
+            // K order of the vector-load kernels: step 2j <- cols (x, y), step 2j+1 <- (z, w)
+            float xs[2][4] = {{vg.x, vh.x, vg.y, vh.y}, {vg.z, vh.z, vg.w, vh.w}};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t ah[4], al[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) split_fast(RELU ? fmaxf(xs[h][q], 0.f) : xs[h][q], ah[q], al[q]);
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    const float4 bf = bfrag[(2 * j + h) * NT + n];
+                    const uint32_t bh0 = __float_as_uint(bf.x), bh1 = __float_as_uint(bf.y);
+                    const uint32_t bl0 = __float_as_uint(bf.z), bl1 = __float_as_uint(bf.w);
+                    mma_tf32(d[n], al[0], al[1], al[2], al[3], bh0, bh1);
+                    mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+                    mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+                }
+            }
+        }
+        const int64_t ig = tile * 16 + g, ih = ig + 8;
+        const bool vgd = ig < a.n_own, vhd = ih < a.n_own;
+        const bool odd = (t & 1) != 0;
+#pragma unroll
+        for (int j = 0; j < NT / 2; ++j) {
+            const int col = odd ? 8 * (2 * j + 1) + 2 * (t - 1) : 8 * (2 * j) + 2 * t;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float p0 = d[2 * j][2 * h], p1 = d[2 * j][2 * h + 1];
+                const float q0 = d[2 * j + 1][2 * h], q1 = d[2 * j + 1][2 * h + 1];
+                const float rx = __shfl_xor_sync(FULL, odd ? p0 : q0, 1);
+                const float ry = __shfl_xor_sync(FULL, odd ? p1 : q1, 1);
+                const int64_t row = h ? ih : ig;
+                if ((h ? vhd : vgd) && col < a.nout) {
+                    float4* p = reinterpret_cast<float4*>(a.out + row * a.ldo + col);
+                    *p = odd ? make_float4(rx, ry, q0, q1) : make_float4(p0, p1, rx, ry);
+                }
+            }
         }
     }
 }
@@ -1039,6 +1145,41 @@ int launch_selfloop_pass(const TilePass& p, int64_t own_lo, int64_t n_own, int R
     ProfScope prof(TAG_SELF, p.kin, p.tag_out, st);
     note_launch(1);
     RGCN_DISPATCH_E(run_selfloop, p.kp, p.np, a, p.relu_in, p.vec4, p.packed, num_sms, st);
+}
+
+// fused padding copy + self loop (see k_selfloop_pad): x = caller's rows (any leading dimension), mirror
+// [n_own, ldm] receives the zero-padded copy; the B fragments must have been prepared with the vector K order
+bool selfloop_pad_ok(int kp, int np) { return kp == 64 && np <= 16; }
+
+int launch_selfloop_pad(const TilePass& p, const float* x_raw, int64_t ld_raw, float* mirror, int64_t ldm, int64_t n_own,
+                        int R, int num_sms, cudaStream_t st) {
+    if (n_own == 0) return 0;
+    if (!selfloop_pad_ok(p.kp, p.np)) return fail(RGCN_ERR_UNSUPPORTED, "fused pad + self loop: unsupported shape");
+    SelfArgs a{};
+    a.x = x_raw;
+    a.ldx = ld_raw;
+    a.kin = p.kin;
+    a.rfrag = p.wfrag + (int64_t)R * (p.kp / 8) * (p.np / 8) * 32;
+    a.bias = p.bias;
+    a.nbias = p.nbias;
+    a.out = p.out;
+    a.ldo = p.ldo;
+    a.nout = p.nout;
+    a.n_own = n_own;
+    a.mirror = mirror;
+    a.ldm = ldm;
+    ProfScope prof(TAG_SELF, p.kin, p.tag_out, st);
+    note_launch(1);
+    const int64_t tiles = (n_own + 15) / 16;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + EW - 1) / EW, (int64_t)num_sms * 2));
+    if (p.np == 16) {
+        if (p.relu_in) k_selfloop_pad<2, true><<<grid, EW * 32, 0, st>>>(a);
+        else k_selfloop_pad<2, false><<<grid, EW * 32, 0, st>>>(a);
+    } else {   // np == 8 does not exist (pad_dim starts at 16)
+        return fail(RGCN_ERR_UNSUPPORTED, "fused pad + self loop: unsupported output width");
+    }
+    RGCN_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int launch_ewgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st) {

@@ -69,7 +69,7 @@ def load():
     lib.rgcn_layer_chunk_rows_bytes.restype = i64
     lib.rgcn_layer_chunk_rows_bytes.argtypes = [vp, i32]
     lib.rgcn_layer_fwd_keep.restype = C.c_int
-    lib.rgcn_layer_fwd_keep.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, i64, i32, u32, vp, i64, vp, vp]
+    lib.rgcn_layer_fwd_keep.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, i64, i32, u32, vp, i64, vp, vp, i64, vp]
     lib.rgcn_layer_bwd_reuse.restype = C.c_int
     lib.rgcn_layer_bwd_reuse.argtypes = [vp, vp, i64, i32, vp, vp, vp, i64, vp, i64, i32, vp, i64, vp, vp, vp, u32, vp, i64,
                                          vp, vp]

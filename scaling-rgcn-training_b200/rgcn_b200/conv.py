@@ -81,8 +81,10 @@ class _RGCNLayerFn(torch.autograd.Function):
         r, fin_w, fout = weight.shape
         if fin_w != fin or r != graph.num_relations:
             raise ValueError('RGCNConv: weight shape does not match input / num_relations')
-        if comm is None:
-            x = pad_rows(x)
+        # unpartitioned: the engine writes the mirror itself (fused with the root pass where it can)
+        mirror = None
+        if comm is None and _PAD_WIDE and 32 < fin <= 64 and (x.stride(0) % 4 != 0 or x.data_ptr() % 16 != 0):
+            mirror = torch.empty((x.size(0), (fin + 3) // 4 * 4), dtype=torch.float32, device=x.device)
         ldo = (fout + 3) // 4 * 4
         out_buf = torch.empty((graph.num_owned, ldo), dtype=torch.float32, device=x.device)
         out = out_buf[:, :fout] if ldo != fout else out_buf
@@ -96,8 +98,11 @@ class _RGCNLayerFn(torch.autograd.Function):
         with torch.cuda.device(x.device):
             rc = lib.rgcn_layer_fwd_keep(graph.handle, x.data_ptr(), x.stride(0), fin, weight.data_ptr(), _ptr(root_c),
                                          _ptr(bias_c), out_buf.data_ptr(), ldo, fout, flags, ws.data_ptr(), ws_bytes,
-                                         _ptr(xc), _stream(x.device))
+                                         _ptr(xc), _ptr(mirror), mirror.stride(0) if mirror is not None else 0,
+                                         _stream(x.device))
         _lib.check(rc, 'rgcn_layer_fwd')
+        if mirror is not None:
+            x = mirror              # what backward re-gathers; the caller's tensor is not kept
         ctx.graph, ctx.flags, ctx.comm, ctx.fin = graph, flags, comm, fin
         ctx.x_chunk_rows = xc
         ctx.has_root, ctx.has_bias = root is not None, bias is not None
