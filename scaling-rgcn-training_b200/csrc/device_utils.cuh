@@ -34,8 +34,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
 __device__ __forceinline__ void red_add_v4(float* p, float x, float y, float z, float w) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
-// L2 eviction policies: gathered rows of a matrix that fits L2 are kept (evict_last); index and
-// weight streams are read exactly once (evict_first, no L1 allocation).
+// L2 eviction policies: gathered rows of a matrix that fits L2 are kept (evict_last).
 __device__ __forceinline__ uint64_t policy_evict_last() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -56,21 +55,5 @@ __device__ __forceinline__ float ldg_hint(const float* p, uint64_t pol) {
     asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
     return v;
 }
-__device__ __forceinline__ uint32_t ldg_stream_u32(const uint32_t* p, uint64_t pol) {
-    uint32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ int32_t ldg_stream_s32(const int32_t* p, uint64_t pol) {
-    int32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ float ldg_stream_f32(const float* p, uint64_t pol) {
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-    return v;
-}
-
 }  // namespace dev
 }  // namespace rgcn

@@ -6,10 +6,12 @@
 // K positions t, t+4 of every 8-column step — so its A fragment is exactly
 //     x[src(g)][8k+t], x[src(g+8)][8k+t], x[src(g)][8k+t+4], x[src(g+8)][8k+t+4]
 // i.e. four plain 4-byte loads off two row pointers with immediate offsets; one load instruction
-// covers 8 rows x 16 B (sector pairs shared by the t / t+4 halves).  No shared memory staging, no
-// per-entry accumulate chain, no segment bookkeeping in the kernel: the per-(relation, dst) mean
-// is the sum of the entries' 1/cnt-weighted rows, and the sum happens in the scatter
-// (REDG.ADD.F32x4 per entry row).  dL/dW needs no segments at all:
+// covers 8 rows x 16 B (sector pairs shared by the t / t+4 halves).  The ROWS are never staged in
+// shared memory, there is no per-entry accumulate chain and no segment bookkeeping in the kernel:
+// the per-(relation, dst) mean is the sum of the entries' 1/cnt-weighted rows, and the sum happens in
+// the scatter (REDG.ADD.F32x4 per entry row, or one bulk reduce per row for 64-column rows).  Only
+// the INDEX streams of a work unit go through shared memory (cp.async, one unit ahead).
+// dL/dW needs no segments at all:
 //     dW_rel = sum_entries (w_e x[src_e])^T (x) gout[owner_e]   =  A^T . B over 16-entry K slices
 // with A^T fragments again direct loads (lane (g,t): entries t, t+4; feature rows 16m+g, +8).
 //
@@ -98,22 +100,6 @@ struct RowRef {   // one gathered row of a lane
     int own;
     bool real;        // a feature row (ReLU applies), not a chunk row
 };
-
-template <int KP>
-__device__ __forceinline__ RowRef make_ref(const ETileArgs& a, int e, bool valid, int koff, uint64_t pol_s) {
-    RowRef r;
-    uint32_t idx = 0;
-    r.w = 0.f;
-    r.own = -1;
-    if (valid) {
-        idx = ldg_stream_u32(a.e_idx + e, pol_s) & IDX_MASK;
-        r.w = ldg_stream_f32(a.e_w + e, pol_s);
-        r.own = ldg_stream_s32(a.e_own + e, pol_s);
-    }
-    r.real = idx < (uint32_t)a.n_rows;
-    r.p = (r.real ? a.feat + (uint64_t)idx * (uint32_t)a.ldf : a.aux + (uint64_t)(idx - (uint32_t)a.n_rows) * KP) + koff;
-    return r;
-}
 
 // ---------------------------------------------------------------------------------------------
 // forward / dL/dx :  out[owner_e] += (w_e * x[src_e]) . B_rel   for the 16 entries of a tile
