@@ -160,6 +160,10 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
         (uint64_t)a.n_rows * (uint64_t)a.ldf * 4ull <= (112ull << 20) ? policy_evict_last() : policy_evict_normal();
     constexpr bool BREG = (KT * NT <= 4);
     float4 bfrag[BREG ? KT * NT : 1];
+    // 16 -> 64 dL/dx: the 16 unsplit fragments of the current relation stay in registers too (their
+    // re-read from L1 every tile is 4 KB per warp per tile: a fifth of the kernel's cycles in L1 returns)
+    constexpr bool BREG2 = (BULK != 0 && KT == 2 && NT == 8);
+    float2 bfrag2[BREG2 ? KT * NT : 1];
     int breg_rel = -1;
     constexpr int KOFF = V4 ? 4 : 1;   // lane's column offset inside a row: 4t (vector) or t
     struct TileRef {   // the two rows of this lane in one tile
@@ -282,6 +286,13 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
                     breg_rel = rel;
                 }
             }
+            if constexpr (BREG2) {
+                if (rel != breg_rel) {
+#pragma unroll
+                    for (int q = 0; q < KT * NT; ++q) bfrag2[q] = __ldg(wf2 + q * 32);
+                    breg_rel = rel;
+                }
+            }
             float d[NT][4];
 #pragma unroll
             for (int n = 0; n < NT; ++n) d[n][0] = d[n][1] = d[n][2] = d[n][3] = 0.f;
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
                         bh0 = __float_as_uint(bf.x), bh1 = __float_as_uint(bf.y);
                         bl0 = __float_as_uint(bf.z), bl1 = __float_as_uint(bf.w);
                     } else {   // fp32 pairs from L1 (half the bytes of the pre-split form), split here
-                        const float2 b2 = __ldg(wf2 + (kt * NT + n) * 32);
+                        const float2 b2 = BREG2 ? bfrag2[kt * NT + n] : __ldg(wf2 + (kt * NT + n) * 32);
                         split_rn(b2.x, bh0, bl0);
                         split_rn(b2.y, bh1, bl1);
                     }
