@@ -421,8 +421,8 @@ def run_engine(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', choices=['engine', 'reference'], default='engine')
     ap.add_argument('--scale', type=float, default=1.0, help='AM-shape scale (1.0 = the BASELINE.json config)')
     ap.add_argument('--ref-scale', type=float, default=1 / 32, help='bounded sample for the CPU reference arm')
