@@ -724,7 +724,7 @@ struct SelfArgs {
 template <int KT, int NT, bool RELU, bool V4, bool PACK = false>
 __global__ void __launch_bounds__(EW * 32, 2) k_selfloop(const SelfArgs a) {
     constexpr bool BREG = (KT * NT <= 16);
-    __shared__ __align__(16) float pack_stage[PACK ? EW * 16 * (NT * 8 + 8) : 4];
+    __shared__ __align__(16) float pack_stage[PACK ? EW * 16 * NT * 8 : 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int64_t gw = (int64_t)blockIdx.x * EW + warp, nw = (int64_t)gridDim.x * EW;
@@ -811,21 +811,40 @@ __global__ void __launch_bounds__(EW * 32, 2) k_selfloop(const SelfArgs a) {
             }
         }
         if constexpr (PACK) {
-            constexpr int SW = NT * 8 + 8;   // staged row stride: 64-bit stores of 8 rows hit 32 distinct banks
-            float* sb = pack_stage + warp * (16 * SW);
+            // the tile's 16 rows are ONE contiguous span of `out` (16 w floats, 64-byte aligned): staged
+            // packed in shared memory and written by a single bulk copy (cp.async.bulk shared -> global)
+            float* sb = pack_stage + warp * (16 * NT * 8);
             const int w = a.nout;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile's copy has read sb
             __syncwarp();
 #pragma unroll
             for (int n = 0; n < NT; ++n) {
-                *reinterpret_cast<float2*>(sb + g * SW + 8 * n + 2 * t) = make_float2(d[n][0], d[n][1]);
-                *reinterpret_cast<float2*>(sb + (g + 8) * SW + 8 * n + 2 * t) = make_float2(d[n][2], d[n][3]);
+                const int col = 8 * n + 2 * t;
+                if (col < w) {
+                    sb[g * w + col] = d[n][0];
+                    sb[(g + 8) * w + col] = d[n][2];
+                }
+                if (col + 1 < w) {
+                    sb[g * w + col + 1] = d[n][1];
+                    sb[(g + 8) * w + col + 1] = d[n][3];
+                }
             }
-            __syncwarp();
             const int rows = (int)min((int64_t)16, a.n_own - tile * 16);
-            float* base = a.out + tile * 16 * w;   // the tile's rows are one contiguous span of `out`
-            for (int r = 0; r < rows; ++r) {
-                if (lane < w) base[r * w + lane] = sb[r * SW + lane];
-                if (lane + 32 < w) base[r * w + lane + 32] = sb[r * SW + lane + 32];
+            float* base = a.out + tile * 16 * w;
+            const int bytes = rows * w * 4;
+            if ((bytes & 15) == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(base),
+                                 "r"((uint32_t)__cvta_generic_to_shared(sb)), "r"(bytes)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else {   // a last tile whose byte count is not a multiple of 16
+                __syncwarp();
+                for (int i = lane; i < rows * w; i += 32) base[i] = sb[i];
+                __syncwarp();
             }
         } else {
         const bool odd = (t & 1) != 0;
@@ -846,6 +865,9 @@ __global__ void __launch_bounds__(EW * 32, 2) k_selfloop(const SelfArgs a) {
             }
         }
         }
+    }
+    if constexpr (PACK) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
 
