@@ -66,3 +66,34 @@ def test_brc_invariants(gr):
             sl = slice(int(b['tile_e0'][i]), int(b['tile_e0'][i]) + int(tn[i]))
             assert np.all(b['seg_rel'][seg_of_entry[sl]] == trel[i])
             assert np.array_equal(b['e_own'][sl], b['seg_own'][seg_of_entry[sl]])
+
+
+@settings(max_examples=80, deadline=None)
+@given(graphs())
+def test_shared_chunk_numbering(gr):
+    """FWD_REL (relation-major) renumbered onto FWD's chunk ids: chunk c of FWD_REL and chunk
+    chunk_out[c] of FWD are the same piece of the same (relation, dst) segment — same gathered rows
+    and weights in the same order — so a chunk-row matrix computed for one serves the other."""
+    src, dst, rel, n, r, nr, t, ch, lo, hi = gr
+    w = csr_oracle.edge_weights(dst, rel, n)
+    fwd = csr_oracle.build_brc(dst, src, rel, n, r, nr, t, ch, w_edge=w, lo=lo, hi=hi)
+    own = csr_oracle.build_brc(dst, src, rel, n, r, hi - lo, t, ch, w_edge=w, lo=lo, hi=hi)   # one range
+    shared = csr_oracle.share_chunks(fwd, own, n)
+    nc = fwd['num_chunks']
+    assert own['num_chunks'] == nc
+    if nc == 0:
+        return
+    order = shared['chunk_out']
+    assert sorted(order.tolist()) == list(range(nc))
+    for c in range(nc):
+        a0, a1 = int(own['chunk_beg'][c]), int(own['chunk_end'][c])
+        b0, b1 = int(fwd['chunk_beg'][order[c]]), int(fwd['chunk_end'][order[c]])
+        assert np.array_equal(own['raw_idx'][a0:a1], fwd['raw_idx'][b0:b1])
+        assert np.array_equal(own['raw_w'][a0:a1], fwd['raw_w'][b0:b1])
+    # the renumbered entries point at FWD ids; everything else is untouched
+    idx_old = own['e_idx'] & np.uint32(0x7fffffff)
+    idx_new = shared['e_idx'] & np.uint32(0x7fffffff)
+    is_chunk = idx_old >= n
+    assert np.array_equal(idx_new[~is_chunk], idx_old[~is_chunk])
+    assert np.array_equal(idx_new[is_chunk].astype(np.int64) - n, order[(idx_old[is_chunk] - n).astype(np.int64)])
+    assert np.array_equal(shared['e_idx'] >> 31, own['e_idx'] >> 31)
