@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RGCN_B200_ABI_VERSION 4
+#define RGCN_B200_ABI_VERSION 5
 
 typedef enum {
     RGCN_OK = 0,
@@ -73,6 +73,14 @@ enum {
 
 const char* rgcn_last_error(void);
 int rgcn_abi_version(void);
+
+/* Process-wide run-time options (no reference counterpart; the defaults are what bench.py measures).
+ * RGCN_OPT_OVERLAP: 1 = passes of one layer call that do not depend on each other (dL/dW vs the dL/dx
+ * chain, chunk pre-pass vs root pass) run concurrently on an engine-owned side stream, forked from and
+ * joined back into the caller's stream inside the call (capturable in a CUDA graph); 0 = one stream.
+ * RGCN_OPT_OVERLAP_*_CTAS: resident CTAs per SM each of the two concurrent backward passes keeps to. */
+enum { RGCN_OPT_OVERLAP = 0, RGCN_OPT_OVERLAP_WGRAD_CTAS = 1, RGCN_OPT_OVERLAP_DX_CTAS = 2 };
+int rgcn_set_option(int32_t option, int64_t value);
 
 /* K0 — replaces nothing in the reference one-to-one: PyG re-derives `edge_type == r` masks on
  * every forward; the engine sorts once.  Inputs are the tensors of

@@ -42,6 +42,47 @@ bool etile_choice(int kp, bool vec4_ok) {
     return kp <= 32 || vec4_ok;
 }
 
+// run-time options (rgcn_set_option); defaults may be overridden by the environment once
+struct Options {
+    int overlap = 1;       // independent passes of one layer call run concurrently (fork/join on the graph's side stream)
+    int wg_ctas = 1;       // resident CTAs per SM of the dL/dW pass while it shares the SMs with the dL/dx chain
+    int dx_ctas = 1;       // same for the dL/dx tile pass
+    Options() {
+        if (const char* e = getenv("RGCN_B200_OVERLAP")) overlap = atoi(e);
+        if (const char* e = getenv("RGCN_B200_OVL_WG")) wg_ctas = atoi(e);
+        if (const char* e = getenv("RGCN_B200_OVL_DX")) dx_ctas = atoi(e);
+    }
+};
+Options& opts() {
+    static Options o;
+    return o;
+}
+
+// fork: the side stream waits for everything issued so far on `st`; join: `st` waits for the side stream.
+// Both are event record + stream wait, which a CUDA-graph capture of `st` turns into graph edges.
+struct Fork {
+    const rgcn_graph* g;
+    cudaStream_t st;
+    bool open = false;
+    Fork(const rgcn_graph* g_, cudaStream_t st_) : g(g_), st(st_) {}
+    bool available() const { return opts().overlap != 0 && g->side && g->ev_fork && g->ev_join; }
+    int begin() {
+        RGCN_CUDA(cudaEventRecord(g->ev_fork, st));
+        RGCN_CUDA(cudaStreamWaitEvent(g->side, g->ev_fork, 0));
+        open = true;
+        return 0;
+    }
+    int end() {
+        if (!open) return 0;
+        open = false;
+        RGCN_CUDA(cudaEventRecord(g->ev_join, g->side));
+        RGCN_CUDA(cudaStreamWaitEvent(st, g->ev_join, 0));
+        return 0;
+    }
+};
+// (an early error return between begin() and end() leaves the side stream un-joined; every such path
+// returns a failure code and the caller raises, so no result of that call is consumed)
+
 bool direct_target(const void* p, int64_t ld, int width) {
     return ld == width && width % 4 == 0 && ((uintptr_t)p & 15) == 0;
 }
@@ -137,7 +178,11 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
     const int64_t ld_raw = ldx;
     bool fused_pad = false;
     if (x_mirror) {
-        fused_pad = !etile_vec4_ok(x, ldx, fin, aux) && selfloop_pad_ok(kp, np) && g->n_own == g->N && etile_choice(kp, true);
+        // the fused pass emits root fragments in the vector K order and replaces the self-loop pass of the
+        // entry-tile family, so it is taken only when the MIRROR will be gathered by k_etile with vector loads
+        const bool mirror_v4 = etile_vec4_ok(x_mirror, ld_mirror, fin, aux);
+        fused_pad = !etile_vec4_ok(x, ldx, fin, aux) && mirror_v4 && etile_choice(kp, mirror_v4) &&
+                    selfloop_pad_ok(kp, np) && g->n_own == g->N;
         if (!fused_pad && (rc = launch_pad_rows(x, ldx, fin, x_mirror, ld_mirror, g->N, st))) return rc;
         x = x_mirror;
         ldx = ld_mirror;
@@ -146,7 +191,6 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
     const bool et = etile_choice(kp, v4ok);
     const bool v4 = et && v4ok;
     WPrep wp{weight, root, g->R, fin, fout, kp, np, false, v4, wfrag, wfrag2};
-    if ((rc = launch_wprep(wp, st))) return rc;
     TilePass p{};
     p.brc = &g->brc[RGCN_BRC_FWD];
     p.n_nodes = g->N;
@@ -161,14 +205,34 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
     p.relu_in = relu;
     p.vec4 = v4;
     p.out_rows = g->n_own;
-    if (fused_pad) {   // writes the mirror (which the pre-pass and the edge tiles then gather) and root + bias
-        if ((rc = launch_selfloop_pad(p, x_raw, ld_raw, x_mirror, ld_mirror, g->n_own, g->R, g->num_sms, st))) return rc;
-    }
-    if ((rc = launch_chunk_prepass(p, st))) return rc;
-    if (et) {   // root + bias with plain stores (initialises the target), then the edge tiles accumulate
-        if (!fused_pad && (rc = launch_selfloop_pass(p, g->own_lo, g->n_own, g->R, g->num_sms, st))) return rc;
-        if ((rc = launch_etile_pass(p, g->num_sms, st))) return rc;
+    if (et) {
+        // the chunk pre-pass (long segments -> chunk rows) and the root pass are independent: the pre-pass
+        // runs on the side stream (reading the caller's rows when the mirror is still being written)
+        Fork fk(g, st);
+        const bool ovl = fk.available() && g->brc[RGCN_BRC_FWD].num_chunks > 0;
+        TilePass pre = p;
+        if (fused_pad) {
+            pre.feat = x_raw;
+            pre.ldf = ld_raw;
+        }
+        if (ovl) {
+            if ((rc = fk.begin())) return rc;
+            if ((rc = launch_chunk_prepass(pre, g->side))) return rc;
+        }
+        if ((rc = launch_wprep(wp, st))) return rc;
+        // root + bias with plain stores (initialises the target; the fused variant also writes the mirror)
+        if (fused_pad) rc = launch_selfloop_pad(p, x_raw, ld_raw, x_mirror, ld_mirror, g->n_own, g->R, g->num_sms, st);
+        else rc = launch_selfloop_pass(p, g->own_lo, g->n_own, g->R, g->num_sms, st);
+        if (rc) return rc;
+        if (ovl) {
+            if ((rc = fk.end())) return rc;
+        } else if ((rc = launch_chunk_prepass(p, st))) {
+            return rc;
+        }
+        if ((rc = launch_etile_pass(p, g->num_sms, st))) return rc;   // the edge tiles accumulate
     } else {
+        if ((rc = launch_wprep(wp, st))) return rc;
+        if ((rc = launch_chunk_prepass(p, st))) return rc;
         RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->n_own * tld * 4, st));
         if ((rc = launch_tile_pass(p, g->num_sms, st))) return rc;
     }
@@ -257,6 +321,15 @@ int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
     const bool direct = gx && (packed || direct_target(gx, ldgx, fin));
     float* target = gx ? (direct ? gx : ws.take<float>((int64_t)g->n_own * kp)) : nullptr;
     if (!ws.ok) return fail(RGCN_ERR_WORKSPACE, "rgcn_layer_bwd: workspace too small (see rgcn_layer_workspace_bytes)");
+    // dL/dW (+ its pre-pass) and the dL/dx chain are independent: with both requested the dL/dW pass runs
+    // on the side stream, each side keeping to its share of every SM so that they are co-resident
+    Fork fk(g, st);
+    const bool ovl = need_w && gx && fk.available();
+    cudaStream_t st_w = st;
+    if (ovl) {
+        if ((rc = fk.begin())) return rc;
+        st_w = g->side;
+    }
     if (need_w) {
         // chunk rows of x in the relation-major ordering, then dW / droot / dbias
         TilePass pre{};
@@ -265,7 +338,7 @@ int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
         pre.feat = x; pre.ldf = ldx; pre.kin = fin; pre.aux = xaux; pre.kp = kp; pre.relu_in = relu;
         // FWD_REL shares FWD's chunk numbering: the rows the forward pass kept are these rows
         if (x_chunk_rows) xaux = const_cast<float*>(x_chunk_rows);
-        else if ((rc = launch_chunk_prepass(pre, st))) return rc;
+        else if ((rc = launch_chunk_prepass(pre, st_w))) return rc;
         WGradPass p{};
         p.brc = &g->brc[RGCN_BRC_FWD_REL];
         p.n_nodes = g->N; p.self_rel = g->R;
@@ -275,7 +348,8 @@ int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
         p.kp = kp; p.np = np; p.relu_in = relu;
         const bool v4ok = kp >= 32 && etile_vec4_ok(x, ldx, fin, xaux);
         p.vec4 = v4ok;
-        if ((rc = etile_choice(kp, v4ok) ? launch_ewgrad_pass(p, g->num_sms, st) : launch_wgrad_pass(p, g->num_sms, st))) return rc;
+        p.ctas_per_sm = ovl ? opts().wg_ctas : 0;
+        if ((rc = etile_choice(kp, v4ok) ? launch_ewgrad_pass(p, g->num_sms, st_w) : launch_wgrad_pass(p, g->num_sms, st_w))) return rc;
     }
     if (gx) {
         // dx: transposed structure, gathers gout rows (width fout), B = W^T : [np x kp]
@@ -300,6 +374,7 @@ int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
         p.vec4 = v4;
         p.packed = packed && v4;
         p.out_rows = g->n_own;
+        p.ctas_per_sm = ovl ? opts().dx_ctas : 0;
         if ((rc = launch_chunk_prepass(p, st))) return rc;
         if (et) {
             if ((rc = launch_selfloop_pass(p, g->own_lo, g->n_own, g->R, g->num_sms, st))) return rc;
@@ -311,9 +386,18 @@ int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
         if (!direct && (rc = launch_copy_cols(target, tld, gx, ldgx, g->n_own, fin, st))) return rc;
         if (relu && (rc = launch_relu_mask(gx, ldgx, x_own, ldx, g->n_own, fin, st))) return rc;
     }
-    return 0;
+    return fk.end();
 }
 }  // namespace
+
+extern "C" int rgcn_set_option(int32_t option, int64_t value) {
+    switch (option) {
+        case RGCN_OPT_OVERLAP: opts().overlap = (int)value; return 0;
+        case RGCN_OPT_OVERLAP_WGRAD_CTAS: opts().wg_ctas = (int)value; return 0;
+        case RGCN_OPT_OVERLAP_DX_CTAS: opts().dx_ctas = (int)value; return 0;
+        default: return fail(RGCN_ERR_INVALID_ARG, "rgcn_set_option: unknown option");
+    }
+}
 
 extern "C" int rgcn_layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, const float* weight,
                               const float* root, const float* gout, int64_t ldg, const float* gout_gather,

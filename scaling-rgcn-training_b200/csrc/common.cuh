@@ -81,6 +81,10 @@ struct rgcn_graph {
     int num_sms = 148;
     rgcn::Brc brc[3];
     bool rel_is_fwd = false;   // FWD_REL aliases FWD (graph fits one range)
+    // fork/join plumbing for passes of one layer call that do not depend on each other (created with the
+    // graph, so nothing is allocated inside a CUDA-graph capture): a side stream and two timing-free events
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace rgcn {
@@ -108,6 +112,7 @@ struct TilePass {
     bool packed;                                    // out rows are tightly packed with an odd width (ldo == nout,
                                                     // not a multiple of 4): bulk-reduce scatter into shifted windows
     int64_t out_rows;                               // rows of `out` (packed mode: bound of the last window)
+    int ctas_per_sm = 0;                            // > 0: cap of resident CTAs per SM (pass shares the SMs with a concurrent one)
 };
 bool etile_packed_ok(const float* out, int64_t ldo, int nout, int np);
 int launch_chunk_prepass(const TilePass& p, cudaStream_t st);
@@ -138,6 +143,7 @@ struct WGradPass {
     int kp, np;
     bool relu_in;
     bool vec4;             // entry-tile kernel with 16-byte row loads
+    int ctas_per_sm = 0;   // > 0: cap of resident CTAs per SM
 };
 int launch_wgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st);
 // entry-tile variants (etile_kernels.cu): rows gathered straight into MMA fragments

@@ -1010,7 +1010,7 @@ int bulk_min_nt() {
 }
 
 template <int KT, int NT>
-int run_etile(const ETileArgs& a, bool relu, bool v4, bool packed, int num_sms, cudaStream_t st) {
+int run_etile(const ETileArgs& a, bool relu, bool v4, bool packed, int num_sms, int cap, cudaStream_t st) {
     auto launch = [&](auto kern, int bulk_bytes = 0) -> int {
         int per_sm = 1;
         const bool small_units = bulk_bytes != 0;
@@ -1019,6 +1019,7 @@ int run_etile(const ETileArgs& a, bool relu, bool v4, bool packed, int num_sms, 
         if (smem > 48 * 1024) RGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EW * 32, smem));
         per_sm = std::max(per_sm, 1);
+        if (cap > 0) per_sm = std::min(per_sm, cap);
         const int64_t units = ((int64_t)a.num_tiles + utu - 1) / utu;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + EW - 1) / EW, (int64_t)num_sms * per_sm));
         kern<<<grid, EW * 32, smem, st>>>(a);
@@ -1049,13 +1050,14 @@ int run_etile(const ETileArgs& a, bool relu, bool v4, bool packed, int num_sms, 
 }
 
 template <int KT, int NT>
-int run_ewgrad(const ETileArgs& a, bool relu, bool v4, int num_sms, cudaStream_t st) {
+int run_ewgrad(const ETileArgs& a, bool relu, bool v4, int num_sms, int cap, cudaStream_t st) {
     auto launch = [&](auto kern) -> int {
         int per_sm = 1;
         const int smem = (KT >= 4) ? MetaStage<1>::CTA_BYTES : MetaStage<0>::CTA_BYTES;
         if (smem > 48 * 1024) RGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EW * 32, smem));
         per_sm = std::max(per_sm, 1);
+        if (cap > 0) per_sm = std::min(per_sm, cap);
         const int64_t units = ((int64_t)a.num_tiles + UT - 1) / UT;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + EW - 1) / EW, (int64_t)num_sms * per_sm));
         kern<<<grid, EW * 32, smem, st>>>(a);
@@ -1144,7 +1146,7 @@ int launch_etile_pass(const TilePass& p, int num_sms, cudaStream_t st) {
     if (a.num_tiles == 0) return 0;
     ProfScope prof(p.transposed ? TAG_TILE_BWD : TAG_TILE_FWD, p.kin, p.tag_out, st);
     note_launch(1);
-    RGCN_DISPATCH_E(run_etile, p.kp, p.np, a, p.relu_in, p.vec4, p.packed, num_sms, st);
+    RGCN_DISPATCH_E(run_etile, p.kp, p.np, a, p.relu_in, p.vec4, p.packed, num_sms, p.ctas_per_sm, st);
 }
 
 // out[i] = act(x[own_lo + i]) . root + bias for every owned row (plain stores: also initialises `out`)
@@ -1219,7 +1221,7 @@ int launch_ewgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st) {
     a.gbias = p.gbias;
     ProfScope prof(TAG_WGRAD, p.kin, p.nout, st);
     note_launch(1);
-    RGCN_DISPATCH_E(run_ewgrad, p.kp, p.np, a, p.relu_in, p.vec4, num_sms, st);
+    RGCN_DISPATCH_E(run_ewgrad, p.kp, p.np, a, p.relu_in, p.vec4, num_sms, p.ctas_per_sm, st);
 }
 
 }  // namespace rgcn

@@ -357,7 +357,9 @@ __global__ void k_chunk_renumber(uint32_t* __restrict__ e_idx, int64_t E3, uint3
 
 int share_chunks(const Brc& fwd, Brc& rel, int64_t n_own, int64_t n_gat, int R, cudaStream_t st) {
     const int32_t NC = fwd.num_chunks;
-    if (NC == 0 || NC != rel.num_chunks) return 0;
+    if (NC != rel.num_chunks)   // both structures chunk the same (relation, dst) segments: a mismatch is a builder bug
+        return fail(RGCN_ERR_INVALID_ARG, "share_chunks: FWD and FWD_REL disagree on the number of chunks");
+    if (NC == 0) return 0;
     Dev<uint64_t> key, skey;
     Dev<int32_t> id, tmp_order;
     Dev<char> tmp;
@@ -530,6 +532,9 @@ extern "C" void rgcn_graph_destroy(rgcn_graph* g) {
         if (i == RGCN_BRC_FWD_REL && g->rel_is_fwd) continue;
         g->brc[i].release();
     }
+    if (g->side) cudaStreamDestroy(g->side);
+    if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+    if (g->ev_join) cudaEventDestroy(g->ev_join);
     delete g;
 }
 
@@ -629,6 +634,9 @@ extern "C" int rgcn_graph_create_part(const int64_t* src, int64_t src_stride, co
     g->n_own = own_hi - own_lo;
     cudaGetDevice(&g->device);
     cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, g->device);
+    if (cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking) != cudaSuccess) g->side = nullptr;
+    if (cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming) != cudaSuccess) g->ev_fork = nullptr;
+    if (cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming) != cudaSuccess) g->ev_join = nullptr;
     g->split_threshold = split_threshold > 0 ? split_threshold : 16;
     g->chunk_size = chunk_size > 0 ? chunk_size : 64;
     int64_t nr = range_nodes > 0 ? range_nodes : 16384;

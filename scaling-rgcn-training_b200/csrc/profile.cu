@@ -1,5 +1,6 @@
 // profile.cu — launch counting and optional per-pass CUDA-event timing (used by bench.py to time
 // the dominant kernel live, on the stream it is launched on, inside the timed region).
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -13,14 +14,15 @@ struct Rec {
 };
 std::mutex g_mu;
 std::vector<Rec> g_recs;
-bool g_enabled = false;
-int64_t g_launches = 0;
+// read on the autograd thread as well as the caller's: atomics
+std::atomic<bool> g_enabled{false};
+std::atomic<int64_t> g_launches{0};
 }  // namespace
 
-void note_launch(int n) { g_launches += n; }
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 ProfScope::ProfScope(int tag, int d0, int d1, cudaStream_t st) : st_(st), idx_(-1) {
-    if (!g_enabled) return;
+    if (!g_enabled.load(std::memory_order_relaxed)) return;
     Rec r{tag, d0, d1, nullptr, nullptr};
     if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
     cudaEventRecord(r.a, st);
@@ -35,11 +37,11 @@ ProfScope::~ProfScope() {
 }
 }  // namespace rgcn
 
-extern "C" int64_t rgcn_kernel_launch_count(void) { return rgcn::g_launches; }
+extern "C" int64_t rgcn_kernel_launch_count(void) { return rgcn::g_launches.load(); }
 
 extern "C" int rgcn_profile_enable(int32_t on) {
     std::lock_guard<std::mutex> lk(rgcn::g_mu);
-    rgcn::g_enabled = on != 0;
+    rgcn::g_enabled.store(on != 0);
     return 0;
 }
 

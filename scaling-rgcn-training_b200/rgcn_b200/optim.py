@@ -5,12 +5,24 @@ correction, no amsgrad) with the whole update of a tensor in ONE engine kernel
 (``step``, ``exp_avg``, ``exp_avg_sq``) as torch's Adam; CUDA fp32 parameters only.
 
 ``capturable=True`` keeps the step count in device memory (``rgcn_adam_step_dev``), so the whole
-training step can be captured in a CUDA graph (``rgcn_b200.trainer.GraphedTrainStep``)."""
+training step can be captured in a CUDA graph (``rgcn_b200.trainer.GraphedTrainStep``).  That counter
+is ONE per device, shared by all tensors of the optimiser: every parameter that requires a gradient
+must receive one on every step (true for the reference's models), otherwise its bias correction would
+run ahead of torch.optim.Adam's per-parameter count — ``step`` raises in that case."""
 from __future__ import annotations
 
 import torch
 
 from . import _lib
+
+
+def _bump_version(p: torch.Tensor) -> None:
+    """The kernel writes through data_ptr(): tell autograd the tensor changed in place, so a backward
+    that still holds it as a saved tensor raises instead of using the updated values."""
+    try:
+        torch.autograd.graph.increment_version(p)
+    except AttributeError:        # very old torch: fall back to a no-op in-place op
+        p.add_(0)
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -45,6 +57,10 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         lib = _lib.load()
         if self.capturable:
+            missing = [p for group in self.param_groups for p in group['params'] if p.requires_grad and p.grad is None]
+            if missing:
+                raise _lib.EngineError('FusedAdam(capturable=True): a parameter that requires grad has none on this step '
+                                       '(the device step counter is shared by all tensors)')
             devices = {p.device for group in self.param_groups for p in group['params'] if p.grad is not None}
             for d in devices:
                 self._device_step(d).add_(1)
@@ -72,6 +88,7 @@ class FusedAdam(torch.optim.Optimizer):
                                                     self._device_step(p.device).data_ptr(),
                                                     torch.cuda.current_stream(p.device).cuda_stream)
                     _lib.check(rc, 'rgcn_adam_step_dev')
+                    _bump_version(p)
                     continue
                 with torch.cuda.device(p.device):
                     rc = lib.rgcn_adam_step(p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(),
@@ -79,4 +96,5 @@ class FusedAdam(torch.optim.Optimizer):
                                             group['weight_decay'], st['step'],
                                             torch.cuda.current_stream(p.device).cuda_stream)
                 _lib.check(rc, 'rgcn_adam_step')
+                _bump_version(p)
         return loss

@@ -82,12 +82,14 @@ class GraphedTrainStep:
         snapshot = [p.detach().clone() for p in params]
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        rng = torch.cuda.get_rng_state(dev)                # dropout (attention head) must see the same stream
         with torch.cuda.stream(side):
             self._body()                                   # eager warm-up on the capture stream
             with torch.no_grad():
                 for p, s in zip(params, snapshot):
                     p.copy_(s)
             optimizer.reset_state()
+        torch.cuda.set_rng_state(rng, dev)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()

@@ -170,6 +170,84 @@ def heads_golden(seed):
                         S=np.int64(S), emb=np.int64(emb), hidden=np.int64(hidden), C=np.int64(C), **pay)
 
 
+def heads_aifb_golden(seed):
+    """Transfer heads at the shape of BASELINE config 2 (S = 3 summaries, emb 63, hidden 16): the real AIFB
+    attr summary graphs and their real map files (8243 original nodes) feed the reference's own
+    concat_embeddings / stack_embeddings; the original graph itself is absent, so its edges are
+    a seeded synthetic multigraph over the real node set with AIFB's counts (24 919 triples, 44 predicates).
+    Emb_MLP_Layers / Emb_ATT_Layers (model/layers.py:49-66, 90-112, unmodified) run forward, CE loss and
+    backward with the embedding trainable; every parameter gradient is stored (embedding gradient: every
+    16th row)."""
+    from torch_geometric.data import Data
+    tags = ('in', 'in_out', 'out')
+    sum_graphs, org_nodes = [], set()
+    for t in tags:
+        sg = load_graph(f'graphs/AIFB/attr/sum/AIFB_sum_{t}.nt')
+        sg.orgNode2sumNode_dict, sg.sumNode2orgNode_dict = get_node_mappings_dict(
+            parse_graph_nt(os.path.join(REF, f'graphs/AIFB/attr/map/AIFB_map_{t}.nt')))
+        org_nodes |= set(sg.orgNode2sumNode_dict.keys())
+        sum_graphs.append(sg)
+    org = _FakeOrg(org_nodes)
+    for k in list(sum_graphs[1].orgNode2sumNode_dict.keys())[::97]:     # some fallback rows
+        del sum_graphs[1].orgNode2sumNode_dict[k]
+    n, preds, triples = org.num_nodes, 44, 24919
+    rng = np.random.default_rng(seed)
+    s_, o_, p_ = rng.integers(0, n, triples), rng.integers(0, n, triples), rng.integers(0, preds, triples)
+    buf = np.empty((2 * triples, 3), dtype=np.int64)
+    buf[0::2] = np.stack([s_, o_, 2 * p_], 1)
+    buf[1::2] = np.stack([o_, s_, 2 * p_ + 1], 1)
+    edge = torch.from_numpy(buf).t()
+    td = Data(edge_index=edge[:2])
+    td.edge_type = edge[2]
+    R, S, emb, hidden, C = 2 * preds + 1, 3, 63, 16, 11
+    torch.manual_seed(seed)
+    for sg in sum_graphs:
+        sg.embedding = torch.randn(sg.num_nodes, emb)
+    torch.manual_seed(seed + 1)
+    e_cat = embeddingTricks.concat_embeddings(org, sum_graphs, emb)
+    torch.manual_seed(seed + 1)
+    e_stack = embeddingTricks.stack_embeddings(org, sum_graphs, emb)
+    torch.manual_seed(seed + 1)
+    fallbacks = [torch.rand(n, emb) for _ in sum_graphs]
+    from rgcn_oracle import build_map_index
+    idx = [build_map_index(org.node_to_enum, sg.node_to_enum, sg.orgNode2sumNode_dict).numpy().astype(np.int32)
+           for sg in sum_graphs]
+    torch.manual_seed(seed + 2)
+    x_train = torch.randperm(n)[:n // 2]
+    y = torch.nn.functional.one_hot(torch.randint(0, C, (n // 2,)), C).float()
+    pay = {'S': np.int64(S), 'emb': np.int64(emb), 'hidden': np.int64(hidden), 'C': np.int64(C),
+           'edge_index': edge[:2].numpy().astype(np.int32), 'edge_type': edge[2].numpy().astype(np.int32),
+           'num_nodes': np.int64(n), 'num_relations': np.int64(R), 'x_train': x_train.numpy(), 'y_train': y.numpy()}
+    for i, sg in enumerate(sum_graphs):
+        pay[f'emb{i}'] = sg.embedding.numpy()
+        pay[f'idx{i}'] = idx[i]
+        rows = np.nonzero(idx[i] < 0)[0]
+        pay[f'fb_rows{i}'] = rows.astype(np.int32)
+        pay[f'fb_vals{i}'] = fallbacks[i].numpy()[rows]
+    mlp = Emb_MLP_Layers(R, hidden, C, n, emb, S)
+    mlp.load_embedding(e_cat.clone(), freeze=False)
+    out = mlp(td, lambda t: t)
+    loss = ce_loss(out[x_train], y)
+    loss.backward()
+    pay.update({f'mlp.{k}': v.detach().numpy() for k, v in mlp.state_dict().items() if k != 'embedding.weight'})
+    pay.update({f'mlp.grad.{k}': v.grad.numpy() for k, v in mlp.named_parameters() if k != 'embedding.weight'})
+    pay['mlp.grad.embedding_rows16'] = mlp.embedding.weight.grad.numpy()[::16]
+    pay['mlp.out'], pay['mlp.loss'] = out.detach().numpy(), np.float64(loss.item())
+    att = Emb_ATT_Layers(R, hidden, C, n, emb, S)
+    att.load_embedding(e_stack.clone(), freeze=False)
+    att.eval()                                  # MHA dropout off; gradients still flow
+    out = att(td, lambda t: t)
+    loss = ce_loss(out[x_train], y)
+    loss.backward()
+    pay.update({f'att.{k}': v.detach().numpy() for k, v in att.state_dict().items() if k != 'embedding'})
+    pay.update({f'att.grad.{k}': v.grad.numpy() for k, v in att.named_parameters() if k != 'embedding'})
+    pay['att.grad.embedding_rows16'] = att.embedding.grad.numpy()[:, ::16]
+    pay['att.out'], pay['att.loss'] = out.detach().numpy(), np.float64(loss.item())
+    # spot rows of the gathered inputs, so the test's own map-gather is tied to the reference's
+    pay['e_cat_rows16'] = e_cat.numpy()[::16]
+    np.savez_compressed(os.path.join(HERE, 'heads_AIFB_attr.npz'), **pay)
+
+
 def main():
     graphs = {k: load_graph(v) for k, v in GRAPHS.items()}
     for k, g in graphs.items():
@@ -191,6 +269,7 @@ def main():
                      [f'graphs/AIFB/bisim/sum/AIFB_bisim_k{k}.nt' for k in (1, 2, 3)],
                      [f'graphs/AIFB/bisim/map/AIFB_bisim_map_k{k}.nt' for k in (1, 2, 3)], emb_dim=6, seed=13)
     heads_golden(21)
+    heads_aifb_golden(31)
     print('golden fixtures written to', HERE)
 
 
