@@ -428,6 +428,7 @@ def main():
     ap.add_argument('--ref-scale', type=float, default=1 / 32, help='bounded sample for the CPU reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='kernel-level timing only (tuning runs; not a bench line)')
+    ap.add_argument('--no-check', action='store_true', help='skip the parity leg (reduced-scale check printed in the line)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == 'reference':

@@ -52,7 +52,7 @@ enum {
     RGCN_Q_NUM_SEGMENTS = 3, RGCN_Q_NUM_ENTRIES = 4, RGCN_Q_NUM_CHUNKS = 5,
     RGCN_Q_NUM_GROUPS = 6, RGCN_Q_NUM_BATCHES = 7, RGCN_Q_RANGE_NODES = 8,
     RGCN_Q_DEVICE_BYTES = 9, RGCN_Q_NUM_OWNED = 10, RGCN_Q_OWN_LO = 11, RGCN_Q_NUM_ENTRIES0 = 12,
-    RGCN_Q_NUM_TILES = 13, RGCN_Q_NUM_TILES_NOSELF = 14
+    RGCN_Q_NUM_TILES = 13, RGCN_Q_NUM_TILES_NOSELF = 14, RGCN_Q_PUSH = 15
 };
 
 /* rgcn_graph_export array ids (element type in brackets) */
@@ -98,6 +98,20 @@ int rgcn_graph_create(const int64_t* src, int64_t src_stride,
  * GLOBAL ids, and the mean normalisers are those of the whole graph.  Layer calls then take x /
  * gout_gather with all N rows (the caller all-gathers them) and produce the owned rows only. */
 int rgcn_graph_create_part(const int64_t* src, int64_t src_stride,
+                           const int64_t* dst, int64_t dst_stride,
+                           const int64_t* etype, int64_t etype_stride,
+                           int64_t num_edges, int64_t num_nodes, int32_t num_relations,
+                           int64_t own_lo, int64_t own_hi,
+                           int32_t range_nodes, int32_t split_threshold, int32_t chunk_size,
+                           void* stream, rgcn_graph** out);
+/* Source-partitioned ("push") variant: the forward structures hold the edges whose SRC is owned, with
+ * LOCAL gathered ids (src - own_lo) and GLOBAL owner ids (dst); the transposed structure is the one of
+ * rgcn_graph_create_part.  rgcn_layer_fwd then takes x with the OWNED rows only and writes a PARTIAL output
+ * with one row per node of the whole graph (root + bias on the owned rows, zero-started elsewhere): the caller
+ * reduce-scatters the partials, so the wide layer-1 input never crosses the links.  rgcn_layer_bwd takes x with
+ * the owned rows, gout_gather with all nodes' rows (used for dL/dW as well as dL/dx; `gout` is ignored) and
+ * produces the owned rows of gx and partial parameter gradients.  Tile kernels only (widths <= 64). */
+int rgcn_graph_create_push(const int64_t* src, int64_t src_stride,
                            const int64_t* dst, int64_t dst_stride,
                            const int64_t* etype, int64_t etype_stride,
                            int64_t num_edges, int64_t num_nodes, int32_t num_relations,

@@ -34,32 +34,41 @@ def edge_weights(dst, rel, n):
     return (np.float32(1.0) / counts.astype(np.float32))[inv].astype(np.float32)
 
 
-def build_brc(own, gat, rel, n, r, nr, t, ch, w_edge=None, lo=0, hi=None):
+def build_brc(own, gat, rel, n, r, nr, t, ch, w_edge=None, lo=0, hi=None, push=False):
     """own/gat/rel: the graph's edges (global ids).  [lo,hi): owned node range (whole graph by
-    default).  Entries = edges whose owner end is owned (input order), then the owned self loops."""
+    default).  Entries = edges whose owner end is owned (input order), then the owned self loops;
+    owner ids local, gather ids global.  push=True (rgcn_graph_create_push): the edges whose GATHER
+    end is owned, gather ids local, owner ids global (owner space = the whole graph)."""
     own = np.asarray(own, dtype=np.int64)
     gat = np.asarray(gat, dtype=np.int64)
     rel = np.asarray(rel, dtype=np.int64)
     hi = n if hi is None else hi
     if w_edge is None:
         raise ValueError('w_edge required (edge_weights(dst, rel, n))')
-    sel = (own >= lo) & (own < hi)
-    n_gat = n
-    n_own = hi - lo
+    n_sel = hi - lo
+    loops = np.arange(n_sel, dtype=np.int64)
+    if push:
+        sel = (gat >= lo) & (gat < hi)
+        n_gat, n_own = n_sel, n
+        own2 = np.concatenate([own[sel], loops + lo])
+        gat2 = np.concatenate([gat[sel] - lo, loops])
+    else:
+        sel = (own >= lo) & (own < hi)
+        n_gat, n_own = n, n_sel
+        own2 = np.concatenate([own[sel] - lo, loops])
+        gat2 = np.concatenate([gat[sel], loops + lo])
     nr = int(min(max(nr, 1), max(n_own, 1)))
-    loops = np.arange(n_own, dtype=np.int64)
-    own2 = np.concatenate([own[sel] - lo, loops])
-    gat2 = np.concatenate([gat[sel], loops + lo])
-    rel2 = np.concatenate([rel[sel], np.full(n_own, r, dtype=np.int64)])
-    w_entry = np.concatenate([np.asarray(w_edge, dtype=np.float32)[sel], np.ones(n_own, dtype=np.float32)])
+    rel2 = np.concatenate([rel[sel], np.full(n_sel, r, dtype=np.int64)])
+    w_entry = np.concatenate([np.asarray(w_edge, dtype=np.float32)[sel], np.ones(n_sel, dtype=np.float32)])
     e = int(sel.sum())
+    n_self = n_sel
     n = n_own
     nranges = max((n + nr - 1) // nr, 1)
     self_base = nranges * (r + 1) * nr            # self loops (relation r) sort after every range, by owner
     key = np.where(rel2 == r, self_base + own2, (own2 // nr) * ((r + 1) * nr) + rel2 * nr + own2 % nr)
     perm = np.argsort(key, kind='stable')
     skey = key[perm]
-    e2 = e + n
+    e2 = e + n_self
     head = np.ones(e2, dtype=bool)
     head[1:] = skey[1:] != skey[:-1]
     seg_of = np.cumsum(head) - 1
@@ -166,10 +175,11 @@ def share_chunks(fwd, fwd_rel, n_gat):
     return out
 
 
-def build_graph(src, dst, rel, n, r, nr, t, ch, lo=0, hi=None):
-    """Forward (owner = dst) and transposed (owner = src) BRCs as the engine builds them."""
+def build_graph(src, dst, rel, n, r, nr, t, ch, lo=0, hi=None, push=False):
+    """Forward (owner = dst) and transposed (owner = src) BRCs as the engine builds them; push=True: the
+    source-partitioned forward structure (the transposed one is the same in both modes)."""
     w = edge_weights(dst, rel, n)
-    fwd = build_brc(dst, src, rel, n, r, nr, t, ch, w_edge=w, lo=lo, hi=hi)
+    fwd = build_brc(dst, src, rel, n, r, nr, t, ch, w_edge=w, lo=lo, hi=hi, push=push)
     bwd = build_brc(src, dst, rel, n, r, nr, t, ch, w_edge=w, lo=lo, hi=hi)
     return fwd, bwd
 

@@ -45,8 +45,9 @@ bool etile_choice(int kp, bool vec4_ok) {
 // run-time options (rgcn_set_option); defaults may be overridden by the environment once
 struct Options {
     int overlap = 1;       // independent passes of one layer call run concurrently (fork/join on the graph's side stream)
-    int wg_ctas = 1;       // resident CTAs per SM of the dL/dW pass while it shares the SMs with the dL/dx chain
-    int dx_ctas = 1;       // same for the dL/dx tile pass
+    int wg_ctas = 0;       // > 0: resident CTAs per SM of the dL/dW pass while it shares the SMs with the dL/dx chain
+    int dx_ctas = 0;       // same for the dL/dx tile pass (0 = no cap: measured best, the second pass fills the SMs
+                           // as the first drains; half-occupancy co-residency was 20 % slower on every pair)
     Options() {
         if (const char* e = getenv("RGCN_B200_OVERLAP")) overlap = atoi(e);
         if (const char* e = getenv("RGCN_B200_OVL_WG")) wg_ctas = atoi(e);
@@ -94,7 +95,7 @@ int64_t fwd_ws(const rgcn_graph* g, int fin, int fout) {
     b += ws_take((int64_t)(g->R + 1) * kp * np * 2, 4);                      // wfrag (hi,lo)
     b += ws_take((int64_t)(g->R + 1) * kp * np, 4);                          // wfrag2 (fp32 pairs)
     b += ws_take((int64_t)g->brc[RGCN_BRC_FWD].num_chunks * kp, 4);          // chunk rows
-    b += ws_take((int64_t)g->n_own * np, 4);                                 // padded accumulate target
+    b += ws_take((int64_t)g->fwd_out_rows() * np, 4);                        // padded accumulate target
     return b;
 }
 
@@ -136,12 +137,15 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
     const bool relu = (flags & RGCN_F_RELU_IN) != 0;
     const int kp = pad_dim(fin), np = pad_dim(fout);
     // tile kernels address gathered rows with 32-bit element offsets
-    const bool big = (uint64_t)g->N * (uint64_t)ldx >= (1ull << 32) ||
-                     (uint64_t)g->n_own * (uint64_t)std::max<int64_t>(ldo, np) >= (1ull << 32);
+    const int64_t n_gat = g->fwd_gather_rows(), n_out = g->fwd_out_rows();   // rows of x / rows of out
+    const bool big = (uint64_t)n_gat * (uint64_t)ldx >= (1ull << 32) ||
+                     (uint64_t)n_out * (uint64_t)std::max<int64_t>(ldo, np) >= (1ull << 32);
+    if (g->push && ((flags & RGCN_F_FORCE_SIMPLE) || !kp || !np || big))
+        return fail(RGCN_ERR_UNSUPPORTED, "rgcn_layer_fwd: a source-partitioned graph runs on the tile kernels only (widths <= 64)");
     if ((flags & RGCN_F_FORCE_SIMPLE) || !kp || !np || big) {
         // (the mirror is always written when one is given: the caller hands it to backward as x)
         if (x_mirror) {
-            int prc = launch_pad_rows(x, ldx, fin, x_mirror, ld_mirror, g->N, st);
+            int prc = launch_pad_rows(x, ldx, fin, x_mirror, ld_mirror, n_gat, st);
             if (prc) return prc;
         }
         RGCN_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)fout * 4, (size_t)g->n_own, st));
@@ -164,7 +168,7 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
     // columns then receive zeros); otherwise through a padded buffer + column copy
     const int fout4 = (fout + 3) & ~3;
     const bool direct = ldo % 4 == 0 && ldo >= fout4 && ((uintptr_t)out & 15) == 0;
-    float* target = direct ? out : ws.take<float>((int64_t)g->n_own * np);
+    float* target = direct ? out : ws.take<float>(n_out * np);
     if (!ws.ok) return fail(RGCN_ERR_WORKSPACE, "rgcn_layer_fwd: workspace too small (see rgcn_layer_workspace_bytes)");
     const int64_t tld = direct ? ldo : np;
     const int tn = direct ? fout4 : np;
@@ -183,7 +187,7 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
         const bool mirror_v4 = etile_vec4_ok(x_mirror, ld_mirror, fin, aux);
         fused_pad = !etile_vec4_ok(x, ldx, fin, aux) && mirror_v4 && etile_choice(kp, mirror_v4) &&
                     selfloop_pad_ok(kp, np) && g->n_own == g->N;
-        if (!fused_pad && (rc = launch_pad_rows(x, ldx, fin, x_mirror, ld_mirror, g->N, st))) return rc;
+        if (!fused_pad && (rc = launch_pad_rows(x, ldx, fin, x_mirror, ld_mirror, n_gat, st))) return rc;
         x = x_mirror;
         ldx = ld_mirror;
     }
@@ -193,7 +197,7 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
     WPrep wp{weight, root, g->R, fin, fout, kp, np, false, v4, wfrag, wfrag2};
     TilePass p{};
     p.brc = &g->brc[RGCN_BRC_FWD];
-    p.n_nodes = g->N;
+    p.n_nodes = n_gat;
     p.self_rel = g->R;
     p.feat = x; p.ldf = ldx; p.kin = fin;
     p.aux = aux;
@@ -204,7 +208,7 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
     p.kp = kp; p.np = np;
     p.relu_in = relu;
     p.vec4 = v4;
-    p.out_rows = g->n_own;
+    p.out_rows = n_out;
     if (et) {
         // the chunk pre-pass (long segments -> chunk rows) and the root pass are independent: the pre-pass
         // runs on the side stream (reading the caller's rows when the mirror is still being written)
@@ -221,8 +225,18 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
         }
         if ((rc = launch_wprep(wp, st))) return rc;
         // root + bias with plain stores (initialises the target; the fused variant also writes the mirror)
-        if (fused_pad) rc = launch_selfloop_pad(p, x_raw, ld_raw, x_mirror, ld_mirror, g->n_own, g->R, g->num_sms, st);
-        else rc = launch_selfloop_pass(p, g->own_lo, g->n_own, g->R, g->num_sms, st);
+        if (fused_pad) {
+            rc = launch_selfloop_pad(p, x_raw, ld_raw, x_mirror, ld_mirror, g->n_own, g->R, g->num_sms, st);
+        } else if (g->push) {
+            // x holds the owned rows, the target the rows of ALL nodes: the rows this rank does not own start
+            // from zero, the owned ones from root + bias
+            RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)n_out * tld * 4, st));
+            TilePass ps = p;
+            ps.out = target + g->own_lo * tld;
+            rc = launch_selfloop_pass(ps, 0, g->n_own, g->R, g->num_sms, st);
+        } else {
+            rc = launch_selfloop_pass(p, g->own_lo, g->n_own, g->R, g->num_sms, st);
+        }
         if (rc) return rc;
         if (ovl) {
             if ((rc = fk.end())) return rc;
@@ -233,10 +247,11 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
     } else {
         if ((rc = launch_wprep(wp, st))) return rc;
         if ((rc = launch_chunk_prepass(p, st))) return rc;
-        RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->n_own * tld * 4, st));
+        if (g->push) return fail(RGCN_ERR_UNSUPPORTED, "rgcn_layer_fwd: source-partitioned graphs need the entry-tile kernels");
+        RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)n_out * tld * 4, st));
         if ((rc = launch_tile_pass(p, g->num_sms, st))) return rc;
     }
-    if (!direct) return launch_copy_cols(target, tld, out, ldo, g->n_own, fout, st);
+    if (!direct) return launch_copy_cols(target, tld, out, ldo, n_out, fout, st);
     return 0;
 }
 }  // namespace
@@ -272,15 +287,21 @@ int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
     } else if (ldgg < fout) {
         return fail(RGCN_ERR_INVALID_ARG, "rgcn_layer_bwd: bad argument");
     }
-    const float* x_own = x + g->own_lo * ldx;   // rows of the owned nodes (ReLU mask)
+    // rows of the owned nodes (ReLU mask): x holds all rows (pull) or just the owned ones (push)
+    const float* x_own = g->push ? x : x + g->own_lo * ldx;
+    const int64_t n_gat = g->fwd_gather_rows();
+    if (g->push && gout_gather == gout && g->n_own != g->N)
+        return fail(RGCN_ERR_INVALID_ARG, "rgcn_layer_bwd: a source-partitioned graph needs gout_gather (all nodes' rows)");
     cudaStream_t st = (cudaStream_t)stream;
     const bool relu = (flags & RGCN_F_RELU_IN) != 0;
     const int kp = pad_dim(fin), np = pad_dim(fout);
-    const bool big = (uint64_t)g->N * (uint64_t)ldx >= (1ull << 32) ||
+    const bool big = (uint64_t)n_gat * (uint64_t)ldx >= (1ull << 32) ||
                      (uint64_t)g->N * (uint64_t)(gout_gather ? ldgg : ldg) >= (1ull << 32) ||
                      (uint64_t)g->n_own * (uint64_t)std::max<int64_t>(ldgx, kp) >= (1ull << 32);
     const bool simple = (flags & RGCN_F_FORCE_SIMPLE) || !kp || !np || big;
     const bool need_w = gweight || groot || gbias;
+    if (g->push && simple)
+        return fail(RGCN_ERR_UNSUPPORTED, "rgcn_layer_bwd: a source-partitioned graph runs on the tile kernels only (widths <= 64)");
     int rc;
     if (gweight) RGCN_CUDA(cudaMemsetAsync(gweight, 0, (size_t)g->R * fin * fout * 4, st));
     if (groot) RGCN_CUDA(cudaMemsetAsync(groot, 0, (size_t)fin * fout * 4, st));
@@ -334,16 +355,19 @@ int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
         // chunk rows of x in the relation-major ordering, then dW / droot / dbias
         TilePass pre{};
         pre.brc = &g->brc[RGCN_BRC_FWD_REL];
-        pre.n_nodes = g->N;
+        pre.n_nodes = n_gat;
         pre.feat = x; pre.ldf = ldx; pre.kin = fin; pre.aux = xaux; pre.kp = kp; pre.relu_in = relu;
         // FWD_REL shares FWD's chunk numbering: the rows the forward pass kept are these rows
         if (x_chunk_rows) xaux = const_cast<float*>(x_chunk_rows);
         else if ((rc = launch_chunk_prepass(pre, st_w))) return rc;
         WGradPass p{};
         p.brc = &g->brc[RGCN_BRC_FWD_REL];
-        p.n_nodes = g->N; p.self_rel = g->R;
+        p.n_nodes = n_gat; p.self_rel = g->R;
         p.feat = x; p.ldf = ldx; p.kin = fin; p.aux = xaux;
-        p.gout = gout; p.ldg = ldg; p.nout = fout;
+        // gout rows are addressed by OWNER id: local (pull) or global (push: the all-gathered rows)
+        p.gout = g->push ? gout_gather : gout;
+        p.ldg = g->push ? ldgg : ldg;
+        p.nout = fout;
         p.gweight = gweight; p.groot = groot; p.gbias = gbias;
         p.kp = kp; p.np = np; p.relu_in = relu;
         const bool v4ok = kp >= 32 && etile_vec4_ok(x, ldx, fin, xaux);

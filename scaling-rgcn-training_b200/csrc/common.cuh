@@ -81,6 +81,10 @@ struct rgcn_graph {
     int num_sms = 148;
     rgcn::Brc brc[3];
     bool rel_is_fwd = false;   // FWD_REL aliases FWD (graph fits one range)
+    bool push = false;         // source-partitioned forward structures (rgcn_graph_create_push)
+    // forward structures: rows of x that are gathered / rows of out that are written
+    int64_t fwd_gather_rows() const { return push ? n_own : N; }
+    int64_t fwd_out_rows() const { return push ? N : n_own; }
     // fork/join plumbing for passes of one layer call that do not depend on each other (created with the
     // graph, so nothing is allocated inside a CUDA-graph capture): a side stream and two timing-free events
     cudaStream_t side = nullptr;

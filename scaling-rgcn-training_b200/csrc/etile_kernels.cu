@@ -145,17 +145,69 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
                  : "memory");
 }
 
-template <int KT, int NT, bool RELU, bool V4, int BULK = 0>
+// STAGE (16-column gathered rows that are 16-byte addressable): the ROWS go through shared memory too.
+// Each warp keeps a ring of RowStage::D tile slots (16 rows x 64 B) filled by 16-byte cp.async (zero-fill
+// form for the unused rows / columns) RowStage::D tiles ahead of the tensor-pipe work, so the bytes in
+// flight per warp no longer sit in registers: D KB instead of 1 KB per warp.  The index streams of a unit
+// arrive by the bulk-copy engine (cp.async.bulk + mbarrier, SASS UBLKCP), two units ahead, in three
+// buffers — the row prefetch runs across unit boundaries and needs the next unit's indices early.
+struct RowStage {
+    static constexpr int D = 4;                       // tile slots per warp
+    static constexpr int NB = 3;                      // metadata buffers per warp
+    static constexpr int SLOT_WORDS = 16 * 16;        // 16 rows x 16 floats
+    static constexpr int BAR_WORDS = EW * NB * 2;     // one 8-byte mbarrier per buffer per warp
+    static constexpr int META_WORDS = EW * NB * MetaStage<1>::MW;
+    static constexpr int ROW_WORDS = EW * D * SLOT_WORDS;
+    static constexpr int CTA_BYTES = (BAR_WORDS + META_WORDS + ROW_WORDS) * 4;
+};
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+template <int KT, int NT, bool RELU, bool V4, int BULK = 0, int STAGE = 0>
 __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(const ETileArgs a) {
     constexpr int KP = KT * 8;
-    using MS = MetaStage<BULK>;
+    static_assert(STAGE == 0 || (KT == 2 && V4), "row staging is built for 16-column vector-addressable rows");
+    using MS = MetaStage<(BULK != 0 || STAGE != 0) ? 1 : 0>;
     constexpr int UTU = MS::UTU, SPAN = MS::SPAN, MW = MS::MW;
     extern __shared__ __align__(16) uint32_t dyn_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int gw = blockIdx.x * EW + warp, nw = gridDim.x * EW;
-    uint32_t* meta = dyn_smem + warp * MS::WARP_WORDS;
-    [[maybe_unused]] float* bulk_smem = reinterpret_cast<float*>(dyn_smem + EW * MS::WARP_WORDS);
+    uint32_t* meta = dyn_smem + (STAGE ? RowStage::BAR_WORDS + warp * (RowStage::NB * MW) : warp * MS::WARP_WORDS);
+    [[maybe_unused]] float* bulk_smem =
+        reinterpret_cast<float*>(dyn_smem + (STAGE ? RowStage::CTA_BYTES / 4 : EW * MS::WARP_WORDS));
     const uint64_t pol_f =
         (uint64_t)a.n_rows * (uint64_t)a.ldf * 4ull <= (112ull << 20) ? policy_evict_last() : policy_evict_normal();
     constexpr bool BREG = (KT * NT <= 4);
@@ -254,13 +306,268 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
     };
 
     if (gw >= num_units) return;
+    [[maybe_unused]] int bulk_par = 0;
+    auto process = [&](const TileRef& cur, const float (&av)[KT][4]) {
+        const int rel = cur.rel;
+        const RowRef cg = cur.g8, ch = cur.h8;
+        const float4* wf = a.wfrag + (int64_t)rel * (KT * NT * 32) + lane;
+        const float2* wf2 = a.wfrag2 + (int64_t)rel * (KT * NT * 32) + lane;
+        if constexpr (BREG) {   // few fragments: keep the current relation's in registers
+            if (rel != breg_rel) {
+#pragma unroll
+                for (int q = 0; q < KT * NT; ++q) bfrag[q] = __ldg(wf + q * 32);
+                breg_rel = rel;
+            }
+        }
+        if constexpr (BREG2) {
+            if (rel != breg_rel) {
+#pragma unroll
+                for (int q = 0; q < KT * NT; ++q) bfrag2[q] = __ldg(wf2 + q * 32);
+                breg_rel = rel;
+            }
+        }
+        float d[NT][4];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) d[n][0] = d[n][1] = d[n][2] = d[n][3] = 0.f;
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+            float x0 = av[kt][0], x1 = av[kt][1], x2 = av[kt][2], x3 = av[kt][3];
+            if (RELU) {
+                if (cg.real) {
+                    x0 = fmaxf(x0, 0.f);
+                    x2 = fmaxf(x2, 0.f);
+                }
+                if (ch.real) {
+                    x1 = fmaxf(x1, 0.f);
+                    x3 = fmaxf(x3, 0.f);
+                }
+            }
+            uint32_t ah[4], al[4];
+            split_fast(x0 * cg.w, ah[0], al[0]);
+            split_fast(x1 * ch.w, ah[1], al[1]);
+            split_fast(x2 * cg.w, ah[2], al[2]);
+            split_fast(x3 * ch.w, ah[3], al[3]);
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                uint32_t bh0, bh1, bl0, bl1;
+                if constexpr (BREG) {
+                    const float4 bf = bfrag[kt * NT + n];
+                    bh0 = __float_as_uint(bf.x), bh1 = __float_as_uint(bf.y);
+                    bl0 = __float_as_uint(bf.z), bl1 = __float_as_uint(bf.w);
+                } else {   // fp32 pairs from L1 (half the bytes of the pre-split form), split here
+                    const float2 b2 = BREG2 ? bfrag2[kt * NT + n] : __ldg(wf2 + (kt * NT + n) * 32);
+                    split_rn(b2.x, bh0, bl0);
+                    split_rn(b2.y, bh1, bl1);
+                }
+                mma_tf32(d[n], al[0], al[1], al[2], al[3], bh0, bh1);
+                mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+                mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+            }
+        }
+        if constexpr (BULK != 0) {
+            using BT = BulkTile<NT>;
+            float* bt = bulk_smem + warp * BT::WARP_WORDS + bulk_par * (16 * BT::ROWW);
+            // the bulk reads of this buffer must be over before it is rewritten
+            if constexpr (BT::NBUF == 2) {
+                bulk_par ^= 1;
+                if (lane < 16) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            } else {
+                if (lane < 16) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            __syncwarp();
+            if constexpr (BULK == 2) {
+                const int fg = cg.own >= 0 ? (int)(((int64_t)cg.own * a.ldo) & 3) : 0;
+                const int fh = ch.own >= 0 ? (int)(((int64_t)ch.own * a.ldo) & 3) : 0;
+                float* rg = bt + g * BT::ROWW;
+                float* rh = bt + (g + 8) * BT::ROWW;
+                rg[t < fg ? t : NT * 8 + t] = 0.f;   // the 4 window cells outside [f, f + 8 NT)
+                rh[t < fh ? t : NT * 8 + t] = 0.f;
+                rg += fg + 2 * t;
+                rh += fh + 2 * t;
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    rg[8 * n] = d[n][0];
+                    rg[8 * n + 1] = d[n][1];
+                    rh[8 * n] = d[n][2];
+                    rh[8 * n + 1] = d[n][3];
+                }
+            } else {
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    *reinterpret_cast<float2*>(bt + g * BT::ROWW + 8 * n + 2 * t) = make_float2(d[n][0], d[n][1]);
+                    *reinterpret_cast<float2*>(bt + (g + 8) * BT::ROWW + 8 * n + 2 * t) = make_float2(d[n][2], d[n][3]);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            const int o1 = __shfl_sync(FULL, cg.own, (lane & 7) * 4);
+            const int o2 = __shfl_sync(FULL, ch.own, (lane & 7) * 4);
+            const int own = lane < 8 ? o1 : o2;
+            if (lane < 16) {
+                if (own >= 0) {
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(bt + lane * BT::ROWW);
+                    if constexpr (BULK == 2) {
+                        const int64_t off = (int64_t)own * a.ldo, w0 = off & ~(int64_t)3;
+                        if (w0 + NT * 8 + 4 <= a.out_elems) {
+                            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                         ::"l"(a.out + w0), "r"(src), "n"(NT * 32 + 16) : "memory");
+                        } else {   // the window of the very last rows would pass the end of the buffer
+                            const float* srow = bt + lane * BT::ROWW + (int)(off & 3);
+                            for (int c = 0; c < a.nout; ++c) atomicAdd(a.out + off + c, srow[c]);
+                        }
+                    } else {
+                        float* dst = a.out + (int64_t)own * a.ldo;
+                        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                     ::"l"(dst), "r"(src), "n"(NT * 32) : "memory");
+                    }
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            // lanes t, t^1 swap halves so that each holds 4 consecutive columns of one n-tile pair
+            const bool odd = (t & 1) != 0;
+            const uint32_t ldo = (uint32_t)a.ldo;
+#pragma unroll
+            for (int j = 0; j < NT / 2; ++j) {
+                const int col = 16 * j + (odd ? 6 : 0) + 2 * t;   // odd: 8(2j+1) + 2(t-1)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {   // h = 0: entry g ; h = 1: entry g + 8
+                    const float p0 = d[2 * j][2 * h], p1 = d[2 * j][2 * h + 1];
+                    const float q0 = d[2 * j + 1][2 * h], q1 = d[2 * j + 1][2 * h + 1];
+                    const float rx = __shfl_xor_sync(FULL, odd ? p0 : q0, 1);
+                    const float ry = __shfl_xor_sync(FULL, odd ? p1 : q1, 1);
+                    const int own = h ? ch.own : cg.own;
+                    if (own >= 0 && col < a.nout)   // row offsets fit 32 bits (checked by the caller)
+                        red_add_v4(a.out + ((uint32_t)own * ldo + (uint32_t)col), odd ? rx : p0, odd ? ry : p1,
+                                   odd ? q0 : rx, odd ? q1 : ry);
+                }
+            }
+        }
+    };
+
+    if constexpr (STAGE != 0) {
+        constexpr int D = RowStage::D, NB = RowStage::NB;
+        uint64_t* bars = reinterpret_cast<uint64_t*>(dyn_smem) + warp * NB;
+        float* rows = reinterpret_cast<float*>(dyn_smem + RowStage::BAR_WORDS + RowStage::META_WORDS) + warp * (D * RowStage::SLOT_WORDS);
+        if (lane == 0) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) mbar_init(bars + b, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        const int ns = (num_units - gw + nw - 1) / nw;   // units of this warp: gw + s * nw, s < ns
+        // lane 0: index streams of unit s -> buffer s % NB (bulk copies, completion counted on the buffer's mbarrier)
+        // (the entry span of the unit staged NEXT is read one staging step ahead, so its latency is hidden)
+        int sp_first = 0, sp_end = 0;
+        unit_span(gw, sp_first, sp_end);
+        auto stage_meta = [&](int s_) {
+            const int first = sp_first, end = sp_end;
+            if (s_ + 1 < ns) unit_span(gw + (s_ + 1) * nw, sp_first, sp_end);
+            if (lane == 0) {
+                const int u = gw + s_ * nw;
+                const int eb = first & ~3;
+                const uint32_t bytes = (uint32_t)((end - eb + 3) >> 2) * 16u;
+                uint32_t* m = meta + (s_ % NB) * MW;
+                uint64_t* bar = bars + (s_ % NB);
+                mbar_expect_tx(bar, 3u * bytes + 2u * UTU * 4u);
+                bulk_g2s(m, a.e_idx + eb, bytes, bar);
+                bulk_g2s(m + SPAN, a.e_w + eb, bytes, bar);
+                bulk_g2s(m + 2 * SPAN, a.e_own + eb, bytes, bar);
+                bulk_g2s(m + 3 * SPAN, a.tile_e0 + u * UTU, UTU * 4, bar);
+                bulk_g2s(m + 3 * SPAN + UTU, a.tile_info + u * UTU, UTU * 4, bar);
+            }
+        };
+        struct Cursor {   // position in this warp's tile stream
+            int s, i, nt, eb;
+            const uint32_t* m;
+        };
+        auto enter = [&](Cursor& c) {   // the unit's index streams have landed (idempotent per phase)
+            if (c.s >= ns) return;
+            mbar_wait(bars + (c.s % NB), (uint32_t)((c.s / NB) & 1));
+            c.m = meta + (c.s % NB) * MW;
+            c.eb = (int)c.m[3 * SPAN] & ~3;
+            const int u = gw + c.s * nw;
+            c.nt = min(a.num_tiles, u * UTU + UTU) - u * UTU;
+            c.i = 0;
+        };
+        auto issue_rows = [&](const Cursor& c, int slot) {
+            const int e0 = (int)c.m[3 * SPAN + c.i], cnt = (int)c.m[3 * SPAN + UTU + c.i] & 0xff;
+            float* dst = rows + slot * RowStage::SLOT_WORDS + 4 * lane;   // row (lane >> 2) + 8 k, quad (lane & 3)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int r = 8 * k + g;
+                const bool valid = r < cnt && 4 * t < kin;
+                const uint32_t idx = valid ? (c.m[e0 - c.eb + r] & IDX_MASK) : 0u;
+                const bool real = idx < n_rows;
+                const float* src = (real ? feat_t : aux_t) + (real ? idx * ldf : (idx - n_rows) * (uint32_t)KP);
+                cp_async16_zfill(dst + k * 128, src, valid ? 16 : 0);
+            }
+        };
+        stage_meta(0);
+        if (ns > 1) stage_meta(1);
+        if (ns > 2) stage_meta(2);
+        Cursor cc{0, 0, 0, 0, nullptr}, ic;
+        enter(cc);
+        ic = cc;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            if (ic.s < ns) {
+                issue_rows(ic, d);
+                if (++ic.i == ic.nt) {
+                    ++ic.s;
+                    enter(ic);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int k = 0; cc.s < ns; ++k) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+            __syncwarp();
+            const int slot = k % D;
+            TileRef cur;
+            {
+                const int e0 = (int)cc.m[3 * SPAN + cc.i], info = (int)cc.m[3 * SPAN + UTU + cc.i];
+                cur.rel = info >> 8;
+                const int o = e0 - cc.eb + g, cnt = info & 0xff;
+                cur.g8 = make_row(cc.m, o, g < cnt);
+                cur.h8 = make_row(cc.m, o + 8, g + 8 < cnt);
+            }
+            float av[KT][4];
+            {
+                const float4 vg = *reinterpret_cast<const float4*>(rows + slot * RowStage::SLOT_WORDS + g * 16 + 4 * t);
+                const float4 vh = *reinterpret_cast<const float4*>(rows + slot * RowStage::SLOT_WORDS + (g + 8) * 16 + 4 * t);
+                av[0][0] = vg.x, av[0][2] = vg.y, av[1][0] = vg.z, av[1][2] = vg.w;
+                av[0][1] = vh.x, av[0][3] = vh.y, av[1][1] = vh.z, av[1][3] = vh.w;
+            }
+            __syncwarp();   // every lane has read the slot before it is refilled
+            if (ic.s < ns) {
+                issue_rows(ic, slot);
+                if (++ic.i == ic.nt) {
+                    ++ic.s;
+                    enter(ic);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            process(cur, av);
+            if (++cc.i == cc.nt) {   // unit done: its buffer takes the unit NB - 1 ahead of the next one
+                ++cc.s;
+                __syncwarp();
+                if (cc.s + NB - 1 < ns) stage_meta(cc.s + NB - 1);
+                enter(cc);
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if constexpr (BULK != 0) {
+            if (lane < 16) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        return;
+    }
     int cur_first, cur_end, nxt_first = 0, nxt_end = 0;
     unit_span(gw, cur_first, cur_end);
     stage_unit(gw, cur_first, cur_end, meta);
     asm volatile("cp.async.commit_group;" ::: "memory");
     if (gw + nw < num_units) unit_span(gw + nw, nxt_first, nxt_end);
     int buf = 0;
-    [[maybe_unused]] int bulk_par = 0;
     for (int unit = gw; unit < num_units; unit += nw, buf ^= 1) {
         const uint32_t* m = meta + buf * MW;
         const int eb = cur_first & ~3;
@@ -274,143 +581,6 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 16) ? 2 : 3) k_etile(cons
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
 
-        auto process = [&](const TileRef& cur, const float (&av)[KT][4]) {
-            const int rel = cur.rel;
-            const RowRef cg = cur.g8, ch = cur.h8;
-            const float4* wf = a.wfrag + (int64_t)rel * (KT * NT * 32) + lane;
-            const float2* wf2 = a.wfrag2 + (int64_t)rel * (KT * NT * 32) + lane;
-            if constexpr (BREG) {   // few fragments: keep the current relation's in registers
-                if (rel != breg_rel) {
-#pragma unroll
-                    for (int q = 0; q < KT * NT; ++q) bfrag[q] = __ldg(wf + q * 32);
-                    breg_rel = rel;
-                }
-            }
-            if constexpr (BREG2) {
-                if (rel != breg_rel) {
-#pragma unroll
-                    for (int q = 0; q < KT * NT; ++q) bfrag2[q] = __ldg(wf2 + q * 32);
-                    breg_rel = rel;
-                }
-            }
-            float d[NT][4];
-#pragma unroll
-            for (int n = 0; n < NT; ++n) d[n][0] = d[n][1] = d[n][2] = d[n][3] = 0.f;
-#pragma unroll
-            for (int kt = 0; kt < KT; ++kt) {
-                float x0 = av[kt][0], x1 = av[kt][1], x2 = av[kt][2], x3 = av[kt][3];
-                if (RELU) {
-                    if (cg.real) {
-                        x0 = fmaxf(x0, 0.f);
-                        x2 = fmaxf(x2, 0.f);
-                    }
-                    if (ch.real) {
-                        x1 = fmaxf(x1, 0.f);
-                        x3 = fmaxf(x3, 0.f);
-                    }
-                }
-                uint32_t ah[4], al[4];
-                split_fast(x0 * cg.w, ah[0], al[0]);
-                split_fast(x1 * ch.w, ah[1], al[1]);
-                split_fast(x2 * cg.w, ah[2], al[2]);
-                split_fast(x3 * ch.w, ah[3], al[3]);
-#pragma unroll
-                for (int n = 0; n < NT; ++n) {
-                    uint32_t bh0, bh1, bl0, bl1;
-                    if constexpr (BREG) {
-                        const float4 bf = bfrag[kt * NT + n];
-                        bh0 = __float_as_uint(bf.x), bh1 = __float_as_uint(bf.y);
-                        bl0 = __float_as_uint(bf.z), bl1 = __float_as_uint(bf.w);
-                    } else {   // fp32 pairs from L1 (half the bytes of the pre-split form), split here
-                        const float2 b2 = BREG2 ? bfrag2[kt * NT + n] : __ldg(wf2 + (kt * NT + n) * 32);
-                        split_rn(b2.x, bh0, bl0);
-                        split_rn(b2.y, bh1, bl1);
-                    }
-                    mma_tf32(d[n], al[0], al[1], al[2], al[3], bh0, bh1);
-                    mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
-                    mma_tf32(d[n], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
-                }
-            }
-            if constexpr (BULK != 0) {
-                using BT = BulkTile<NT>;
-                float* bt = bulk_smem + warp * BT::WARP_WORDS + bulk_par * (16 * BT::ROWW);
-                // the bulk reads of this buffer must be over before it is rewritten
-                if constexpr (BT::NBUF == 2) {
-                    bulk_par ^= 1;
-                    if (lane < 16) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                } else {
-                    if (lane < 16) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                }
-                __syncwarp();
-                if constexpr (BULK == 2) {
-                    const int fg = cg.own >= 0 ? (int)(((int64_t)cg.own * a.ldo) & 3) : 0;
-                    const int fh = ch.own >= 0 ? (int)(((int64_t)ch.own * a.ldo) & 3) : 0;
-                    float* rg = bt + g * BT::ROWW;
-                    float* rh = bt + (g + 8) * BT::ROWW;
-                    rg[t < fg ? t : NT * 8 + t] = 0.f;   // the 4 window cells outside [f, f + 8 NT)
-                    rh[t < fh ? t : NT * 8 + t] = 0.f;
-                    rg += fg + 2 * t;
-                    rh += fh + 2 * t;
-#pragma unroll
-                    for (int n = 0; n < NT; ++n) {
-                        rg[8 * n] = d[n][0];
-                        rg[8 * n + 1] = d[n][1];
-                        rh[8 * n] = d[n][2];
-                        rh[8 * n + 1] = d[n][3];
-                    }
-                } else {
-#pragma unroll
-                    for (int n = 0; n < NT; ++n) {
-                        *reinterpret_cast<float2*>(bt + g * BT::ROWW + 8 * n + 2 * t) = make_float2(d[n][0], d[n][1]);
-                        *reinterpret_cast<float2*>(bt + (g + 8) * BT::ROWW + 8 * n + 2 * t) = make_float2(d[n][2], d[n][3]);
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                const int o1 = __shfl_sync(FULL, cg.own, (lane & 7) * 4);
-                const int o2 = __shfl_sync(FULL, ch.own, (lane & 7) * 4);
-                const int own = lane < 8 ? o1 : o2;
-                if (lane < 16) {
-                    if (own >= 0) {
-                        const uint32_t src = (uint32_t)__cvta_generic_to_shared(bt + lane * BT::ROWW);
-                        if constexpr (BULK == 2) {
-                            const int64_t off = (int64_t)own * a.ldo, w0 = off & ~(int64_t)3;
-                            if (w0 + NT * 8 + 4 <= a.out_elems) {
-                                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
-                                             ::"l"(a.out + w0), "r"(src), "n"(NT * 32 + 16) : "memory");
-                            } else {   // the window of the very last rows would pass the end of the buffer
-                                const float* srow = bt + lane * BT::ROWW + (int)(off & 3);
-                                for (int c = 0; c < a.nout; ++c) atomicAdd(a.out + off + c, srow[c]);
-                            }
-                        } else {
-                            float* dst = a.out + (int64_t)own * a.ldo;
-                            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
-                                         ::"l"(dst), "r"(src), "n"(NT * 32) : "memory");
-                        }
-                    }
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-            } else {
-                // lanes t, t^1 swap halves so that each holds 4 consecutive columns of one n-tile pair
-                const bool odd = (t & 1) != 0;
-                const uint32_t ldo = (uint32_t)a.ldo;
-#pragma unroll
-                for (int j = 0; j < NT / 2; ++j) {
-                    const int col = 16 * j + (odd ? 6 : 0) + 2 * t;   // odd: 8(2j+1) + 2(t-1)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {   // h = 0: entry g ; h = 1: entry g + 8
-                        const float p0 = d[2 * j][2 * h], p1 = d[2 * j][2 * h + 1];
-                        const float q0 = d[2 * j + 1][2 * h], q1 = d[2 * j + 1][2 * h + 1];
-                        const float rx = __shfl_xor_sync(FULL, odd ? p0 : q0, 1);
-                        const float ry = __shfl_xor_sync(FULL, odd ? p1 : q1, 1);
-                        const int own = h ? ch.own : cg.own;
-                        if (own >= 0 && col < a.nout)   // row offsets fit 32 bits (checked by the caller)
-                            red_add_v4(a.out + ((uint32_t)own * ldo + (uint32_t)col), odd ? rx : p0, odd ? ry : p1,
-                                       odd ? q0 : rx, odd ? q1 : ry);
-                    }
-                }
-            }
-        };
         // rows one tile ahead of the tensor-pipe work; two tiles per trip with swapped roles, so the
         // pipeline registers are never copied
         TileRef rA = tile_ref(m, 0, eb), rB = rA;
@@ -1009,12 +1179,22 @@ int bulk_min_nt() {
     return v;
 }
 
+// RGCN_B200_STAGE=0 keeps the gathered rows of the 16-column kernels in registers (round-1 path)
+bool row_stage_on() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RGCN_B200_STAGE");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 template <int KT, int NT>
 int run_etile(const ETileArgs& a, bool relu, bool v4, bool packed, int num_sms, int cap, cudaStream_t st) {
-    auto launch = [&](auto kern, int bulk_bytes = 0) -> int {
+    auto launch = [&](auto kern, int bulk_bytes = 0, bool staged = false) -> int {
         int per_sm = 1;
-        const bool small_units = bulk_bytes != 0;
-        const int smem = (small_units ? MetaStage<1>::CTA_BYTES : MetaStage<0>::CTA_BYTES) + bulk_bytes;
+        const bool small_units = bulk_bytes != 0 || staged;
+        const int smem = (staged ? RowStage::CTA_BYTES : small_units ? MetaStage<1>::CTA_BYTES : MetaStage<0>::CTA_BYTES) + bulk_bytes;
         const int utu = small_units ? MetaStage<1>::UTU : MetaStage<0>::UTU;
         if (smem > 48 * 1024) RGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EW * 32, smem));
@@ -1027,9 +1207,17 @@ int run_etile(const ETileArgs& a, bool relu, bool v4, bool packed, int num_sms, 
         return 0;
     };
     // bulk scatter: whole padded rows (8 NT floats) are added, so the target row must hold them
+    // 16-column vector-addressable rows: rows staged in shared memory, RowStage::D tiles ahead
+    [[maybe_unused]] const bool staged = KT == 2 && v4 && row_stage_on();
     if constexpr (NT == 8) {
         if (packed) {
             if (!v4) return fail(RGCN_ERR_UNSUPPORTED, "packed scatter needs 16-byte addressable gathered rows");
+            if constexpr (KT == 2) {
+                if (staged) {
+                    if (relu) return launch(k_etile<KT, NT, true, true, 2, 1>, BulkTile<NT>::CTA_BYTES, true);
+                    return launch(k_etile<KT, NT, false, true, 2, 1>, BulkTile<NT>::CTA_BYTES, true);
+                }
+            }
             if (relu) return launch(k_etile<KT, NT, true, true, 2>, BulkTile<NT>::CTA_BYTES);
             return launch(k_etile<KT, NT, false, true, 2>, BulkTile<NT>::CTA_BYTES);
         }
@@ -1038,10 +1226,22 @@ int run_etile(const ETileArgs& a, bool relu, bool v4, bool packed, int num_sms, 
     const bool bulk = v4 && bulk_min_nt() > 0 && NT >= bulk_min_nt() && a.ldo >= 8 * NT && a.ldo % 4 == 0 &&
                       ((uintptr_t)a.out & 15) == 0;
     if (bulk) {
+        if constexpr (KT == 2) {
+            if (staged) {
+                if (relu) return launch(k_etile<KT, NT, true, true, 1, 1>, BulkTile<NT>::CTA_BYTES, true);
+                return launch(k_etile<KT, NT, false, true, 1, 1>, BulkTile<NT>::CTA_BYTES, true);
+            }
+        }
         if (relu) return launch(k_etile<KT, NT, true, true, 1>, BulkTile<NT>::CTA_BYTES);
         return launch(k_etile<KT, NT, false, true, 1>, BulkTile<NT>::CTA_BYTES);
     }
     if (v4) {
+        if constexpr (KT == 2) {
+            if (staged) {
+                if (relu) return launch(k_etile<KT, NT, true, true, 0, 1>, 0, true);
+                return launch(k_etile<KT, NT, false, true, 0, 1>, 0, true);
+            }
+        }
         if (relu) return launch(k_etile<KT, NT, true, true>);
         return launch(k_etile<KT, NT, false, true>);
     }

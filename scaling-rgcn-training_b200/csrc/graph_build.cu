@@ -103,22 +103,24 @@ __global__ void k_flag_owned(const int32_t* __restrict__ own_g, int64_t E, int32
 __global__ void k_fill_entries(const int32_t* __restrict__ own_g, const int32_t* __restrict__ gat_g,
                                const int32_t* __restrict__ rel_g, const float* __restrict__ w_edge,
                                const int32_t* __restrict__ flag, const int32_t* __restrict__ pos, int64_t E, int64_t nsel,
-                               int32_t lo, int32_t hi, int R, int32_t* __restrict__ own, int32_t* __restrict__ gat,
-                               int32_t* __restrict__ rel, float* __restrict__ w) {
+                               int32_t lo, int32_t hi, int R, int push, int32_t* __restrict__ own,
+                               int32_t* __restrict__ gat, int32_t* __restrict__ rel, float* __restrict__ w) {
+    // pull (push == 0): the OWNER end is in [lo, hi) -> owner ids local, gather ids global
+    // push            : the GATHER end is in [lo, hi) -> gather ids local, owner ids global
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < E) {
         if (flag[i]) {
             int32_t o = pos[i];
-            own[o] = own_g[i] - lo;
-            gat[o] = gat_g[i];
+            own[o] = push ? own_g[i] : own_g[i] - lo;
+            gat[o] = push ? gat_g[i] - lo : gat_g[i];
             rel[o] = rel_g[i];
             w[o] = w_edge[i];
         }
     } else if (i < E + (hi - lo)) {
         int32_t v = (int32_t)(i - E);
         int64_t o = nsel + v;
-        own[o] = v;
-        gat[o] = lo + v;
+        own[o] = push ? lo + v : v;
+        gat[o] = push ? v : lo + v;
         rel[o] = R;
         w[o] = 1.0f;
     }
@@ -573,9 +575,11 @@ int compute_edge_weights(const int32_t* dst32, const int32_t* rel32, int64_t E, 
 
 // Entry list (owner-local, gather-global, rel, weight) of the edges whose owner end is in [lo,hi),
 // in input order, followed by the self loops of the owned nodes; then the BRC(s) over it.
+// push: select on the GATHER end instead (source-partitioned forward structures: gathered rows are the
+// rank's own, owner rows span the whole graph; num_all = nodes of the whole graph).
 int build_side(const int32_t* own_g, const int32_t* gat_g, const int32_t* rel_g, const float* w_edge, int64_t E,
-               int64_t n_gat, int R, int64_t lo, int64_t hi, int NR, int T, int CH, cudaStream_t st, Brc* blocked,
-               Brc* relmajor) {
+               int64_t num_all, int R, int64_t lo, int64_t hi, int NR, int T, int CH, cudaStream_t st, Brc* blocked,
+               Brc* relmajor, bool push = false) {
     Dev<int32_t> flag, pos, own, gat, rel;
     Dev<float> w;
     RGCN_CUDA(flag.alloc(E + 1));
@@ -583,18 +587,21 @@ int build_side(const int32_t* own_g, const int32_t* gat_g, const int32_t* rel_g,
     int32_t nsel = 0;
     if (E > 0) {
         RGCN_CUDA(cudaMemsetAsync(flag.p, 0, (size_t)(E + 1) * 4, st));
-        k_flag_owned<<<blocks_for(E), TPB, 0, st>>>(own_g, E, (int32_t)lo, (int32_t)hi, flag.p);
+        k_flag_owned<<<blocks_for(E), TPB, 0, st>>>(push ? gat_g : own_g, E, (int32_t)lo, (int32_t)hi, flag.p);
         RGCN_CUDA(scan_exclusive(flag.p, pos.p, E + 1, st));
         RGCN_CUDA(cudaMemcpy(&nsel, pos.p + E, 4, cudaMemcpyDeviceToHost));
     }
-    const int64_t n_own = hi - lo;
-    const int64_t n2 = (int64_t)nsel + n_own;
+    const int64_t n_sel = hi - lo;
+    const int64_t n2 = (int64_t)nsel + n_sel;
     RGCN_CUDA(own.alloc(n2));
     RGCN_CUDA(gat.alloc(n2));
     RGCN_CUDA(rel.alloc(n2));
     RGCN_CUDA(w.alloc(n2));
-    k_fill_entries<<<blocks_for(E + n_own), TPB, 0, st>>>(own_g, gat_g, rel_g, w_edge, flag.p, pos.p, E, nsel,
-                                                          (int32_t)lo, (int32_t)hi, R, own.p, gat.p, rel.p, w.p);
+    k_fill_entries<<<blocks_for(E + n_sel), TPB, 0, st>>>(own_g, gat_g, rel_g, w_edge, flag.p, pos.p, E, nsel,
+                                                          (int32_t)lo, (int32_t)hi, R, push ? 1 : 0, own.p, gat.p, rel.p,
+                                                          w.p);
+    const int64_t n_own = push ? num_all : n_sel;   // owner id space
+    const int64_t n_gat = push ? n_sel : num_all;   // gather id space (chunk rows are numbered from here)
     int rc;
     if ((rc = build_brc(own.p, gat.p, rel.p, w.p, n2, n_own, n_gat, R, NR, T, CH, st, blocked))) return rc;
     if (relmajor && (rc = build_brc(own.p, gat.p, rel.p, w.p, n2, n_own, n_gat, R, (int)std::max<int64_t>(n_own, 1), T,
@@ -605,11 +612,11 @@ int build_side(const int32_t* own_g, const int32_t* gat_g, const int32_t* rel_g,
 
 }  // namespace
 
-extern "C" int rgcn_graph_create_part(const int64_t* src, int64_t src_stride, const int64_t* dst, int64_t dst_stride,
-                                      const int64_t* etype, int64_t etype_stride, int64_t num_edges,
-                                      int64_t num_nodes, int32_t num_relations, int64_t own_lo, int64_t own_hi,
-                                      int32_t range_nodes, int32_t split_threshold, int32_t chunk_size, void* stream,
-                                      rgcn_graph** out) {
+namespace {
+int graph_create_impl(const int64_t* src, int64_t src_stride, const int64_t* dst, int64_t dst_stride,
+                      const int64_t* etype, int64_t etype_stride, int64_t num_edges, int64_t num_nodes,
+                      int32_t num_relations, int64_t own_lo, int64_t own_hi, int32_t range_nodes,
+                      int32_t split_threshold, int32_t chunk_size, bool push, void* stream, rgcn_graph** out) {
     if (!out) return fail(RGCN_ERR_INVALID_ARG, "rgcn_graph_create: out is null");
     *out = nullptr;
     if (num_edges < 0 || num_nodes <= 0 || num_relations <= 0)
@@ -632,6 +639,7 @@ extern "C" int rgcn_graph_create_part(const int64_t* src, int64_t src_stride, co
     g->R = num_relations;
     g->own_lo = own_lo;
     g->n_own = own_hi - own_lo;
+    g->push = push;
     cudaGetDevice(&g->device);
     cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, g->device);
     if (cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking) != cudaSuccess) g->side = nullptr;
@@ -641,7 +649,9 @@ extern "C" int rgcn_graph_create_part(const int64_t* src, int64_t src_stride, co
     g->chunk_size = chunk_size > 0 ? chunk_size : 64;
     int64_t nr = range_nodes > 0 ? range_nodes : 16384;
     // small graphs: one range (pure relation-major); large: blocked so accumulate targets stay L2-hot
-    if (nr >= g->n_own) nr = g->n_own;
+    const int64_t fwd_owners = push ? num_nodes : g->n_own;   // owner space of the forward structures
+    const int64_t nr_bwd = std::min<int64_t>(nr, g->n_own);
+    if (nr >= fwd_owners) nr = fwd_owners;
     g->range_nodes = (int32_t)nr;
 
     const int64_t E = num_edges;
@@ -676,24 +686,45 @@ extern "C" int rgcn_graph_create_part(const int64_t* src, int64_t src_stride, co
                          "rgcn_graph_create: edge_index outside [0,num_nodes) or edge_type outside [0,num_relations)"));
     if ((rc = compute_edge_weights(dst32.p, rel32.p, E, num_nodes, num_relations, w_edge.p, st))) return bail(rc);
     const int T = g->split_threshold, CH = g->chunk_size;
-    const bool one_range = nr >= g->n_own;
-    // forward: owner = dst, gather = src (+ the same entries in pure relation-major order for dL/dW)
+    const bool one_range = nr >= fwd_owners;
+    // forward: owner = dst, gather = src (+ the same entries in pure relation-major order for dL/dW);
+    // pull: the edges whose dst is owned; push: the edges whose SRC is owned
     if ((rc = build_side(dst32.p, src32.p, rel32.p, w_edge.p, E, num_nodes, num_relations, own_lo, own_hi, (int)nr, T,
-                         CH, st, &g->brc[RGCN_BRC_FWD], one_range ? nullptr : &g->brc[RGCN_BRC_FWD_REL])))
+                         CH, st, &g->brc[RGCN_BRC_FWD], one_range ? nullptr : &g->brc[RGCN_BRC_FWD_REL], push)))
         return bail(rc);
     if (one_range) {
         g->brc[RGCN_BRC_FWD_REL] = g->brc[RGCN_BRC_FWD];
         g->rel_is_fwd = true;
-    } else if ((rc = share_chunks(g->brc[RGCN_BRC_FWD], g->brc[RGCN_BRC_FWD_REL], g->n_own, num_nodes, num_relations, st))) {
+    } else if ((rc = share_chunks(g->brc[RGCN_BRC_FWD], g->brc[RGCN_BRC_FWD_REL], fwd_owners, push ? g->n_own : num_nodes,
+                                  num_relations, st))) {
         return bail(rc);
     }
-    // transposed: owner = src, gather = dst, same per-edge weights
-    if ((rc = build_side(src32.p, dst32.p, rel32.p, w_edge.p, E, num_nodes, num_relations, own_lo, own_hi, (int)nr, T,
+    // transposed: owner = src, gather = dst, same per-edge weights (the edges whose src is owned, either mode)
+    if ((rc = build_side(src32.p, dst32.p, rel32.p, w_edge.p, E, num_nodes, num_relations, own_lo, own_hi, (int)nr_bwd, T,
                          CH, st, &g->brc[RGCN_BRC_BWD], nullptr)))
         return bail(rc);
 #undef RGCN_CUDA_G
     *out = g;
     return 0;
+}
+}  // namespace
+
+extern "C" int rgcn_graph_create_part(const int64_t* src, int64_t src_stride, const int64_t* dst, int64_t dst_stride,
+                                      const int64_t* etype, int64_t etype_stride, int64_t num_edges,
+                                      int64_t num_nodes, int32_t num_relations, int64_t own_lo, int64_t own_hi,
+                                      int32_t range_nodes, int32_t split_threshold, int32_t chunk_size, void* stream,
+                                      rgcn_graph** out) {
+    return graph_create_impl(src, src_stride, dst, dst_stride, etype, etype_stride, num_edges, num_nodes, num_relations,
+                             own_lo, own_hi, range_nodes, split_threshold, chunk_size, false, stream, out);
+}
+
+extern "C" int rgcn_graph_create_push(const int64_t* src, int64_t src_stride, const int64_t* dst, int64_t dst_stride,
+                                      const int64_t* etype, int64_t etype_stride, int64_t num_edges,
+                                      int64_t num_nodes, int32_t num_relations, int64_t own_lo, int64_t own_hi,
+                                      int32_t range_nodes, int32_t split_threshold, int32_t chunk_size, void* stream,
+                                      rgcn_graph** out) {
+    return graph_create_impl(src, src_stride, dst, dst_stride, etype, etype_stride, num_edges, num_nodes, num_relations,
+                             own_lo, own_hi, range_nodes, split_threshold, chunk_size, true, stream, out);
 }
 
 extern "C" int rgcn_graph_create(const int64_t* src, int64_t src_stride, const int64_t* dst, int64_t dst_stride,
@@ -719,6 +750,7 @@ extern "C" int rgcn_graph_query(const rgcn_graph* g, int32_t brc, int32_t key, i
         case RGCN_Q_RANGE_NODES: *out = b.range_nodes; break;
         case RGCN_Q_NUM_OWNED: *out = g->n_own; break;
         case RGCN_Q_OWN_LO: *out = g->own_lo; break;
+        case RGCN_Q_PUSH: *out = g->push ? 1 : 0; break;
         case RGCN_Q_NUM_ENTRIES0: *out = b.num_entries0; break;
         case RGCN_Q_NUM_TILES: *out = b.num_tiles; break;
         case RGCN_Q_NUM_TILES_NOSELF: *out = b.num_tiles_noself; break;

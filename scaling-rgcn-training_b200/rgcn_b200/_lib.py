@@ -18,13 +18,13 @@ EXPORTS = (
     'rgcn_graph_export', 'rgcn_layer_workspace_bytes', 'rgcn_layer_fwd', 'rgcn_layer_bwd', 'rgcn_map_gather',
     'rgcn_kernel_launch_count', 'rgcn_profile_enable', 'rgcn_profile_collect', 'rgcn_pad_rows',
     'rgcn_eval_counts', 'rgcn_adam_step', 'rgcn_adam_step_dev', 'rgcn_layer_chunk_rows_bytes', 'rgcn_layer_fwd_keep',
-    'rgcn_layer_bwd_reuse', 'rgcn_set_option',
+    'rgcn_layer_bwd_reuse', 'rgcn_set_option', 'rgcn_graph_create_push',
 )
 
 BRC_FWD, BRC_BWD, BRC_FWD_REL = 0, 1, 2
 Q_NUM_NODES, Q_NUM_EDGES, Q_NUM_RELATIONS, Q_NUM_SEGMENTS, Q_NUM_ENTRIES, Q_NUM_CHUNKS, Q_NUM_GROUPS, \
     Q_NUM_BATCHES, Q_RANGE_NODES, Q_DEVICE_BYTES, Q_NUM_OWNED, Q_OWN_LO, Q_NUM_ENTRIES0, Q_NUM_TILES, \
-    Q_NUM_TILES_NOSELF = range(15)
+    Q_NUM_TILES_NOSELF, Q_PUSH = range(16)
 A_PERM, A_SEG_PTR, A_SEG_OWN, A_SEG_REL, A_SEG_PTR0, A_E_IDX, A_E_W, A_RAW_IDX, A_RAW_W, A_CHUNK_BEG, \
     A_CHUNK_END, A_BAT_SEG0, A_BAT_INFO, A_E_OWN, A_TILE_E0, A_TILE_INFO, A_CHUNK_OUT = range(17)
 F_RELU_IN, F_FORCE_SIMPLE = 1, 2
@@ -55,6 +55,8 @@ def load():
     lib.rgcn_graph_create_part.restype = C.c_int
     lib.rgcn_graph_create_part.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i32, i64, i64, i32, i32, i32, vp,
                                            C.POINTER(vp)]
+    lib.rgcn_graph_create_push.restype = C.c_int
+    lib.rgcn_graph_create_push.argtypes = lib.rgcn_graph_create_part.argtypes
     lib.rgcn_graph_destroy.restype = None
     lib.rgcn_graph_destroy.argtypes = [vp]
     lib.rgcn_graph_query.restype = C.c_int

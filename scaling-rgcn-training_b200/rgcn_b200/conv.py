@@ -67,11 +67,14 @@ class _RGCNLayerFn(torch.autograd.Function):
                                              _stream(t.device)), 'rgcn_pad_rows')
             return tp
 
+        push = comm is not None and graph.push
         if comm is not None:
             if x.dim() != 2 or x.size(0) != graph.num_owned:
                 raise ValueError(f'RGCNConv (partitioned): x must hold the {graph.num_owned} owned rows')
-            x = comm.all_gather_rows(pad_rows(x.contiguous()))   # pad the owned shard, gather the mirror
-        if x.dim() != 2 or x.size(0) < graph.num_nodes or (comm is None and x.size(0) != graph.num_nodes):
+            x = pad_rows(x.contiguous())                     # the owned shard, 16-byte addressable
+            if not push:
+                x = comm.all_gather_rows(x)                  # pull: every rank needs the rows of all sources
+        if not push and (x.dim() != 2 or x.size(0) < graph.num_nodes or (comm is None and x.size(0) != graph.num_nodes)):
             raise ValueError(f'RGCNConv: x must be [num_nodes={graph.num_nodes}, in_channels]')
         x = x if x.stride(1) == 1 or x.size(1) == 1 else x.contiguous()
         weight = weight.contiguous()
@@ -86,7 +89,13 @@ class _RGCNLayerFn(torch.autograd.Function):
         if comm is None and _PAD_WIDE and 32 < fin <= 64 and (x.stride(0) % 4 != 0 or x.data_ptr() % 16 != 0):
             mirror = torch.empty((x.size(0), (fin + 3) // 4 * 4), dtype=torch.float32, device=x.device)
         ldo = (fout + 3) // 4 * 4
-        out_buf = torch.empty((graph.num_owned, ldo), dtype=torch.float32, device=x.device)
+        if push:
+            # partial output over ALL nodes (padded to world * chunk rows for the reduce-scatter)
+            out_buf = torch.empty((comm.world * comm.chunk, ldo), dtype=torch.float32, device=x.device)
+            if out_buf.size(0) > graph.num_nodes:
+                out_buf[graph.num_nodes:].zero_()
+        else:
+            out_buf = torch.empty((graph.num_owned, ldo), dtype=torch.float32, device=x.device)
         out = out_buf[:, :fout] if ldo != fout else out_buf
         ws_bytes = graph.workspace_bytes(fin, fout, False)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
@@ -101,6 +110,9 @@ class _RGCNLayerFn(torch.autograd.Function):
                                          _ptr(xc), _ptr(mirror), mirror.stride(0) if mirror is not None else 0,
                                          _stream(x.device))
         _lib.check(rc, 'rgcn_layer_fwd')
+        if push:   # sum of the ranks' partials, each rank keeping its own rows
+            out_buf = comm.reduce_scatter_rows(out_buf)[:graph.num_owned]
+            out = out_buf[:, :fout] if ldo != fout else out_buf
         if mirror is not None:
             x = mirror              # what backward re-gathers; the caller's tensor is not kept
         ctx.graph, ctx.flags, ctx.comm, ctx.fin = graph, flags, comm, fin
@@ -126,7 +138,11 @@ class _RGCNLayerFn(torch.autograd.Function):
         # partitioned graph: the all-gather of gout (needed only by dL/dx) is started first and
         # overlaps the dL/dW pass, which reads the owned rows only
         gout_all, work = None, None
-        if comm is not None and need_x:
+        if comm is not None and graph.push:
+            # source-partitioned: dL/dW and dL/dx both read the rows of all destinations
+            if need_x or need_w or need_root or need_bias:
+                gout_all = comm.all_gather_rows(gout)
+        elif comm is not None and need_x:
             if hasattr(comm, 'all_gather_rows_async'):
                 gout_all, work = comm.all_gather_rows_async(gout)
             else:

@@ -23,7 +23,8 @@ def _env_int(name: str, default: int) -> int:
 
 class RGCNGraph:
     def __init__(self, edge_index: torch.Tensor, edge_type: torch.Tensor, num_nodes: int, num_relations: int,
-                 range_nodes: int = 0, split_threshold: int = 0, chunk_size: int = 0, own_range=None) -> None:
+                 range_nodes: int = 0, split_threshold: int = 0, chunk_size: int = 0, own_range=None,
+                 push: bool = False) -> None:
         lib = _lib.load()
         if edge_index.dtype != torch.int64 or edge_type.dtype != torch.int64:
             raise TypeError('edge_index and edge_type must be int64 (as graphs/graph.py:65 builds them)')
@@ -38,6 +39,9 @@ class RGCNGraph:
         # own_range = (lo, hi): destination-partitioned graph of one rank; default = the whole graph
         self.own_lo, self.own_hi = (0, self.num_nodes) if own_range is None else (int(own_range[0]), int(own_range[1]))
         self.num_owned = self.own_hi - self.own_lo
+        # push = source-partitioned forward structures (rgcn_graph_create_push): x holds the owned rows, the
+        # forward output is a partial over ALL nodes that the caller reduce-scatters
+        self.push = bool(push)
         range_nodes = range_nodes or _env_int('RGCN_B200_RANGE_NODES', 0)
         split_threshold = split_threshold or _env_int('RGCN_B200_SPLIT', 0)
         chunk_size = chunk_size or _env_int('RGCN_B200_CHUNK', 0)
@@ -45,7 +49,8 @@ class RGCNGraph:
         src, dst = edge_index[0], edge_index[1]          # strided views are passed as they are
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
-            rc = lib.rgcn_graph_create_part(src.data_ptr(), src.stride(0) if src.numel() else 1,
+            create = lib.rgcn_graph_create_push if self.push else lib.rgcn_graph_create_part
+            rc = create(src.data_ptr(), src.stride(0) if src.numel() else 1,
                                             dst.data_ptr(), dst.stride(0) if dst.numel() else 1,
                                             edge_type.data_ptr(), edge_type.stride(0) if edge_type.numel() else 1,
                                             self.num_edges, self.num_nodes, self.num_relations, self.own_lo,

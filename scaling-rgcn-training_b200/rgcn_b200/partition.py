@@ -48,6 +48,7 @@ class RowComm:
         self.chunk, self.ranges = plan_ranges(num_nodes, self.world)
         self.lo, self.hi = self.ranges[self.rank]
         self.bytes_gathered = 0
+        self.bytes_reduced = 0
         self.events = None        # list of (start, stop) CUDA-event pairs when timing is on (bench)
 
     def all_gather_rows_async(self, t: Tensor):
@@ -78,6 +79,17 @@ class RowComm:
         dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
         self._toc(ev)
         self.bytes_gathered += out.numel() * out.element_size()
+        return out
+
+    def reduce_scatter_rows(self, t: Tensor) -> Tensor:
+        """[world*chunk, F] partial sums on every rank -> [chunk, F]: this rank's rows of the total."""
+        if t.size(0) != self.world * self.chunk:
+            raise ValueError('reduce_scatter_rows: expected world * chunk rows')
+        out = t.new_empty((self.chunk, t.size(1)))
+        ev = self._tic(t)
+        dist.reduce_scatter_tensor(out, t.contiguous(), op=dist.ReduceOp.SUM, group=self.group)
+        self._toc(ev)
+        self.bytes_reduced += t.numel() * t.element_size()
         return out
 
     def _tic(self, t: Tensor):
@@ -113,7 +125,10 @@ class RowComm:
 
 class PartitionedRGCN(nn.Module):
     """2-layer R-GCN (Emb_Layers arithmetic, reference model/layers.py:20-25) on a partitioned
-    graph: sharded embedding rows, replicated layer weights, fused inter-layer ReLU."""
+    graph: sharded embedding rows, replicated layer weights, fused inter-layer ReLU.  The graph decides the
+    exchange: destination-partitioned ("pull": all-gather of the input rows forward and of gout backward) or
+    source-partitioned ("push": reduce-scatter of partial outputs forward, all-gather of gout backward — the
+    63-wide layer-1 input never crosses the links)."""
 
     def __init__(self, graph, comm: RowComm, num_relations: int, hidden_l: int, num_labels: int, emb_dim: int,
                  seed: int = 0) -> None:
@@ -136,18 +151,74 @@ class PartitionedRGCN(nn.Module):
         return rgcn_layer(h, c2.weight, c2.root, c2.bias, self.graph, relu_in=True, comm=self.comm)
 
 
+def partition_mode() -> str:
+    m = os.environ.get('RGCN_B200_PARTITION', 'push')
+    if m not in ('push', 'pull'):
+        raise ValueError('RGCN_B200_PARTITION must be push or pull')
+    return m
+
+
+def partitioned_parity_check(rank: int, world: int, device, mode: str, hidden: int, classes: int, emb: int,
+                             scale: float = 1 / 16) -> Optional[dict]:
+    """bench.py --gpus N, N > 1: the partitioned fwd+bwd on the AM-shape graph at `scale` against the SAME step on
+    one GPU (rank 0, unpartitioned graph): max-norm relative errors of the output, the embedding gradient and all
+    parameter gradients.  Proves on the measuring box that the N-rank path computes what the 1-rank path does."""
+    from .conv import rgcn_layer
+    from .graph import RGCNGraph
+    from .synthetic import am_shape
+    ei, et, n, r = am_shape(scale=scale)
+    comm = RowComm(n)
+    ei_d, et_d = ei.to(device), et.to(device)
+    graph = RGCNGraph(ei_d, et_d, n, r, own_range=(comm.lo, comm.hi), push=(mode == 'push'))
+    model = PartitionedRGCN(graph, comm, r, hidden, classes, emb, seed=7).to(device)
+    gen = torch.Generator().manual_seed(8)
+    gout_full = torch.randn(n, classes, generator=gen)
+    out = model()
+    out.backward(gout_full[comm.lo:comm.hi].to(device))
+    out_all = comm.all_gather_rows(out.detach().contiguous())[:n]
+    gx_all = comm.all_gather_rows(model.embedding.grad.contiguous())[:n]
+    res = None
+    if rank == 0:
+        g1 = RGCNGraph(ei_d, et_d, n, r)
+        full = torch.randn(n, emb, generator=torch.Generator().manual_seed(7)).to(device).requires_grad_()
+        ps = [p.detach().clone().requires_grad_() for p in (model.rgcn1.weight, model.rgcn1.root, model.rgcn1.bias,
+                                                            model.rgcn2.weight, model.rgcn2.root, model.rgcn2.bias)]
+        h = rgcn_layer(full, ps[0], ps[1], ps[2], g1)
+        ref = rgcn_layer(h, ps[3], ps[4], ps[5], g1, relu_in=True)
+        ref.backward(gout_full.to(device))
+
+        def rel(a, b):
+            return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+        got = [model.rgcn1.weight.grad, model.rgcn1.root.grad, model.rgcn1.bias.grad, model.rgcn2.weight.grad,
+               model.rgcn2.root.grad, model.rgcn2.bias.grad]
+        errs = {'out': rel(out_all, ref.detach()), 'gx': rel(gx_all, full.grad)}
+        for name, a, b in zip(('gW1', 'groot1', 'gbias1', 'gW2', 'groot2', 'gbias2'), got, ps):
+            errs[name] = rel(a, b.grad)
+        res = {'against': f'the same step on 1 GPU (unpartitioned), AM-shape at scale {scale:g} (N={n}, E={et.numel()})',
+               'max_rel_err': errs, 'worst': max(errs.values()), 'argmax_equal': bool(torch.equal(out_all.argmax(1), ref.argmax(1)))}
+        del g1
+    del graph, model
+    torch.cuda.synchronize(device)
+    dist.barrier()
+    return res
+
+
 def run_partitioned_bench(args, rank: int, world: int, device, metric: str, unit: str) -> None:
     """bench.py --gpus N (N > 1): strong scaling of the AM-shape fwd+bwd step."""
     from . import _lib
     from .graph import RGCNGraph
     from .synthetic import am_shape
     import bench as B                                        # helpers of the single-GPU arm
+    mode = partition_mode()
+    parity = None
+    if not getattr(args, 'no_check', False):
+        parity = partitioned_parity_check(rank, world, device, mode, B.HIDDEN, B.CLASSES, B.EMB)
     ei, et, n, r = am_shape(scale=args.scale)                # every rank derives the same graph (seed 0)
     e = et.numel()
     comm = RowComm(n)
     t0 = time.perf_counter()
     ei_d, et_d = ei.to(device), et.to(device)
-    graph = RGCNGraph(ei_d, et_d, n, r, own_range=(comm.lo, comm.hi))
+    graph = RGCNGraph(ei_d, et_d, n, r, own_range=(comm.lo, comm.hi), push=(mode == 'push'))
     del ei_d, et_d
     torch.cuda.synchronize(device)
     setup_ms = (time.perf_counter() - t0) * 1e3
@@ -161,27 +232,53 @@ def run_partitioned_bench(args, rank: int, world: int, device, metric: str, unit
             p.grad = None
         model().backward(gout)
 
+    # the step is captured once in a CUDA graph (collectives included) and replayed: at 8 GPUs a rank's
+    # kernels are ~50 us each and eager launches would show; RGCN_B200_PART_GRAPH=0 launches eagerly
+    use_graph = os.environ.get('RGCN_B200_PART_GRAPH', '1') != '0'
     sampler = B.ClockSampler(device.index)
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize(device)
-    comm.bytes_gathered = 0
-    comm.events = []
+    comm.bytes_gathered = comm.bytes_reduced = 0
+    step()
+    gathered, reduced = comm.bytes_gathered, comm.bytes_reduced
     launches0 = _lib.launch_count()
+    step()
+    launches_per_step = _lib.launch_count() - launches0
+    # synchronous-collective time, measured on an eager step (events cannot be recorded inside a capture)
+    comm.events = []
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(device)
+    sync_ms = comm.comm_ms() / 3
+    comm.events = None
+    cuda_graph = None
+    run = step
+    if use_graph:
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        dist.barrier()
+        cuda_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cuda_graph):
+            step()
+        run = cuda_graph.replay
+        torch.cuda.synchronize(device)
     if rank == 0:
         sampler.start()
-    total_ms = B.time_steps(step, args.steps, 0, world, device)
+    total_ms = B.time_steps(run, args.steps, max(args.warmup, 3), world, device)
     clocks = sampler.stop() if rank == 0 else None
-    launches = _lib.launch_count() - launches0
     ms = total_ms / args.steps
     value = e / (ms * 1e-3)
-    sync_ms = comm.comm_ms() / max(args.steps, 1)
-    gathered = comm.bytes_gathered // max(args.steps, 1)
     # end to end: the Trainer.train iteration body on the partitioned model — this rank's share of the
     # labelled batch copied from pinned host memory every step, forward, CE loss (global mean: local
     # sum / total count), backward (weight gradients all-reduced inside the layer), Adam on the local
     # embedding shard and the replicated weights, loss all-reduced and read back
     e2e = None
+    e2e_graph = None
     if not getattr(args, 'no_e2e', False):
         from .synthetic import labelled_split
         from .trainer import make_optimizer
@@ -190,49 +287,92 @@ def run_partitioned_bench(args, rank: int, world: int, device, metric: str, unit
         x_h = (x_all[mine] - comm.lo).contiguous().pin_memory()
         y_h = y_all[mine].contiguous().pin_memory()
         m_total = float(x_all.numel())
-        opt = make_optimizer(model)
+        opt = make_optimizer(model, capturable=use_graph)
+        xs, ys = torch.empty_like(x_h, device=device), torch.empty_like(y_h, device=device)
+        tot = torch.zeros((), device=device)
 
-        def e2e_step():
-            xs, ys = x_h.to(device, non_blocking=True), y_h.to(device, non_blocking=True)
-            opt.zero_grad()
+        def body():
+            opt.zero_grad(set_to_none=True)
             out = model()[xs]
             picked = out.gather(1, ys.to(torch.float32).argmax(-1, keepdim=True)).squeeze(1)
             local = (torch.logsumexp(out, dim=1) - picked).sum() / m_total
             local.backward()
             opt.step()
-            tot = local.detach().clone()
+            tot.copy_(local.detach())
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+
+        if use_graph:
+            snapshot = [p.detach().clone() for p in params]
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                xs.copy_(x_h, non_blocking=True)
+                ys.copy_(y_h, non_blocking=True)
+                body()
+                with torch.no_grad():
+                    for p, s_ in zip(params, snapshot):
+                        p.copy_(s_)
+                opt.reset_state()
+            torch.cuda.current_stream(device).wait_stream(side)
+            torch.cuda.synchronize(device)
+            dist.barrier()
+            e2e_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(e2e_graph):
+                body()
+
+        def e2e_step():
+            xs.copy_(x_h, non_blocking=True)
+            ys.copy_(y_h, non_blocking=True)
+            if e2e_graph is not None:
+                e2e_graph.replay()
+            else:
+                body()
             return tot.item()
 
-        e2e_ms = B.time_steps(e2e_step, args.steps, args.warmup, world, device) / args.steps
+        e2e_ms = B.time_steps(e2e_step, args.steps, max(args.warmup, 3), world, device) / args.steps
         h2d = torch.tensor([x_h.numel() * x_h.element_size() + y_h.numel() * y_h.element_size()], device=device,
                            dtype=torch.float64)
         dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
         e2e = {'value': e / (e2e_ms * 1e-3), 'unit': unit, 'h2d_bytes_per_step': int(h2d.item()),
                'd2h_bytes_per_step': 4 * world, 'ms_per_step': e2e_ms,
-               'what': 'Trainer.train iteration body on the partitioned model (eager): per-rank share of x_train/y_train '
+               'what': 'Trainer.train iteration body on the partitioned model (' + ('one CUDA-graph replay per step' if use_graph else 'eager') +
+                       '): per-rank share of x_train/y_train '
                        'from pinned host memory, fwd, CE loss (global mean), bwd, FusedAdam on the embedding shard and '
                        'the replicated weights, all-reduced loss .item(); bytes summed over ranks'}
-    own_edges = torch.tensor([graph.query(_lib.Q_NUM_ENTRIES0, _lib.BRC_FWD) - graph.num_owned], device=device,
+    own_edges = torch.tensor([graph.query(_lib.Q_NUM_ENTRIES0, _lib.BRC_BWD) - graph.num_owned], device=device,
                              dtype=torch.float64)
     mx = own_edges.clone()
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     if rank == 0:
+        if mode == 'push':
+            coll = ('per layer: reduce_scatter(partial out) fwd, all_gather(gout) bwd; one all_reduce of dW/droot/dbias; '
+                    'the 63-wide layer-1 input is never exchanged')
+            limiting = 'all_gather(gout of layer 1, 16 wide) + reduce_scatter(partial h1, 16 wide)'
+        else:
+            coll = 'per layer: all_gather(x) fwd, all_gather(gout) bwd; one all_reduce of dW/droot/dbias'
+            limiting = 'all_gather(x0 mirror, 64 wide)'
         line = {
             'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
             'config': {'workload': 'am_shape_full_graph_rgcn_63_16_11_all_grads', 'scale': args.scale, 'nodes': n,
-                       'directed_edges': e, 'relations': r, 'partition': f'dst-partitioned x{world}, equal node ranges',
-                       'collectives': 'per layer: all_gather(x) fwd, all_gather(gout) bwd; one all_reduce of dW/droot/dbias',
+                       'directed_edges': e, 'relations': r,
+                       'partition': f'{"source" if mode == "push" else "dst"}-partitioned x{world}, equal node ranges',
+                       'collectives': coll, 'limiting_collective': limiting,
                        'all_gather_bytes_per_step_per_rank': gathered,
-                       'max_rank_in_edges': int(mx.item()), 'mean_rank_in_edges': e / world,
-                       'sync_collectives_ms_per_step_rank0': sync_ms,
+                       'reduce_scatter_bytes_per_step_per_rank': reduced,
+                       'max_rank_edges': int(mx.item()), 'mean_rank_edges': e / world,
+                       'sync_collectives_ms_per_step_rank0_eager': sync_ms,
+                       'step_launch': 'cuda graph replay (collectives captured)' if use_graph else 'eager',
                        'graph_build_ms_once': setup_ms,
                        'l2_policy': 'inputs larger than L2; no flush'},
-            'clocks': clocks, 'gpu_launches': int(launches),
+            'parity': parity,
+            'clocks': clocks, 'gpu_launches': int(launches_per_step * args.steps),
             'e2e': e2e, 'roofline': None, 'cpu_baseline': None,
         }
         print(json.dumps(line), flush=True)
+    # graphs hold references to the communicator's work: drop them before the process group goes away
+    del cuda_graph, e2e_graph, run
+    torch.cuda.synchronize(device)
     dist.barrier()
     dist.destroy_process_group()

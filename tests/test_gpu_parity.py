@@ -374,6 +374,17 @@ class _LocalComm:
     def all_reduce_sum_(self, tensors):
         self.reduced.append([t.clone() for t in tensors])
 
+    # source-partitioned ("push") layers: the rank's partial over all nodes is kept for the test to sum; what
+    # comes back are this rank's rows of the true total (supplied by the test), so autograd continues from
+    # exactly what a real reduce-scatter would deliver
+    def reduce_scatter_rows(self, t):
+        self.partials.append(t.detach().clone())
+        lo = self.rank * self.chunk
+        out = t.new_zeros((self.chunk, t.size(1)))
+        rows = self.total[lo:lo + self.chunk]
+        out[:rows.size(0), :rows.size(1)] = rows
+        return out
+
 
 @pytest.mark.parametrize('world', [2, 3])
 def test_partitioned_graph_matches_unpartitioned(world):
@@ -409,6 +420,53 @@ def test_partitioned_graph_matches_unpartitioned(world):
         gw, gr, gb = comm.reduced[0]
         gws, groots, gbiases = gws + gw, groots + gr, gbiases + gb
     assert rel_err(torch.cat(outs), ref.detach().cpu()) < TOL
+    assert rel_err(torch.cat(gxs), leaves[0].grad.cpu()) < TOL
+    assert rel_err(gws, leaves[1].grad.cpu()) < TOL
+    assert rel_err(groots, leaves[2].grad.cpu()) < TOL
+    assert rel_err(gbiases, leaves[3].grad.cpu()) < TOL
+
+
+@pytest.mark.parametrize('world', [2, 3])
+@pytest.mark.parametrize('fin,fout,relu', [(63, 16, False), (16, 11, True)])
+def test_source_partitioned_graph_matches_unpartitioned(world, fin, fout, relu):
+    """rgcn_graph_create_push: per-rank structures bit-exact against the oracle; the ranks' PARTIAL outputs sum
+    to the unpartitioned layer's output (what the reduce-scatter computes); gx rows and the summed parameter
+    gradients match.  x never leaves its rank."""
+    from rgcn_b200.partition import plan_ranges
+    ei, et, n, r = golden_graph('AIFB_bisim_k3')
+    eid, etd = ei.to(DEV), et.to(DEV)
+    chunk, ranges = plan_ranges(n, world)
+    torch.manual_seed(1)
+    x = torch.randn(n, fin, device=DEV)
+    w = ((torch.rand(r, fin, fout, device=DEV) - 0.5) * 0.3)
+    root = ((torch.rand(fin, fout, device=DEV) - 0.5) * 0.3)
+    bias = torch.rand(fout, device=DEV)
+    gout = torch.randn(n, fout, device=DEV)
+    g_full = RGCNGraph(eid, etd, n, r)
+    leaves = [t.clone().requires_grad_() for t in (x, w, root, bias)]
+    ref = rgcn_layer(*leaves, g_full, relu_in=relu)
+    ref.backward(gout)
+    total = torch.zeros(world * chunk, fout, device=DEV)
+    gxs, gws, groots, gbiases = [], 0, 0, 0
+    for rank, (lo, hi) in enumerate(ranges):
+        g = RGCNGraph(eid, etd, n, r, own_range=(lo, hi), range_nodes=64, split_threshold=8, chunk_size=4, push=True)
+        fwd, bwd = csr_oracle.build_graph(ei[0].numpy(), ei[1].numpy(), et.numpy(), n, r, 64, 8, 4, lo=lo, hi=hi, push=True)
+        _check_brc(g, _lib.BRC_FWD, fwd)
+        _check_brc(g, _lib.BRC_BWD, bwd)
+        comm = _LocalComm(chunk, world)
+        comm.rank, comm.partials, comm.total = rank, [], ref.detach()
+        comm.set_full(fout, gout)
+        lv = [x[lo:hi].clone().requires_grad_()] + [t.clone().requires_grad_() for t in (w, root, bias)]
+        out = rgcn_layer(*lv, g, relu_in=relu, comm=comm)
+        assert tuple(out.shape) == (hi - lo, fout)
+        out.backward(gout[lo:hi])
+        part = comm.partials[0]
+        total[:, :] += part[:, :fout]
+        gxs.append(lv[0].grad)
+        gw, gr, gb = comm.reduced[0]
+        gws, groots, gbiases = gws + gw, groots + gr, gbiases + gb
+    assert rel_err(total[:n], ref.detach().cpu()) < TOL
+    assert float(total[n:].abs().max()) == 0.0 if total.size(0) > n else True
     assert rel_err(torch.cat(gxs), leaves[0].grad.cpu()) < TOL
     assert rel_err(gws, leaves[1].grad.cpu()) < TOL
     assert rel_err(groots, leaves[2].grad.cpu()) < TOL

@@ -36,15 +36,17 @@ def _worker(rank, world, port, ret):
         ref = rgcn_layer(*full, RGCNGraph(ei, et, n, r))
         ref.backward(gout)
         comm = RowComm(n)
-        g = RGCNGraph(ei, et, n, r, own_range=(comm.lo, comm.hi))
-        part = [x[comm.lo:comm.hi].clone().requires_grad_()] + [t.clone().requires_grad_() for t in (w, root, bias)]
-        out = rgcn_layer(*part, g, comm=comm)
-        out.backward(gout[comm.lo:comm.hi])
 
         def rel(a, b):
             return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
-        errs = [rel(out, ref[comm.lo:comm.hi]), rel(part[0].grad, full[0].grad[comm.lo:comm.hi])]
-        errs += [rel(a.grad, b.grad) for a, b in zip(part[1:], full[1:])]
+        errs = []
+        for push in (False, True):      # destination-partitioned (all-gather) and source-partitioned (reduce-scatter)
+            g = RGCNGraph(ei, et, n, r, own_range=(comm.lo, comm.hi), push=push)
+            part = [x[comm.lo:comm.hi].clone().requires_grad_()] + [t.clone().requires_grad_() for t in (w, root, bias)]
+            out = rgcn_layer(*part, g, comm=comm)
+            out.backward(gout[comm.lo:comm.hi])
+            errs += [rel(out, ref[comm.lo:comm.hi]), rel(part[0].grad, full[0].grad[comm.lo:comm.hi])]
+            errs += [rel(a.grad, b.grad) for a, b in zip(part[1:], full[1:])]
         ret[rank] = max(errs)
     finally:
         dist.destroy_process_group()

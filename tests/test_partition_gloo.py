@@ -64,6 +64,21 @@ def _worker(rank, world, port, ret):
         comm.all_reduce_sum_(grads)
         for a, b in zip(grads, leaves[1:]):
             assert torch.allclose(a, b.grad, atol=1e-5), 'all-reduced parameter gradients'
+        # source-partitioned ("push") forward: every rank runs the layer over the edges whose SRC it owns from
+        # its own x rows (root + bias on its own rows only) and the partials are reduce-scattered
+        mine_src = (ei[0] >= lo) & (ei[0] < hi)
+        # mean normalisers are those of the WHOLE graph: scale each edge's message by cnt_local / cnt_global
+        pad_n = comm.world * comm.chunk
+        partial = torch.zeros(pad_n, 3)
+        key_all = et * n_odd + ei[1]
+        cnt_all = torch.bincount(key_all, minlength=r * n_odd).float()
+        for e_id in torch.nonzero(mine_src).flatten().tolist():
+            s_, d_, t_ = int(ei[0, e_id]), int(ei[1, e_id]), int(et[e_id])
+            partial[d_] += (x[s_] @ w[t_]) / cnt_all[t_ * n_odd + d_]
+        partial[lo:hi] += x[lo:hi] @ root + bias
+        mine = comm.reduce_scatter_rows(partial)
+        assert mine.shape == (comm.chunk, 3) and comm.bytes_reduced == partial.numel() * 4
+        assert torch.allclose(mine[:hi - lo], ref[lo:hi], atol=1e-5), 'reduce-scattered partial outputs'
         ret[rank] = 'ok'
     finally:
         dist.destroy_process_group()
