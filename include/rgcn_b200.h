@@ -70,6 +70,8 @@ enum {
 #define RGCN_F_RELU_IN     1u  /* apply max(0,.) to every gathered input row (fuses the reference's
                                   F.relu between the two layers, model/layers.py:22) */
 #define RGCN_F_FORCE_SIMPLE 2u /* use the generic (any-shape, scalar-FMA) kernels */
+#define RGCN_F_NO_RELU_MASK 4u /* backward with RGCN_F_RELU_IN: leave gx UNMASKED — the caller applies the ReLU
+                                  mask itself (fused into the exchange of gx: rgcn_nvl_store_rows relu_pre) */
 
 const char* rgcn_last_error(void);
 int rgcn_abi_version(void);
@@ -78,8 +80,10 @@ int rgcn_abi_version(void);
  * RGCN_OPT_OVERLAP: 1 = passes of one layer call that do not depend on each other (dL/dW vs the dL/dx
  * chain, chunk pre-pass vs root pass) run concurrently on an engine-owned side stream, forked from and
  * joined back into the caller's stream inside the call (capturable in a CUDA graph); 0 = one stream.
- * RGCN_OPT_OVERLAP_*_CTAS: resident CTAs per SM each of the two concurrent backward passes keeps to. */
-enum { RGCN_OPT_OVERLAP = 0, RGCN_OPT_OVERLAP_WGRAD_CTAS = 1, RGCN_OPT_OVERLAP_DX_CTAS = 2 };
+ * RGCN_OPT_OVERLAP_*_CTAS: resident CTAs per SM each of the two concurrent backward passes keeps to.
+ * RGCN_OPT_NVL_MODE: the NVLink exchange kernels use 1 = multimem.* with weak semantics (default; the rank
+ * barrier orders them), 0 = relaxed.sys, 2 = plain peer pointers even when a multicast address is given. */
+enum { RGCN_OPT_OVERLAP = 0, RGCN_OPT_OVERLAP_WGRAD_CTAS = 1, RGCN_OPT_OVERLAP_DX_CTAS = 2, RGCN_OPT_NVL_MODE = 3 };
 int rgcn_set_option(int32_t option, int64_t value);
 
 /* K0 — replaces nothing in the reference one-to-one: PyG re-derives `edge_type == r` masks on
@@ -207,12 +211,31 @@ int rgcn_adam_step_dev(float* param, const float* grad, float* exp_avg, float* e
 int rgcn_pad_rows(const float* src, int64_t lds, int32_t cols, float* dst, int64_t ldd, int64_t num_rows,
                   void* stream);
 
+/* Row exchanges of the partitioned layers as engine kernels over NVLink / NVSwitch peer memory (no reference
+ * counterpart).  The buffers are symmetric allocations of all ranks (host side: torch.distributed.
+ * _symmetric_memory); `*_multicast` is the NVSwitch multicast address of the buffer, or null with `host_peers`
+ * = HOST array of the `num_peers` ranks' device pointers (peer-mapped) when the fabric has no multicast.
+ * Ordering between ranks (store -> barrier -> read) is the caller's.
+ * rgcn_nvl_store_rows: all-gather half — row r of src ([rows, cols], leading dimension lds) lands in row
+ *   row0 + r of EVERY rank's buffer ([*, ldd], ldd % 4 == 0, columns >= cols zero) through one multimem.st
+ *   per 16 bytes.  relu_pre != null fuses the ReLU backward of the inter-layer activation
+ *   (reference model/layers.py:22): src[r][c] is zeroed where relu_pre[r][c] <= 0 first (and written back).
+ * rgcn_nvl_reduce_rows: reduce-scatter / all-reduce half — dst[r][c] = sum over ranks of
+ *   buffer_rank[row0 + r][c], c < width (width % 4 == 0), one multimem.ld_reduce.add.f32 per 16 bytes:
+ *   the switch adds the ranks' copies in flight. */
+int rgcn_nvl_store_rows(float* src, int64_t lds, int32_t cols, const float* relu_pre, int64_t ld_pre,
+                        float* dst_multicast, void* const* host_peers, int32_t num_peers, int64_t ldd,
+                        int64_t row0, int64_t rows, void* stream);
+int rgcn_nvl_reduce_rows(const float* src_multicast, void* const* host_peers, int32_t num_peers, int64_t lds,
+                         int64_t row0, int64_t rows, float* dst, int64_t ldd, int32_t width, void* stream);
+
 /* Instrumentation (no reference counterpart).  rgcn_kernel_launch_count: engine kernels launched
  * by this process so far.  rgcn_profile_enable(1): every pass launch is bracketed by a CUDA-event
  * pair on its own stream; rgcn_profile_collect synchronises those events, returns up to
  * max_records (tag, dims[2], milliseconds) records and clears the log.  Tags: 1 weight-fragment
  * prep, 2 chunk pre-pass, 3 forward tile pass, 4 dL/dx tile pass, 5 dL/dW pass, 6 column copy,
- * 7 ReLU mask, 8 generic kernels, 9 map gather, 10 self-loop (root + bias) pass.
+ * 7 ReLU mask, 8 generic kernels, 9 map gather, 10 self-loop (root + bias) pass, 11 / 12 the NVLink
+ * exchange kernels (multicast store / load-reduce).
  * dims = (gathered width, output width). */
 int64_t rgcn_kernel_launch_count(void);
 int rgcn_profile_enable(int32_t on);

@@ -294,6 +294,7 @@ int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
         return fail(RGCN_ERR_INVALID_ARG, "rgcn_layer_bwd: a source-partitioned graph needs gout_gather (all nodes' rows)");
     cudaStream_t st = (cudaStream_t)stream;
     const bool relu = (flags & RGCN_F_RELU_IN) != 0;
+    const bool mask = relu && !(flags & RGCN_F_NO_RELU_MASK);   // apply the ReLU mask to gx here
     const int kp = pad_dim(fin), np = pad_dim(fout);
     const bool big = (uint64_t)n_gat * (uint64_t)ldx >= (1ull << 32) ||
                      (uint64_t)g->N * (uint64_t)(gout_gather ? ldgg : ldg) >= (1ull << 32) ||
@@ -325,7 +326,7 @@ int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
             p.weight = weight; p.root = root; p.bias = nullptr; p.transpose = true; p.w_rows = fin; p.w_cols = fout;
             p.out = gx; p.ldo = ldgx; p.nout = fin; p.relu_in = false;
             if ((rc = launch_simple_pass(p, st))) return rc;
-            if (relu && (rc = launch_relu_mask(gx, ldgx, x_own, ldx, g->n_own, fin, st))) return rc;
+            if (mask && (rc = launch_relu_mask(gx, ldgx, x_own, ldx, g->n_own, fin, st))) return rc;
         }
         return 0;
     }
@@ -408,7 +409,7 @@ int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
             if ((rc = launch_tile_pass(p, g->num_sms, st))) return rc;
         }
         if (!direct && (rc = launch_copy_cols(target, tld, gx, ldgx, g->n_own, fin, st))) return rc;
-        if (relu && (rc = launch_relu_mask(gx, ldgx, x_own, ldx, g->n_own, fin, st))) return rc;
+        if (mask && (rc = launch_relu_mask(gx, ldgx, x_own, ldx, g->n_own, fin, st))) return rc;
     }
     return fk.end();
 }
@@ -419,6 +420,7 @@ extern "C" int rgcn_set_option(int32_t option, int64_t value) {
         case RGCN_OPT_OVERLAP: opts().overlap = (int)value; return 0;
         case RGCN_OPT_OVERLAP_WGRAD_CTAS: opts().wg_ctas = (int)value; return 0;
         case RGCN_OPT_OVERLAP_DX_CTAS: opts().dx_ctas = (int)value; return 0;
+        case RGCN_OPT_NVL_MODE: set_nvl_mode((int)value); return 0;
         default: return fail(RGCN_ERR_INVALID_ARG, "rgcn_set_option: unknown option");
     }
 }

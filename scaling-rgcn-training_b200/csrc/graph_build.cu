@@ -384,8 +384,11 @@ int share_chunks(const Brc& fwd, Brc& rel, int64_t n_own, int64_t n_gat, int R, 
 
 // Build one BRC from an entry list (owner local id, gather global id, relation, weight).
 // n_own owners (ranges of NR), chunk rows are numbered from n_gat (the gather row count).
+// The self loops belong to the owners [self_lo, self_hi) (all owners unless the structure is source-partitioned).
 int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const float* w_entry, int64_t n2,
-              int64_t n_own, int64_t n_gat, int R, int NR, int T, int CH, cudaStream_t st, Brc* out) {
+              int64_t n_own, int64_t n_gat, int R, int NR, int T, int CH, cudaStream_t st, Brc* out,
+              int64_t self_lo = 0, int64_t self_hi = -1) {
+    if (self_hi < 0) self_hi = n_own;
     const int64_t N = n_own;
     Brc b;
     b.num_entries0 = n2;
@@ -496,7 +499,9 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const 
         // self loops sort last: their groups (one per owner range) are the tail of the group list
         b.num_tiles_noself = NTL;
         if (G > 0) {
-            const int32_t first_self_group = G - (int32_t)nranges;
+            // (one self-loop group per owner range that holds self loops)
+            const int64_t self_groups = self_hi > self_lo ? (self_hi - 1) / NR - self_lo / NR + 1 : 0;
+            const int32_t first_self_group = G - (int32_t)self_groups;
             if (first_self_group >= 0)
                 RGCN_CUDA(cudaMemcpy(&b.num_tiles_noself, tile_base.p + first_self_group, 4, cudaMemcpyDeviceToHost));
         }
@@ -603,9 +608,10 @@ int build_side(const int32_t* own_g, const int32_t* gat_g, const int32_t* rel_g,
     const int64_t n_own = push ? num_all : n_sel;   // owner id space
     const int64_t n_gat = push ? n_sel : num_all;   // gather id space (chunk rows are numbered from here)
     int rc;
-    if ((rc = build_brc(own.p, gat.p, rel.p, w.p, n2, n_own, n_gat, R, NR, T, CH, st, blocked))) return rc;
+    const int64_t self_lo = push ? lo : 0, self_hi = push ? hi : n_sel;
+    if ((rc = build_brc(own.p, gat.p, rel.p, w.p, n2, n_own, n_gat, R, NR, T, CH, st, blocked, self_lo, self_hi))) return rc;
     if (relmajor && (rc = build_brc(own.p, gat.p, rel.p, w.p, n2, n_own, n_gat, R, (int)std::max<int64_t>(n_own, 1), T,
-                                    CH, st, relmajor)))
+                                    CH, st, relmajor, self_lo, self_hi)))
         return rc;
     return 0;
 }

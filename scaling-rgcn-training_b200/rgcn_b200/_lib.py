@@ -18,7 +18,7 @@ EXPORTS = (
     'rgcn_graph_export', 'rgcn_layer_workspace_bytes', 'rgcn_layer_fwd', 'rgcn_layer_bwd', 'rgcn_map_gather',
     'rgcn_kernel_launch_count', 'rgcn_profile_enable', 'rgcn_profile_collect', 'rgcn_pad_rows',
     'rgcn_eval_counts', 'rgcn_adam_step', 'rgcn_adam_step_dev', 'rgcn_layer_chunk_rows_bytes', 'rgcn_layer_fwd_keep',
-    'rgcn_layer_bwd_reuse', 'rgcn_set_option', 'rgcn_graph_create_push',
+    'rgcn_layer_bwd_reuse', 'rgcn_set_option', 'rgcn_graph_create_push', 'rgcn_nvl_store_rows', 'rgcn_nvl_reduce_rows',
 )
 
 BRC_FWD, BRC_BWD, BRC_FWD_REL = 0, 1, 2
@@ -27,8 +27,8 @@ Q_NUM_NODES, Q_NUM_EDGES, Q_NUM_RELATIONS, Q_NUM_SEGMENTS, Q_NUM_ENTRIES, Q_NUM_
     Q_NUM_TILES_NOSELF, Q_PUSH = range(16)
 A_PERM, A_SEG_PTR, A_SEG_OWN, A_SEG_REL, A_SEG_PTR0, A_E_IDX, A_E_W, A_RAW_IDX, A_RAW_W, A_CHUNK_BEG, \
     A_CHUNK_END, A_BAT_SEG0, A_BAT_INFO, A_E_OWN, A_TILE_E0, A_TILE_INFO, A_CHUNK_OUT = range(17)
-F_RELU_IN, F_FORCE_SIMPLE = 1, 2
-OPT_OVERLAP, OPT_OVERLAP_WGRAD_CTAS, OPT_OVERLAP_DX_CTAS = 0, 1, 2
+F_RELU_IN, F_FORCE_SIMPLE, F_NO_RELU_MASK = 1, 2, 4
+OPT_OVERLAP, OPT_OVERLAP_WGRAD_CTAS, OPT_OVERLAP_DX_CTAS, OPT_NVL_MODE = 0, 1, 2, 3
 
 _lib = None
 
@@ -86,6 +86,10 @@ def load():
     lib.rgcn_adam_step_dev.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
     lib.rgcn_pad_rows.restype = C.c_int
     lib.rgcn_pad_rows.argtypes = [vp, i64, i32, vp, i64, i64, vp]
+    lib.rgcn_nvl_store_rows.restype = C.c_int
+    lib.rgcn_nvl_store_rows.argtypes = [vp, i64, i32, vp, i64, vp, vp, i32, i64, i64, i64, vp]
+    lib.rgcn_nvl_reduce_rows.restype = C.c_int
+    lib.rgcn_nvl_reduce_rows.argtypes = [vp, vp, i32, i64, i64, i64, vp, i64, i32, vp]
     lib.rgcn_set_option.restype = C.c_int
     lib.rgcn_set_option.argtypes = [i32, i64]
     lib.rgcn_kernel_launch_count.restype = i64
@@ -105,7 +109,7 @@ def check(rc: int, what: str = '') -> None:
 
 
 PASS_NAMES = {1: 'wprep', 2: 'chunk_prepass', 3: 'tile_fwd', 4: 'tile_dx', 5: 'wgrad', 6: 'copy_cols', 7: 'relu_mask',
-              8: 'generic', 9: 'map_gather', 10: 'self_loop'}
+              8: 'generic', 9: 'map_gather', 10: 'self_loop', 11: 'nvl_store', 12: 'nvl_reduce'}
 
 
 def set_option(option: int, value: int) -> None:

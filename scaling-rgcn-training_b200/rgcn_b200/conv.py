@@ -44,7 +44,7 @@ class _RGCNLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x: Tensor, weight: Tensor, root: Optional[Tensor], bias: Optional[Tensor],
-                graph: RGCNGraph, flags: int, comm=None) -> Tensor:
+                graph: RGCNGraph, flags: int, comm=None, comm_key=None) -> Tensor:
         # comm (partitioned graphs only): object with all_gather_rows(t) -> [N, F] and
         # all_reduce_sum_(list of tensors); x then holds the OWNED rows and is all-gathered here.
         lib = _lib.load()
@@ -91,9 +91,7 @@ class _RGCNLayerFn(torch.autograd.Function):
         ldo = (fout + 3) // 4 * 4
         if push:
             # partial output over ALL nodes (padded to world * chunk rows for the reduce-scatter)
-            out_buf = torch.empty((comm.world * comm.chunk, ldo), dtype=torch.float32, device=x.device)
-            if out_buf.size(0) > graph.num_nodes:
-                out_buf[graph.num_nodes:].zero_()
+            out_buf = comm.partial_buffer(ldo, comm_key, x.device)
         else:
             out_buf = torch.empty((graph.num_owned, ldo), dtype=torch.float32, device=x.device)
         out = out_buf[:, :fout] if ldo != fout else out_buf
@@ -111,11 +109,11 @@ class _RGCNLayerFn(torch.autograd.Function):
                                          _stream(x.device))
         _lib.check(rc, 'rgcn_layer_fwd')
         if push:   # sum of the ranks' partials, each rank keeping its own rows
-            out_buf = comm.reduce_scatter_rows(out_buf)[:graph.num_owned]
+            out_buf = comm.reduce_scatter_rows(out_buf, comm_key)[:graph.num_owned]
             out = out_buf[:, :fout] if ldo != fout else out_buf
         if mirror is not None:
             x = mirror              # what backward re-gathers; the caller's tensor is not kept
-        ctx.graph, ctx.flags, ctx.comm, ctx.fin = graph, flags, comm, fin
+        ctx.graph, ctx.flags, ctx.comm, ctx.fin, ctx.comm_key = graph, flags, comm, fin, comm_key
         ctx.x_chunk_rows = xc
         ctx.has_root, ctx.has_bias = root is not None, bias is not None
         ctx.save_for_backward(x, weight, root_c if root_c is not None else x.new_empty(0))
@@ -138,12 +136,20 @@ class _RGCNLayerFn(torch.autograd.Function):
         # partitioned graph: the all-gather of gout (needed only by dL/dx) is started first and
         # overlaps the dL/dW pass, which reads the owned rows only
         gout_all, work = None, None
+        fuse_mask = False
         if comm is not None and graph.push:
             # source-partitioned: dL/dW and dL/dx both read the rows of all destinations
             if need_x or need_w or need_root or need_bias:
-                gout_all = comm.all_gather_rows(gout)
+                ho = getattr(comm, 'handoff', None)
+                if ho is not None and ho[0] == gout.data_ptr() and ho[1] == tuple(gout.shape):
+                    gout_all = ho[2]          # the layer above exchanged its gx while it wrote it
+                    comm.handoff = None
+                else:
+                    gout_all = comm.all_gather_rows(gout, ('g', ctx.comm_key))
+            # ReLU backward of the fused inter-layer activation rides on the exchange of gx (engine comm only)
+            fuse_mask = need_x and bool(ctx.flags & _lib.F_RELU_IN) and hasattr(comm, 'handoff')
         elif comm is not None and need_x:
-            if hasattr(comm, 'all_gather_rows_async'):
+            if getattr(comm, 'all_gather_rows_async', None) is not None:
                 gout_all, work = comm.all_gather_rows_async(gout)
             else:
                 gout_all = comm.all_gather_rows(gout)
@@ -159,11 +165,20 @@ class _RGCNLayerFn(torch.autograd.Function):
                 rc = lib.rgcn_layer_bwd_reuse(graph.handle, x.data_ptr(), x.stride(0), fin, weight.data_ptr(), _ptr(root),
                                               gout.data_ptr(), gout.stride(0), _ptr(gout_all),
                                               gout_all.stride(0) if gout_all is not None else 0, fout, _ptr(gx_t), fin,
-                                              _ptr(gw_t), _ptr(groot_t), _ptr(gbias_t), ctx.flags, ws.data_ptr(),
+                                              _ptr(gw_t), _ptr(groot_t), _ptr(gbias_t),
+                                              ctx.flags | (_lib.F_NO_RELU_MASK if fuse_mask else 0), ws.data_ptr(),
                                               ws_bytes, _ptr(ctx.x_chunk_rows), _stream(dev))
             _lib.check(rc, 'rgcn_layer_bwd')
 
-        if work is not None and (need_w or need_root or need_bias):
+        if fuse_mask:
+            # dL/dx first; its rows are masked and stored into every rank's copy by ONE kernel, and the exchange
+            # is in flight while dL/dW runs; the layer below picks the gathered rows up (comm.handoff)
+            call(gx, None, None, None)
+            gathered = comm.all_gather_rows(gx, ('g', 'below', ctx.comm_key), relu_pre=x)
+            comm.handoff = (gx.data_ptr(), tuple(gx.shape), gathered)
+            if need_w or need_root or need_bias:
+                call(None, gw, groot, gbias)
+        elif work is not None and (need_w or need_root or need_bias):
             call(None, gw, groot, gbias)      # runs while the all-gather is in flight
             work.wait()
             call(gx, None, None, None)
@@ -173,15 +188,15 @@ class _RGCNLayerFn(torch.autograd.Function):
             call(gx, gw, groot, gbias)
         if comm is not None:
             comm.all_reduce_sum_([t for t in (gw, groot, gbias) if t is not None])
-        return gx, gw, groot, gbias, None, None, None
+        return gx, gw, groot, gbias, None, None, None, None
 
 
 def rgcn_layer(x: Tensor, weight: Tensor, root: Optional[Tensor], bias: Optional[Tensor], graph: RGCNGraph,
-               relu_in: bool = False, force_simple: bool = False, comm=None) -> Tensor:
+               relu_in: bool = False, force_simple: bool = False, comm=None, comm_key=None) -> Tensor:
     flags = (_lib.F_RELU_IN if relu_in else 0) | (_lib.F_FORCE_SIMPLE if force_simple else 0)
     if comm is None and graph.num_owned != graph.num_nodes:
         raise ValueError('rgcn_layer: a partitioned graph needs comm= (see rgcn_b200.partition)')
-    return _RGCNLayerFn.apply(x, weight, root, bias, graph, flags, comm)
+    return _RGCNLayerFn.apply(x, weight, root, bias, graph, flags, comm, comm_key)
 
 
 class RGCNConv(nn.Module):

@@ -36,16 +36,42 @@ def plan_ranges(num_nodes: int, world: int) -> Tuple[int, List[Tuple[int, int]]]
     return chunk, ranges
 
 
+def plan_ranges_balanced(node_weight, world: int) -> List[Tuple[int, int]]:
+    """Contiguous node ranges with (nearly) equal total weight — e.g. out-degree + 1, the work a node brings to
+    the rank that owns it in the source-partitioned layers (balance by edges, not by
+    nodes: the hubs make equal node ranges ~9 % uneven at 8 ranks).  Range ends are rounded to multiples of 4
+    nodes (16-byte row blocks) and every range keeps at least one node."""
+    import numpy as np
+    w = np.asarray(node_weight, dtype=np.float64)
+    n = int(w.size)
+    if world < 1 or n < world:
+        raise ValueError('plan_ranges_balanced: need 1 <= world <= num_nodes')
+    csum = np.cumsum(w)
+    cuts = [0]
+    for p in range(1, world):
+        c = int(np.searchsorted(csum, csum[-1] * p / world, side='left')) + 1
+        c = (c + 3) // 4 * 4
+        c = max(c, cuts[-1] + 1)
+        c = min(c, n - (world - p))
+        cuts.append(c)
+    cuts.append(n)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
 class RowComm:
     """The two collectives of the partitioned layer, over any torch.distributed backend
     (nccl on the GPUs; gloo in the CPU tests of this host logic)."""
 
-    def __init__(self, num_nodes: int, group=None) -> None:
+    def __init__(self, num_nodes: int, group=None, ranges=None) -> None:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.num_nodes = num_nodes
         self.chunk, self.ranges = plan_ranges(num_nodes, self.world)
+        if ranges is not None:
+            if type(self) is RowComm and list(ranges) != self.ranges:
+                raise ValueError('RowComm (NCCL collectives) needs equal node ranges; NvlComm takes any')
+            self.ranges = [(int(a), int(b)) for a, b in ranges]
         self.lo, self.hi = self.ranges[self.rank]
         self.bytes_gathered = 0
         self.bytes_reduced = 0
@@ -65,7 +91,7 @@ class RowComm:
         self.bytes_gathered += out.numel() * out.element_size()
         return out, work
 
-    def all_gather_rows(self, t: Tensor) -> Tensor:
+    def all_gather_rows(self, t: Tensor, key=None) -> Tensor:
         """[n_owned, F] on every rank -> [world*chunk, F]; row i is node i for i < num_nodes."""
         n_own, f = t.shape
         if n_own != self.hi - self.lo:
@@ -81,7 +107,15 @@ class RowComm:
         self.bytes_gathered += out.numel() * out.element_size()
         return out
 
-    def reduce_scatter_rows(self, t: Tensor) -> Tensor:
+    def partial_buffer(self, cols: int, key=None, device=None) -> Tensor:
+        """[world*chunk, cols] buffer a source-partitioned layer accumulates its partial output into (rows >=
+        num_nodes are zero); reduce_scatter_rows takes it back."""
+        t = torch.empty((self.world * self.chunk, cols), dtype=torch.float32, device=device)
+        if t.size(0) > self.num_nodes:
+            t[self.num_nodes:].zero_()
+        return t
+
+    def reduce_scatter_rows(self, t: Tensor, key=None) -> Tensor:
         """[world*chunk, F] partial sums on every rank -> [chunk, F]: this rank's rows of the total."""
         if t.size(0) != self.world * self.chunk:
             raise ValueError('reduce_scatter_rows: expected world * chunk rows')
@@ -123,6 +157,163 @@ class RowComm:
             off += t.numel()
 
 
+class NvlComm(RowComm):
+    """The same exchanges as the engine's own kernels over NVLink / NVSwitch peer memory (csrc/nvl_comm.cu)
+    instead of NCCL calls.  Buffers are symmetric allocations (torch.distributed._symmetric_memory: same size on
+    every rank, peer-mapped, with an NVSwitch multicast address):
+
+      all-gather      one multimem.st per 16 bytes of the rank's own rows -> the switch replicates them into every
+                      rank's copy; the ReLU backward of the inter-layer activation can ride on the same kernel
+      reduce-scatter  the layer kernels accumulate the rank's partial output straight into its copy
+                      (partial_buffer); after a barrier each rank reads ITS rows with multimem.ld_reduce.add.f32,
+                      the switch summing the P copies in flight
+      all-reduce      the same load-reduce over the flat parameter-gradient buffer
+
+    Ordering: every exchange is write -> device barrier over all ranks -> read (the barrier is the signal-pad
+    kernel of the symmetric-memory handle; everything is stream-ordered and CUDA-graph capturable).  In the
+    training loop one barrier per exchange is enough — a buffer is rewritten only after a LATER exchange's
+    barrier of the same step, which no rank passes before every rank has finished reading (`steady_state=True`,
+    what PartitionedRGCN's step satisfies: distinct buffers per call site, >= 1 other exchange between two uses
+    of a buffer).  `steady_state=False` adds a second barrier on the other side of every exchange.
+    Source-partitioned ("push") graphs only: nothing the layers save for backward may alias these buffers."""
+
+    def __init__(self, num_nodes: int, group=None, steady_state: bool = False, ranges=None) -> None:
+        super().__init__(num_nodes, group, ranges)
+        self.rows = (num_nodes + 3) // 4 * 4      # rows of every exchange buffer: ranges need not be equal here
+        import ctypes as C
+        import torch.distributed._symmetric_memory as sm
+        from . import _lib
+        self._C, self._sm, self._lib = C, sm, _lib.load()
+        self._check = _lib.check
+        self.steady_state = steady_state
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        self._bufs = {}
+        self._grp = self.group if self.group is not None else dist.group.WORLD
+        self._ctl = sm.empty((1024,), dtype=torch.float32, device=self.device)
+        self._ctl_h = sm.rendezvous(self._ctl, self._grp)
+        try:
+            self.multicast = int(self._ctl_h.multicast_ptr) != 0
+        except Exception:
+            self.multicast = False
+        # multicast (multimem.*) or plain peer pointers: measured on 2 B200s the peer-pointer kernels move the
+        # 16-wide rows at 560 GB/s against 305 GB/s through the 2-member multicast group; with more ranks the
+        # multicast store sends the shard once instead of P-1 times (RGCN_B200_NVL_MODE: 1 multicast, 2 peers)
+        mode = os.environ.get('RGCN_B200_NVL_MODE')
+        self.mode = int(mode) if mode else (1 if self.multicast and self.world > 2 else 2)
+        _lib.set_option(_lib.OPT_NVL_MODE, self.mode)
+        self.handoff = None          # (data_ptr of an exchanged tensor, its gathered rows): see all_gather_rows
+
+    def barrier(self) -> None:
+        self._ctl_h.barrier(0)
+
+    def _symm(self, key, rows: int, cols: int):
+        ent = self._bufs.get(key)
+        if ent is None or tuple(ent[0].shape) != (rows, cols):
+            t = self._sm.empty((rows, cols), dtype=torch.float32, device=self.device)
+            h = self._sm.rendezvous(t, self._grp)          # collective: every rank asks for the same keys in order
+            peers = (self._C.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs])
+            mc = int(h.multicast_ptr) if self.multicast else 0
+            t.zero_()
+            ent = (t, h, mc, peers)
+            self._bufs[key] = ent
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+        return ent
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def all_gather_rows(self, t: Tensor, key=None, relu_pre: Optional[Tensor] = None) -> Tensor:
+        """[n_owned, F] -> [world*chunk, F] (a view of the symmetric buffer, rows 16-byte addressable: the row
+        stride is F rounded up to 4).  relu_pre: zero t where relu_pre <= 0 first, in the same kernel."""
+        n_own, f = t.shape
+        if n_own != self.hi - self.lo or t.stride(1) != 1:
+            raise ValueError('all_gather_rows: wrong number of owned rows / non-unit column stride')
+        ld = (f + 3) // 4 * 4
+        buf, _, mc, peers = self._symm(('ag', key if key is not None else f, ld), self.rows, ld)
+        if not self.steady_state:
+            self.barrier()
+        rc = self._lib.rgcn_nvl_store_rows(t.data_ptr(), t.stride(0), f,
+                                           relu_pre.data_ptr() if relu_pre is not None else None,
+                                           relu_pre.stride(0) if relu_pre is not None else 0,
+                                           mc if mc else None, peers, self.world, ld, self.lo, n_own, self._stream())
+        self._check(rc, 'rgcn_nvl_store_rows')
+        self.barrier()
+        self.bytes_gathered += buf.numel() * 4
+        return buf[:, :f] if ld != f else buf
+
+    all_gather_rows_async = None          # (no NCCL work handle: the exchange is stream-ordered)
+
+    def partial_buffer(self, cols: int, key=None, device=None) -> Tensor:
+        if cols % 4:
+            raise ValueError('partial_buffer: width must be a multiple of 4')
+        return self._symm(('rs', key if key is not None else cols, cols), self.rows, cols)[0]
+
+    def reduce_scatter_rows(self, t: Tensor, key=None) -> Tensor:
+        cols = t.size(1)
+        buf, _, mc, peers = self._symm(('rs', key if key is not None else cols, cols), self.rows, cols)
+        if t.data_ptr() != buf.data_ptr():
+            raise ValueError('reduce_scatter_rows: pass the tensor partial_buffer() returned')
+        self.barrier()
+        n_own = self.hi - self.lo
+        out = torch.empty((n_own, cols), dtype=torch.float32, device=self.device)
+        rc = self._lib.rgcn_nvl_reduce_rows(mc if mc else None, peers, self.world, cols, self.lo, n_own, out.data_ptr(),
+                                            cols, cols, self._stream())
+        self._check(rc, 'rgcn_nvl_reduce_rows')
+        if not self.steady_state:
+            self.barrier()
+        self.bytes_reduced += buf.numel() * 4
+        return out
+
+    def all_reduce_sum_(self, tensors: List[Tensor]) -> None:
+        tensors = [t for t in tensors if t is not None]
+        if not tensors or self.world == 1:
+            return
+        n = sum(t.numel() for t in tensors)
+        width = 256
+        rows = (n + width - 1) // width
+        buf, _, mc, peers = self._symm(('ar', rows), rows, width)
+        flat = buf.view(-1)
+        off = 0
+        for t in tensors:
+            flat[off:off + t.numel()].copy_(t.reshape(-1))
+            off += t.numel()
+        self.barrier()
+        out = torch.empty((rows, width), dtype=torch.float32, device=self.device)
+        rc = self._lib.rgcn_nvl_reduce_rows(mc if mc else None, peers, self.world, width, 0, rows, out.data_ptr(), width,
+                                            width, self._stream())
+        self._check(rc, 'rgcn_nvl_reduce_rows')
+        if not self.steady_state:
+            self.barrier()
+        res = out.view(-1)
+        off = 0
+        for t in tensors:
+            t.copy_(res[off:off + t.numel()].view_as(t))
+            off += t.numel()
+
+
+def comm_backend(backend: Optional[str] = None) -> str:
+    backend = backend or os.environ.get('RGCN_B200_COMM', 'nvl' if torch.cuda.is_available() else 'nccl')
+    if backend not in ('nvl', 'nccl'):
+        raise ValueError('RGCN_B200_COMM must be nvl or nccl')
+    return backend
+
+
+def make_comm(num_nodes: int, backend: Optional[str] = None, steady_state: bool = False, ranges=None) -> RowComm:
+    """RGCN_B200_COMM=nvl (default on CUDA: engine kernels over NVLink multicast) | nccl (torch.distributed calls)."""
+    if comm_backend(backend) == 'nvl':
+        return NvlComm(num_nodes, steady_state=steady_state, ranges=ranges)
+    return RowComm(num_nodes)
+
+
+def balanced_ranges_for(edge_index: Tensor, num_nodes: int, world: int) -> List[Tuple[int, int]]:
+    """Node ranges balanced by the work of the source-partitioned layers: out-degree (every pass walks the edges
+    whose src is owned) + 1 for the node's own row."""
+    import numpy as np
+    deg = np.bincount(edge_index[0].numpy(), minlength=num_nodes).astype(np.float64)
+    return plan_ranges_balanced(deg + 1.0, world)
+
+
 class PartitionedRGCN(nn.Module):
     """2-layer R-GCN (Emb_Layers arithmetic, reference model/layers.py:20-25) on a partitioned
     graph: sharded embedding rows, replicated layer weights, fused inter-layer ReLU.  The graph decides the
@@ -147,8 +338,8 @@ class PartitionedRGCN(nn.Module):
     def forward(self) -> Tensor:
         from .conv import rgcn_layer
         c1, c2 = self.rgcn1, self.rgcn2
-        h = rgcn_layer(self.embedding, c1.weight, c1.root, c1.bias, self.graph, comm=self.comm)
-        return rgcn_layer(h, c2.weight, c2.root, c2.bias, self.graph, relu_in=True, comm=self.comm)
+        h = rgcn_layer(self.embedding, c1.weight, c1.root, c1.bias, self.graph, comm=self.comm, comm_key=1)
+        return rgcn_layer(h, c2.weight, c2.root, c2.bias, self.graph, relu_in=True, comm=self.comm, comm_key=2)
 
 
 def partition_mode() -> str:
@@ -159,7 +350,7 @@ def partition_mode() -> str:
 
 
 def partitioned_parity_check(rank: int, world: int, device, mode: str, hidden: int, classes: int, emb: int,
-                             scale: float = 1 / 16) -> Optional[dict]:
+                             scale: float = 1 / 16, backend: Optional[str] = None) -> Optional[dict]:
     """bench.py --gpus N, N > 1: the partitioned fwd+bwd on the AM-shape graph at `scale` against the SAME step on
     one GPU (rank 0, unpartitioned graph): max-norm relative errors of the output, the embedding gradient and all
     parameter gradients.  Proves on the measuring box that the N-rank path computes what the 1-rank path does."""
@@ -167,7 +358,9 @@ def partitioned_parity_check(rank: int, world: int, device, mode: str, hidden: i
     from .graph import RGCNGraph
     from .synthetic import am_shape
     ei, et, n, r = am_shape(scale=scale)
-    comm = RowComm(n)
+    nvl = mode == 'push' and comm_backend(backend) == 'nvl'
+    comm = make_comm(n, backend, steady_state=False, ranges=balanced_ranges_for(ei, n, world) if nvl else None) \
+        if mode == 'push' else RowComm(n)
     ei_d, et_d = ei.to(device), et.to(device)
     graph = RGCNGraph(ei_d, et_d, n, r, own_range=(comm.lo, comm.hi), push=(mode == 'push'))
     model = PartitionedRGCN(graph, comm, r, hidden, classes, emb, seed=7).to(device)
@@ -175,8 +368,12 @@ def partitioned_parity_check(rank: int, world: int, device, mode: str, hidden: i
     gout_full = torch.randn(n, classes, generator=gen)
     out = model()
     out.backward(gout_full[comm.lo:comm.hi].to(device))
-    out_all = comm.all_gather_rows(out.detach().contiguous())[:n]
-    gx_all = comm.all_gather_rows(model.embedding.grad.contiguous())[:n]
+    def gather_all(t):          # (the comparison itself gathers over NCCL; ranges may be unequal)
+        parts = [torch.empty((b - a, t.size(1)), dtype=t.dtype, device=t.device) for a, b in comm.ranges]
+        dist.all_gather(parts, t.contiguous())
+        return torch.cat(parts)
+    out_all = gather_all(out.detach())
+    gx_all = gather_all(model.embedding.grad)
     res = None
     if rank == 0:
         g1 = RGCNGraph(ei_d, et_d, n, r)
@@ -215,7 +412,10 @@ def run_partitioned_bench(args, rank: int, world: int, device, metric: str, unit
         parity = partitioned_parity_check(rank, world, device, mode, B.HIDDEN, B.CLASSES, B.EMB)
     ei, et, n, r = am_shape(scale=args.scale)                # every rank derives the same graph (seed 0)
     e = et.numel()
-    comm = RowComm(n)
+    nvl = mode == 'push' and comm_backend() == 'nvl'
+    comm = make_comm(n, steady_state=True, ranges=balanced_ranges_for(ei, n, world) if nvl else None) \
+        if mode == 'push' else RowComm(n)
+    backend = 'nvl' if isinstance(comm, NvlComm) else 'nccl'
     t0 = time.perf_counter()
     ei_d, et_d = ei.to(device), et.to(device)
     graph = RGCNGraph(ei_d, et_d, n, r, own_range=(comm.lo, comm.hi), push=(mode == 'push'))
@@ -252,6 +452,25 @@ def run_partitioned_bench(args, rank: int, world: int, device, metric: str, unit
     torch.cuda.synchronize(device)
     sync_ms = comm.comm_ms() / 3
     comm.events = None
+    # per-pass device times of one eager step with the concurrent passes serialised (rank 0's view)
+    _lib.set_option(_lib.OPT_OVERLAP, 0)
+    _lib.profile_enable(True)
+    _lib.profile_collect()
+    step()
+    torch.cuda.synchronize(device)
+    prof = {}
+    for name, dims, pms in _lib.profile_collect():
+        k = f'{name}_{dims[0]}x{dims[1]}'
+        prof[k] = prof.get(k, 0.0) + pms
+    _lib.profile_enable(False)
+    _lib.set_option(_lib.OPT_OVERLAP, 1)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(5):
+        step()
+    ev[1].record()
+    torch.cuda.synchronize(device)
+    eager_ms = ev[0].elapsed_time(ev[1]) / 5
     cuda_graph = None
     run = step
     if use_graph:
@@ -346,7 +565,9 @@ def run_partitioned_bench(args, rank: int, world: int, device, metric: str, unit
     if rank == 0:
         if mode == 'push':
             coll = ('per layer: reduce_scatter(partial out) fwd, all_gather(gout) bwd; one all_reduce of dW/droot/dbias; '
-                    'the 63-wide layer-1 input is never exchanged')
+                    'the 63-wide layer-1 input is never exchanged; ' +
+                    ('engine kernels over NVSwitch multicast (multimem.st / multimem.ld_reduce), one device barrier each'
+                     if backend == 'nvl' else 'NCCL calls'))
             limiting = 'all_gather(gout of layer 1, 16 wide) + reduce_scatter(partial h1, 16 wide)'
         else:
             coll = 'per layer: all_gather(x) fwd, all_gather(gout) bwd; one all_reduce of dW/droot/dbias'
@@ -357,13 +578,15 @@ def run_partitioned_bench(args, rank: int, world: int, device, metric: str, unit
             'data': 'synthetic',
             'config': {'workload': 'am_shape_full_graph_rgcn_63_16_11_all_grads', 'scale': args.scale, 'nodes': n,
                        'directed_edges': e, 'relations': r,
-                       'partition': f'{"source" if mode == "push" else "dst"}-partitioned x{world}, equal node ranges',
-                       'collectives': coll, 'limiting_collective': limiting,
+                       'partition': f'{"source" if mode == "push" else "dst"}-partitioned x{world}, ' +
+                                    ('node ranges balanced by out-degree' if backend == 'nvl' else 'equal node ranges'),
+                       'collectives': coll, 'comm_backend': backend, 'limiting_collective': limiting,
                        'all_gather_bytes_per_step_per_rank': gathered,
                        'reduce_scatter_bytes_per_step_per_rank': reduced,
                        'max_rank_edges': int(mx.item()), 'mean_rank_edges': e / world,
                        'sync_collectives_ms_per_step_rank0_eager': sync_ms,
                        'step_launch': 'cuda graph replay (collectives captured)' if use_graph else 'eager',
+                       'ms_per_step_eager': eager_ms, 'passes_rank0_serialised_ms': prof,
                        'graph_build_ms_once': setup_ms,
                        'l2_policy': 'inputs larger than L2; no flush'},
             'parity': parity,

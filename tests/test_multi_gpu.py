@@ -40,13 +40,31 @@ def _worker(rank, world, port, ret):
         def rel(a, b):
             return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
         errs = []
-        for push in (False, True):      # destination-partitioned (all-gather) and source-partitioned (reduce-scatter)
+        from rgcn_b200.partition import NvlComm
+        nvl = NvlComm(n)                # the engine's own exchanges over NVLink multicast / peer memory
+        # destination-partitioned (all-gather), source-partitioned (reduce-scatter) over NCCL, and source-
+        # partitioned over the engine's exchange kernels
+        for push, c in ((False, comm), (True, comm), (True, nvl)):
             g = RGCNGraph(ei, et, n, r, own_range=(comm.lo, comm.hi), push=push)
             part = [x[comm.lo:comm.hi].clone().requires_grad_()] + [t.clone().requires_grad_() for t in (w, root, bias)]
-            out = rgcn_layer(*part, g, comm=comm)
+            out = rgcn_layer(*part, g, comm=c)
             out.backward(gout[comm.lo:comm.hi])
             errs += [rel(out, ref[comm.lo:comm.hi]), rel(part[0].grad, full[0].grad[comm.lo:comm.hi])]
             errs += [rel(a.grad, b.grad) for a, b in zip(part[1:], full[1:])]
+        # two layers with the fused ReLU: the mask rides on the exchange of the upper layer's gx (handoff)
+        w2 = (torch.rand(r, 16, 11, device=dev) - 0.5) * 0.5
+        f2 = [t.clone().requires_grad_() for t in (x, w, root, bias, w2)]
+        g1 = RGCNGraph(ei, et, n, r)
+        ref2 = rgcn_layer(rgcn_layer(f2[0], f2[1], f2[2], f2[3], g1), f2[4], None, None, g1, relu_in=True)
+        gout2 = torch.randn(n, 11, device=dev)
+        ref2.backward(gout2)
+        g = RGCNGraph(ei, et, n, r, own_range=(comm.lo, comm.hi), push=True)
+        p2 = [x[comm.lo:comm.hi].clone().requires_grad_()] + [t.clone().requires_grad_() for t in (w, root, bias, w2)]
+        out2 = rgcn_layer(rgcn_layer(p2[0], p2[1], p2[2], p2[3], g, comm=nvl, comm_key=1), p2[4], None, None, g,
+                          relu_in=True, comm=nvl, comm_key=2)
+        out2.backward(gout2[comm.lo:comm.hi])
+        errs += [rel(out2, ref2[comm.lo:comm.hi]), rel(p2[0].grad, f2[0].grad[comm.lo:comm.hi])]
+        errs += [rel(a.grad, b.grad) for a, b in zip(p2[1:], f2[1:])]
         ret[rank] = max(errs)
     finally:
         dist.destroy_process_group()

@@ -24,6 +24,25 @@ def test_plan_ranges():
         plan_ranges(3, 8)
 
 
+def test_plan_ranges_balanced():
+    import numpy as np
+    from rgcn_b200.partition import plan_ranges_balanced
+    rng = np.random.default_rng(0)
+    w = np.minimum(rng.zipf(2.0, size=10007), 500).astype(np.float64)          # hubs
+    for world in (2, 3, 8):
+        r = plan_ranges_balanced(w, world)
+        assert r[0][0] == 0 and r[-1][1] == w.size and all(a < b for a, b in r)
+        assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+        assert all(b % 4 == 0 for _, b in r[:-1])
+        loads = np.array([w[a:b].sum() for a, b in r])
+        equal = np.array([w[a:b].sum() for a, b in [(i * w.size // world, (i + 1) * w.size // world) for i in range(world)]])
+        assert loads.max() <= loads.mean() + w.max() + 4 * w.mean()
+        assert loads.max() <= equal.max() + w.max()
+    assert plan_ranges_balanced(np.ones(5), 5) == [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5)]
+    with pytest.raises(ValueError):
+        plan_ranges_balanced(np.ones(3), 4)
+
+
 def _worker(rank, world, port, ret):
     for p in (REPO, PKG, ORACLE):
         sys.path.insert(0, p)
