@@ -185,8 +185,9 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
         // the fused pass emits root fragments in the vector K order and replaces the self-loop pass of the
         // entry-tile family, so it is taken only when the MIRROR will be gathered by k_etile with vector loads
         const bool mirror_v4 = etile_vec4_ok(x_mirror, ld_mirror, fin, aux);
+        // (x rows 0.. are the owned rows: the whole graph, or a source-partitioned rank's shard)
         fused_pad = !etile_vec4_ok(x, ldx, fin, aux) && mirror_v4 && etile_choice(kp, mirror_v4) &&
-                    selfloop_pad_ok(kp, np) && g->n_own == g->N;
+                    selfloop_pad_ok(kp, np) && (g->push || g->n_own == g->N);
         if (!fused_pad && (rc = launch_pad_rows(x, ldx, fin, x_mirror, ld_mirror, n_gat, st))) return rc;
         x = x_mirror;
         ldx = ld_mirror;
@@ -225,18 +226,15 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
         }
         if ((rc = launch_wprep(wp, st))) return rc;
         // root + bias with plain stores (initialises the target; the fused variant also writes the mirror)
-        if (fused_pad) {
-            rc = launch_selfloop_pad(p, x_raw, ld_raw, x_mirror, ld_mirror, g->n_own, g->R, g->num_sms, st);
-        } else if (g->push) {
+        TilePass ps = p;
+        if (g->push) {
             // x holds the owned rows, the target the rows of ALL nodes: the rows this rank does not own start
             // from zero, the owned ones from root + bias
             RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)n_out * tld * 4, st));
-            TilePass ps = p;
             ps.out = target + g->own_lo * tld;
-            rc = launch_selfloop_pass(ps, 0, g->n_own, g->R, g->num_sms, st);
-        } else {
-            rc = launch_selfloop_pass(p, g->own_lo, g->n_own, g->R, g->num_sms, st);
         }
+        if (fused_pad) rc = launch_selfloop_pad(ps, x_raw, ld_raw, x_mirror, ld_mirror, g->n_own, g->R, g->num_sms, st);
+        else rc = launch_selfloop_pass(ps, g->push ? 0 : g->own_lo, g->n_own, g->R, g->num_sms, st);
         if (rc) return rc;
         if (ovl) {
             if ((rc = fk.end())) return rc;

@@ -71,9 +71,9 @@ class _RGCNLayerFn(torch.autograd.Function):
         if comm is not None:
             if x.dim() != 2 or x.size(0) != graph.num_owned:
                 raise ValueError(f'RGCNConv (partitioned): x must hold the {graph.num_owned} owned rows')
-            x = pad_rows(x.contiguous())                     # the owned shard, 16-byte addressable
-            if not push:
-                x = comm.all_gather_rows(x)                  # pull: every rank needs the rows of all sources
+            x = x.contiguous()
+            if not push:                                     # pull: every rank needs the rows of all sources
+                x = comm.all_gather_rows(pad_rows(x))        # (the owned shard made 16-byte addressable first)
         if not push and (x.dim() != 2 or x.size(0) < graph.num_nodes or (comm is None and x.size(0) != graph.num_nodes)):
             raise ValueError(f'RGCNConv: x must be [num_nodes={graph.num_nodes}, in_channels]')
         x = x if x.stride(1) == 1 or x.size(1) == 1 else x.contiguous()
@@ -86,7 +86,7 @@ class _RGCNLayerFn(torch.autograd.Function):
             raise ValueError('RGCNConv: weight shape does not match input / num_relations')
         # unpartitioned: the engine writes the mirror itself (fused with the root pass where it can)
         mirror = None
-        if comm is None and _PAD_WIDE and 32 < fin <= 64 and (x.stride(0) % 4 != 0 or x.data_ptr() % 16 != 0):
+        if (comm is None or push) and _PAD_WIDE and 32 < fin <= 64 and (x.stride(0) % 4 != 0 or x.data_ptr() % 16 != 0):
             mirror = torch.empty((x.size(0), (fin + 3) // 4 * 4), dtype=torch.float32, device=x.device)
         ldo = (fout + 3) // 4 * 4
         if push:
@@ -174,10 +174,17 @@ class _RGCNLayerFn(torch.autograd.Function):
             # dL/dx first; its rows are masked and stored into every rank's copy by ONE kernel, and the exchange
             # is in flight while dL/dW runs; the layer below picks the gathered rows up (comm.handoff)
             call(gx, None, None, None)
+            cur = torch.cuda.current_stream(dev)
+            side = None
+            if need_w or need_root or need_bias:          # dL/dW on a side stream, under the exchange
+                side = comm.side_stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    call(None, gw, groot, gbias)
             gathered = comm.all_gather_rows(gx, ('g', 'below', ctx.comm_key), relu_pre=x)
             comm.handoff = (gx.data_ptr(), tuple(gx.shape), gathered)
-            if need_w or need_root or need_bias:
-                call(None, gw, groot, gbias)
+            if side is not None:
+                cur.wait_stream(side)
         elif work is not None and (need_w or need_root or need_bias):
             call(None, gw, groot, gbias)      # runs while the all-gather is in flight
             work.wait()

@@ -206,6 +206,12 @@ class NvlComm(RowComm):
     def barrier(self) -> None:
         self._ctl_h.barrier(0)
 
+    def side_stream(self):
+        """Stream for compute that may run under an exchange (dL/dW of the upper layer while its gx is stored)."""
+        if getattr(self, '_side', None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def _symm(self, key, rows: int, cols: int):
         ent = self._bufs.get(key)
         if ent is None or tuple(ent[0].shape) != (rows, cols):

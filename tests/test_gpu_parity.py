@@ -364,7 +364,7 @@ class _LocalComm:
     def set_full(self, key_rows, full):
         self.table[key_rows] = full
 
-    def all_gather_rows(self, t):
+    def all_gather_rows(self, t, key=None):
         # the layer gathers the zero-padded 16-byte aligned mirror of odd-width rows (63 -> 64)
         full = self.table.get(t.size(1), self.table.get(t.size(1) - 1))
         out = full.new_zeros((self.world * self.chunk, t.size(1)))
@@ -377,7 +377,10 @@ class _LocalComm:
     # source-partitioned ("push") layers: the rank's partial over all nodes is kept for the test to sum; what
     # comes back are this rank's rows of the true total (supplied by the test), so autograd continues from
     # exactly what a real reduce-scatter would deliver
-    def reduce_scatter_rows(self, t):
+    def partial_buffer(self, cols, key=None, device=None):
+        return torch.zeros((self.world * self.chunk, cols), dtype=torch.float32, device=device)
+
+    def reduce_scatter_rows(self, t, key=None):
         self.partials.append(t.detach().clone())
         lo = self.rank * self.chunk
         out = t.new_zeros((self.chunk, t.size(1)))
