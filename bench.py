@@ -203,6 +203,38 @@ def cpu_reference(steps: int, warmup: int, scale: float, threads: int):
     return e / dt, dt * 1e3, n, e, sample
 
 
+def oracle_parity_check(device, scale: float = 1 / 64):
+    """The engine's two layers (63 -> 16 -> 11, fused ReLU), output and ALL gradients, against the CPU oracle
+    (oracle/rgcn_oracle.py: the reference's PyG loop path restated) on the AM-shape generator at `scale`."""
+    sys.path.insert(0, os.path.join(REPO, 'oracle'))
+    import rgcn_oracle                                 # the checker, not the thing measured
+    from rgcn_b200 import RGCNGraph, rgcn_layer
+    from rgcn_b200.synthetic import am_shape
+    ei, et, n, r = am_shape(scale=scale)
+    torch.manual_seed(4)
+    p = [torch.randn(n, EMB), (torch.rand(r, EMB, HIDDEN) - 0.5) * 0.3, (torch.rand(EMB, HIDDEN) - 0.5) * 0.3,
+         torch.rand(HIDDEN) - 0.5, (torch.rand(r, HIDDEN, CLASSES) - 0.5) * 0.5, (torch.rand(HIDDEN, CLASSES) - 0.5) * 0.5,
+         torch.rand(CLASSES) - 0.5]
+    gout = torch.randn(n, CLASSES)
+    ref = [t.clone().requires_grad_() for t in p]
+    want = rgcn_oracle.rgcn_forward(torch.relu(rgcn_oracle.rgcn_forward(ref[0], ei, et, ref[1], ref[2], ref[3])), ei, et,
+                                    ref[4], ref[5], ref[6])
+    want.backward(gout)
+    g = RGCNGraph(ei.to(device), et.to(device), n, r)
+    dl = [t.clone().to(device).requires_grad_() for t in p]
+    out = rgcn_layer(rgcn_layer(dl[0], dl[1], dl[2], dl[3], g), dl[4], dl[5], dl[6], g, relu_in=True)
+    out.backward(gout.to(device))
+
+    def rel(a, b):
+        return float((a.detach().cpu().double() - b.detach().double()).abs().max() / b.detach().abs().max().clamp_min(1e-30))
+    errs = {'out': rel(out, want)}
+    for name, a, b in zip(('gx', 'gW1', 'groot1', 'gbias1', 'gW2', 'groot2', 'gbias2'), dl, ref):
+        errs[name] = rel(a.grad, b.grad)
+    return {'against': f'CPU oracle (PyG 2.3.1 loop path restated), AM-shape at scale {scale:g} (N={n}, E={et.numel()})',
+            'max_rel_err': errs, 'worst': max(errs.values()),
+            'argmax_equal': bool(torch.equal(out.argmax(1).cpu(), want.argmax(1)))}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -236,6 +268,9 @@ def run_engine(args):
     rank, world, local = dist_setup(args.gpus)
     device = torch.device('cuda', local)
     torch.cuda.set_device(device)
+    if args.workload == 'am10x_h64_bases30_frozenW':        # BASELINE.json configs[4]
+        from rgcn_b200 import workloads
+        return workloads.run(args, rank, world, device, METRIC, UNIT)
     if world > 1:
         from rgcn_b200 import partition
         return partition.run_partitioned_bench(args, rank, world, device, METRIC, UNIT)
@@ -277,17 +312,25 @@ def run_engine(args):
     for _ in range(args.warmup):
         layer_step()
     torch.cuda.synchronize(device)
-    _lib.profile_enable(True)
-    _lib.profile_collect()
+    # the headline: K steps as the library runs them (independent passes of a layer call overlap on the
+    # engine's side stream), CUDA events around the whole region
     launches0 = _lib.launch_count()
     sampler.start()
     total_ms = time_steps(layer_step, args.steps, 0, world, device)
     clocks = sampler.stop()
     launches = _lib.launch_count() - launches0
-    recs = _lib.profile_collect()
-    _lib.profile_enable(False)
     ms_per_step = total_ms / args.steps
     value = e / (ms_per_step * 1e-3)
+    # per-pass device times: the same K steps once more with the passes SERIALISED (overlap off) and an event
+    # pair around every launch, so that a pass's time is its own; the roofline of the dominant kernel uses these
+    _lib.set_option(_lib.OPT_OVERLAP, 0)
+    _lib.profile_enable(True)
+    _lib.profile_collect()
+    serial_ms = time_steps(layer_step, args.steps, 1, world, device) / args.steps
+    recs = _lib.profile_collect()
+    _lib.profile_enable(False)
+    _lib.set_option(_lib.OPT_OVERLAP, 1)
+    recs = recs[len(recs) - (len(recs) // (args.steps + 1)) * args.steps:]      # drop the warm-up step's records
 
     # dominant kernel and its roofline
     peak, peak_src = load_peaks()
@@ -318,7 +361,9 @@ def run_engine(args):
         roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
                     'frac': ach / peak, 'traffic': ncu_traffic(kname) if args.scale == 1.0 else None, 'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': pb[dom], 'avg_launch_ms': avg_ms,
-                    'share_of_step': tot[dom] / args.steps / ms_per_step}
+                    'share_of_step': tot[dom] / args.steps / serial_ms,
+                    'timing': 'CUDA-event pair around every launch, passes serialised (RGCN_OPT_OVERLAP 0), '
+                              f'{args.steps} steps; the step then takes {serial_ms:.3f} ms'}
     f1, b1 = algorithmic_bytes(n, e, EMB, HIDDEN)
     f2, b2 = algorithmic_bytes(n, e, HIDDEN, CLASSES)
     step_bytes = f1 + b1 + f2 + b2
@@ -326,6 +371,39 @@ def run_engine(args):
                                         'gbps_algorithmic': (pb[k] / (statistics.mean(v) * 1e-3) / 1e9) if k in pb else None,
                                         **({'of_which_self_loop_ms': self_ms[k]} if k in self_ms else {})}
               for k, v in sorted(agg.items())}
+
+    # frozen variants of BASELINE.md section 2 (-e_freeze True / -w_grad False), same graph and kernels
+    variants = {}
+    if not args.no_e2e:
+        emb_w = model.embedding.weight
+
+        def frozen_x0_step():
+            for p in params:
+                p.grad = None
+            h = rgcn_layer(emb_w.detach(), c1.weight, c1.root, c1.bias, graph)
+            rgcn_layer(h, c2.weight, c2.root, c2.bias, graph, relu_in=True).backward(gout)
+
+        wd = [t.detach() for t in (c1.weight, c1.root, c1.bias, c2.weight, c2.root, c2.bias)]
+
+        def frozen_x0_w_step():
+            with torch.no_grad():
+                h = rgcn_layer(emb_w, wd[0], wd[1], wd[2], graph)
+            h.requires_grad_(True)          # something upstream of layer 2 still wants dL/dh1 (a transfer head)
+            rgcn_layer(h, wd[3], wd[4], wd[5], graph, relu_in=True).backward(gout)
+
+        for name, fn, flags in (('frozen_x0', frozen_x0_step, (True, False, True, True)),
+                                ('frozen_x0_frozen_w', frozen_x0_w_step, (False, False, False, True))):
+            v_ms = time_steps(fn, args.steps, args.warmup, world, device) / args.steps
+            fa, ba = algorithmic_bytes(n, e, EMB, HIDDEN, need_w=flags[0], need_x=flags[1])
+            fb, bb = algorithmic_bytes(n, e, HIDDEN, CLASSES, need_w=flags[2], need_x=flags[3])
+            vb = fa + ba + fb + bb
+            variants[name] = {'ms_per_step': v_ms, 'edges_per_s': e / (v_ms * 1e-3), 'algorithmic_bytes': vb,
+                              'roofline_frac': vb / (v_ms * 1e-3) / 1e9 / peak}
+
+    # parity leg: the same two layers, all gradients, against the CPU oracle on the AM-shape generator at 1/64
+    parity = None
+    if not args.no_check:
+        parity = oracle_parity_check(device)
 
     # end to end: the reference's Trainer.train iteration body through the public (drop-in) API,
     # labelled batch copied from pinned host memory every step, loss read back every step
@@ -366,8 +444,17 @@ def run_engine(args):
         # same step with torch.optim.Adam, i.e. what the unmodified reference Trainer runs on the drop-in layers
         torch_adam_ms = time_steps(make_e2e_step(make_optimizer(model, fused=False)), args.steps, args.warmup, world,
                                    device) / args.steps
+    # one run of the reference = 51 epochs (main.py -epochs default) after ONE graph build (edge tensors host ->
+    # device + K0) and ONE upload of the [N,63] embedding: the amortised epoch time carries both
+    t_up = time.perf_counter()
+    _emb_up = torch.empty(n, EMB).pin_memory().to(device, non_blocking=True)
+    torch.cuda.synchronize(device)
+    upload_ms = (time.perf_counter() - t_up) * 1e3
+    del _emb_up
     e2e = {'value': e / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4,
-           'ms_per_step': e2e_ms, 'ms_per_step_eager': eager_ms, 'ms_per_step_eager_torch_adam': torch_adam_ms,
+           'ms_per_step': e2e_ms, 'epoch_ms_51': (setup_ms + upload_ms + 51 * e2e_ms) / 51,
+           'epoch_ms_51_what': f'(graph build {setup_ms:.1f} ms + embedding upload {upload_ms:.1f} ms, incl. pinning + 51 x step) / 51',
+           'h2d_bytes_once': int(2 * e * 8 + e * 8 + n * EMB * 4), 'ms_per_step_eager': eager_ms, 'ms_per_step_eager_torch_adam': torch_adam_ms,
            'what': 'Trainer.train iteration body (modelTrainer.py:61-69) via Emb_Layers on the drop-in RGCNConv, captured '
                    'in a CUDA graph (GraphedTrainStep): pinned H2D of x_train/y_train every step (copy stream, overlapping the previous step), fwd, CE loss, bwd, Adam step '
                    '(engine FusedAdam, same update rule as torch.optim.Adam(lr, weight_decay); incl. the [N,63] '
@@ -393,14 +480,18 @@ def run_engine(args):
         torch.cuda.synchronize(device)
         mg_ms = ev0.elapsed_time(ev1) / 10
         mg_bytes = 3 * n * (4 * EMB + 4) + n * 4 * EMB        # S x (row + index) read, one row written
+        # what has to cross the HBM pins: the output, the index vectors, the (L2-resident) tables once
+        mg_dram = n * 4 * EMB + 3 * n * 4 + 3 * n_sum * EMB * 4
         map_gather = {'ms': mg_ms, 'algorithmic_bytes': mg_bytes, 'gbps': mg_bytes / (mg_ms * 1e-3) / 1e9,
-                      'frac_of_peak': mg_bytes / (mg_ms * 1e-3) / 1e9 / peak, 'mode': 'sum', 'summaries': 3}
+                      'frac_of_peak': mg_bytes / (mg_ms * 1e-3) / 1e9 / peak, 'dram_bytes': mg_dram,
+                      'frac_of_peak_dram_bytes': mg_dram / (mg_ms * 1e-3) / 1e9 / peak, 'mode': 'sum', 'summaries': 3,
+                      'summary_rows': n_sum}
         del embs, idxs, fbs
 
     cpu = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        cval, cms, cn, ce_, sample = cpu_reference(3, 1, args.ref_scale, threads)
+        cval, cms, cn, ce_, sample = cpu_reference(min(args.steps, 20), min(args.warmup, 5), args.ref_scale, threads)
         cpu = {'value': cval, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample, 'ms_per_step': cms}
 
     line = {
@@ -411,8 +502,10 @@ def run_engine(args):
                    'directed_edges': e, 'triples_per_s': value / 2, 'relations': r, 'emb': EMB, 'hidden': HIDDEN,
                    'classes': CLASSES, 'l2_policy': 'inputs larger than L2 (features 420 MB + CSR > 126 MB L2); no flush',
                    'graph_build_ms_once': setup_ms, 'range_nodes': graph.query(_lib.Q_RANGE_NODES),
+                   'ms_per_step_passes_serialised': serial_ms, 'variants': variants,
                    'step_algorithmic_bytes': step_bytes, 'step_roofline_frac': step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
                    'passes': passes, 'map_gather': map_gather},
+        'parity': parity,
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
     }
     print(json.dumps(line), flush=True)
@@ -424,6 +517,8 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', choices=['engine', 'reference'], default='engine')
+    ap.add_argument('--workload', choices=['am_63_16_11', 'am10x_h64_bases30_frozenW'], default='am_63_16_11',
+                    help='am_63_16_11 = BASELINE.json configs[3] (the headline); am10x_... = configs[4]')
     ap.add_argument('--scale', type=float, default=1.0, help='AM-shape scale (1.0 = the BASELINE.json config)')
     ap.add_argument('--ref-scale', type=float, default=1 / 32, help='bounded sample for the CPU reference arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -1,7 +1,7 @@
 // map_gather.cu — K5: summary -> original embedding map-gather with the three combiners.
 // Replaces the O(N*S) Python dict walk of reference model/embeddingTricks.py:8-25 and
 // sum/concat/stack (:27-49).  The string->index resolution stays on the host (exact integer
-// work, done once); the device does the row traffic: one warp per original node.
+// work, done once); the device does the row traffic: one warp per 32 original nodes, flat 128-byte walks.
 // Sum order is s = 0..S-1 with the same fp32 adds as python's sum() -> bit-exact.
 #include "common.cuh"
 
@@ -20,26 +20,64 @@ struct MapArgs {
     float* out;
 };
 
+// One warp per block of 32 consecutive original nodes.  The block's output is ONE contiguous span of
+// 32 * feat floats (sum / stack; per-summary spans of feat for concat), so the warp walks it 32 floats at a
+// time: every store instruction writes a full, aligned 128-byte line whatever the row width (63 floats = 252 B
+// rows are not even 16-byte aligned, a warp-per-row walk leaves every second store half empty), and the loads
+// of one instruction fall into at most two table rows.  The block's map entries sit in shared memory; the row
+// of an element is (j + 0.5) / feat in float, exact for j < 32 * feat <= 2^16.
 __global__ void __launch_bounds__(256) k_map_gather(const MapArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= a.n) return;
-    if (a.mode == 0) {
-        for (int c = lane; c < a.feat; c += 32) {
-            float acc = 0.f;
-            for (int s = 0; s < a.num_sums; ++s) {
-                const int32_t j = a.idx[s][i];
-                const float v = j >= 0 ? a.emb[s][(int64_t)j * a.feat + c] : a.fb[s][i * a.feat + c];
-                acc = s == 0 ? v : acc + v;
-            }
-            a.out[i * a.feat + c] = acc;
+    __shared__ int32_t s_idx[8][MAX_SUMS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t blk = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    const int64_t row0 = blk * 32;
+    if (row0 >= a.n) return;
+    const int rows = (int)min((int64_t)32, a.n - row0);
+    const int feat = a.feat, span = rows * feat, ns = a.num_sums;
+    const float inv_feat = 1.0f / (float)feat;
+    for (int s = 0; s < ns; ++s) s_idx[warp][s][lane] = lane < rows ? a.idx[s][row0 + lane] : -1;
+    __syncwarp();
+    auto fetch = [&](int s, int r, int c) -> float {
+        const int32_t j = s_idx[warp][s][r];
+        const float* p = j >= 0 ? a.emb[s] + (int64_t)j * feat + c : a.fb[s] + (row0 + r) * feat + c;
+        return __ldg(p);
+    };
+    // two 32-float steps per trip: the loads of both are in flight together
+    for (int j0 = 0; j0 < span; j0 += 64) {
+        int r[2], c[2];
+        bool ok[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = j0 + 32 * h + lane;
+            ok[h] = j < span;
+            const int jj = ok[h] ? j : 0;
+            r[h] = min((int)(((float)jj + 0.5f) * inv_feat), rows - 1);
+            c[h] = jj - r[h] * feat;
         }
-    } else {
-        for (int s = 0; s < a.num_sums; ++s) {
-            const int32_t j = a.idx[s][i];
-            const float* rp = j >= 0 ? a.emb[s] + (int64_t)j * a.feat : a.fb[s] + i * a.feat;
-            float* op = a.mode == 1 ? a.out + (i * a.num_sums + s) * a.feat : a.out + ((int64_t)s * a.n + i) * a.feat;
-            for (int c = lane; c < a.feat; c += 32) op[c] = rp[c];
+        if (a.mode == 0) {
+            float acc[2] = {0.f, 0.f};
+            for (int s = 0; s < ns; ++s) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float v = ok[h] ? fetch(s, r[h], c[h]) : 0.f;
+                    acc[h] = s == 0 ? v : acc[h] + v;
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (ok[h]) a.out[row0 * feat + j0 + 32 * h + lane] = acc[h];
+        } else {
+            for (int s = 0; s < ns; ++s) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (!ok[h]) continue;
+                    const float v = fetch(s, r[h], c[h]);
+                    // stack: out[s][node][c] ; concat: out[node][s * feat + c]
+                    const int64_t o = a.mode == 2 ? ((int64_t)s * a.n + row0 + r[h]) * feat + c[h]
+                                                  : ((row0 + r[h]) * ns + s) * (int64_t)feat + c[h];
+                    a.out[o] = v;
+                }
+            }
         }
     }
 }
@@ -68,10 +106,12 @@ extern "C" int rgcn_map_gather(const float* const* host_emb, const int32_t* cons
     a.feat = feat;
     a.mode = mode;
     a.out = out;
+    if (feat > 2048) return fail(RGCN_ERR_UNSUPPORTED, "rgcn_map_gather: feat > 2048");
     const int wpb = 8;
+    const int64_t blocks32 = (num_nodes + 31) / 32;
     ProfScope prof(TAG_MAP, feat, num_sums, (cudaStream_t)stream);
     note_launch(1);
-    k_map_gather<<<(int)((num_nodes + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(a);
+    k_map_gather<<<(int)((blocks32 + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(a);
     RGCN_CUDA(cudaGetLastError());
     return 0;
 }
