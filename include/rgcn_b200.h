@@ -229,13 +229,28 @@ int rgcn_nvl_store_rows(float* src, int64_t lds, int32_t cols, const float* relu
 int rgcn_nvl_reduce_rows(const float* src_multicast, void* const* host_peers, int32_t num_peers, int64_t lds,
                          int64_t row0, int64_t rows, float* dst, int64_t ldd, int32_t width, void* stream);
 
+/* Dense contractions of the path on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMA operand
+ * loads, accumulators in tensor memory), fp32-faithful through the error-compensated 3xTF32 split:
+ *   C[m, n_store] = act( A[m, k] . W[n, k]^T + bias )       act 0 = identity, 1 = tanh
+ * — the two nn.Linear calls of the reference's MLP transfer head (model/layers.py:105-107).
+ * rgcn_gemm_prepack splits W ([n, k], leading dimension ldw; transpose = 1: W is given as [k, n]) once per call
+ * into hi / lo parts, zero-padded to [n_pad, k_pad] (n_pad % 16 == 0, <= 256; k_pad % 32 == 0).
+ * rgcn_gemm3x_tf32: rows of A (lda % 4 == 0, 16-byte aligned base) and of C (ldc % 4 == 0) must be 16-byte
+ * addressable; columns [n, n_store) of C receive act(0) = 0 (bias_padded: [n_pad], zero beyond n, or null),
+ * so a 63-wide result can be written straight into the zero-padded 64-wide rows the first layer gathers. */
+int rgcn_gemm_prepack(const float* w, int64_t ldw, int32_t n, int32_t k, int32_t n_pad, int32_t k_pad,
+                      int32_t transpose, float* w_hi, float* w_lo, void* stream);
+int rgcn_gemm3x_tf32(const float* a, int64_t lda, int64_t m, int32_t k, const float* w_hi, const float* w_lo,
+                     int32_t n_pad, int32_t k_pad, const float* bias_padded, int32_t act, float* c, int64_t ldc,
+                     int32_t n_store, void* stream);
+
 /* Instrumentation (no reference counterpart).  rgcn_kernel_launch_count: engine kernels launched
  * by this process so far.  rgcn_profile_enable(1): every pass launch is bracketed by a CUDA-event
  * pair on its own stream; rgcn_profile_collect synchronises those events, returns up to
  * max_records (tag, dims[2], milliseconds) records and clears the log.  Tags: 1 weight-fragment
  * prep, 2 chunk pre-pass, 3 forward tile pass, 4 dL/dx tile pass, 5 dL/dW pass, 6 column copy,
  * 7 ReLU mask, 8 generic kernels, 9 map gather, 10 self-loop (root + bias) pass, 11 / 12 the NVLink
- * exchange kernels (multicast store / load-reduce).
+ * exchange kernels (multicast store / load-reduce), 13 the tcgen05 dense contraction.
  * dims = (gathered width, output width). */
 int64_t rgcn_kernel_launch_count(void);
 int rgcn_profile_enable(int32_t on);

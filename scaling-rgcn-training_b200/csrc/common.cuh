@@ -21,7 +21,7 @@ int fail(int code, const std::string& msg);
 
 // pass tags reported by rgcn_profile_collect (see include/rgcn_b200.h)
 enum { TAG_WPREP = 1, TAG_PREPASS = 2, TAG_TILE_FWD = 3, TAG_TILE_BWD = 4, TAG_WGRAD = 5, TAG_COPY = 6, TAG_MASK = 7,
-       TAG_SIMPLE = 8, TAG_MAP = 9, TAG_SELF = 10, TAG_NVL_STORE = 11, TAG_NVL_REDUCE = 12 };
+       TAG_SIMPLE = 8, TAG_MAP = 9, TAG_SELF = 10, TAG_NVL_STORE = 11, TAG_NVL_REDUCE = 12, TAG_GEMM = 13 };
 void note_launch(int n);
 void set_nvl_mode(int m);   // nvl_comm.cu
 struct ProfScope {   // records a CUDA-event pair around a launch when profiling is enabled

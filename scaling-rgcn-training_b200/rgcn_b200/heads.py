@@ -1,0 +1,119 @@
+"""Transfer heads on the engine (reference model/layers.py:49-66, 90-112).
+
+MLP head: ``x0 = lin2(tanh(lin1(E_cat)))`` — two dense contractions per step at the size of the whole
+graph (AM-shape: 1.67 M x 189 x 137 and x 137 x 63).  Forward runs on the engine's tcgen05 kernel
+(csrc/gemm_tc.cu: TMA operand loads, ``tcgen05.mma kind::tf32`` with the error-compensated 3xTF32 split,
+accumulators in tensor memory, bias / tanh in the epilogue); ``lin2``'s result is written straight into
+zero-padded 64-wide rows, i.e. the 16-byte addressable layout the first R-GCN layer gathers from, so the
+layer needs no padding copy of x0.  Backward: ``dL/dh`` through the same kernel (W2 as the transposed
+operand); the parameter gradients are reductions over all nodes with tiny outputs (137 x 189) and go
+through torch matmuls on the saved activations.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+
+def _pad(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def prepack(weight: Tensor, transpose: bool = False) -> Tuple[Tensor, Tensor, int, int]:
+    """nn.Linear weight [n, k] (or, transpose=True, the same tensor used as [k, n] -> n = weight.size(1)) split
+    into tf32 hi / lo parts, zero-padded to [n_pad, k_pad]."""
+    lib = _lib.load()
+    w = weight.detach()
+    if not w.is_cuda or w.dtype != torch.float32:
+        raise _lib.EngineError('gemm: CUDA fp32 weights only (no CPU path)')
+    w = w if w.stride(1) == 1 else w.contiguous()
+    n, k = (w.size(1), w.size(0)) if transpose else (w.size(0), w.size(1))
+    n_pad, k_pad = _pad(n, 16), _pad(k, 32)
+    if n_pad > 256:
+        raise _lib.EngineError('gemm: output width > 256 is outside the heads this kernel serves')
+    hi = torch.empty((n_pad, k_pad), dtype=torch.float32, device=w.device)
+    lo = torch.empty_like(hi)
+    with torch.cuda.device(w.device):
+        _lib.check(lib.rgcn_gemm_prepack(w.data_ptr(), w.stride(0), n, k, n_pad, k_pad, 1 if transpose else 0,
+                                         hi.data_ptr(), lo.data_ptr(), _stream(w.device)), 'rgcn_gemm_prepack')
+    return hi, lo, n_pad, k_pad
+
+
+def rows16(a: Tensor) -> Tensor:
+    """a [m, k] with 16-byte addressable rows (row stride a multiple of 4 floats, aligned base): a itself or a
+    zero-padded copy."""
+    if a.stride(1) == 1 and a.stride(0) % 4 == 0 and a.data_ptr() % 16 == 0:
+        return a
+    ld = _pad(a.size(1), 4)
+    buf = torch.zeros((a.size(0), ld), dtype=torch.float32, device=a.device)
+    buf[:, :a.size(1)] = a
+    return buf[:, :a.size(1)]
+
+
+def gemm(a: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: str = 'none', out_ld: Optional[int] = None,
+         transpose_w: bool = False) -> Tensor:
+    """act(a @ W^T + bias) on the tcgen05 kernel.  a [m, k]; weight [n, k] (transpose_w: weight is [k, n]).
+    Returns a [m, n] VIEW of an [m, out_ld] buffer whose extra columns are zero (out_ld default = n rounded up to 4)."""
+    lib = _lib.load()
+    if not a.is_cuda or a.dtype != torch.float32:
+        raise _lib.EngineError('gemm: CUDA fp32 input only (no CPU path)')
+    a = rows16(a)
+    m, k = a.shape
+    hi, lo, n_pad, k_pad = prepack(weight, transpose_w)
+    n = weight.size(1) if transpose_w else weight.size(0)
+    ld = out_ld if out_ld is not None else _pad(n, 4)
+    if ld % 4 or ld < n or ld > n_pad:
+        raise ValueError('gemm: out_ld must be a multiple of 4 in [n, n_pad]')
+    bp = None
+    if bias is not None:
+        bp = torch.zeros(n_pad, dtype=torch.float32, device=a.device)
+        bp[:n] = bias.detach()
+    out = torch.empty((m, ld), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = lib.rgcn_gemm3x_tf32(a.data_ptr(), a.stride(0), m, k, hi.data_ptr(), lo.data_ptr(), n_pad, k_pad,
+                                  bp.data_ptr() if bp is not None else None, 1 if act == 'tanh' else 0, out.data_ptr(), ld, ld,
+                                  _stream(a.device))
+    _lib.check(rc, 'rgcn_gemm3x_tf32')
+    return out[:, :n] if ld != n else out
+
+
+class _MLPHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, e_cat: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor) -> Tensor:
+        a = rows16(e_cat)
+        h = gemm(a, w1, b1, act='tanh')                       # [N, mid], rows padded to a multiple of 4
+        x0 = gemm(h, w2, b2, out_ld=_pad(w2.size(0), 4))      # [N, emb] view of [N, ceil4(emb)]: the layer's mirror layout
+        ctx.save_for_backward(a, h, w1, w2)
+        return x0
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        a, h, w1, w2 = ctx.saved_tensors
+        need_e, need_w1, need_b1, need_w2, need_b2 = ctx.needs_input_grad
+        g = g.contiguous()
+        gw2 = g.t() @ h if need_w2 else None                  # [emb, mid]: reduction over all nodes, tiny output
+        gb2 = g.sum(0) if need_b2 else None
+        ge = gw1 = gb1 = None
+        if need_e or need_w1 or need_b1:
+            dh = gemm(g, w2, transpose_w=True)                # g @ W2 -> [N, mid] on the tensor-core kernel
+            dpre = dh * (1.0 - h * h)
+            if need_w1:
+                gw1 = dpre.t() @ a
+            if need_b1:
+                gb1 = dpre.sum(0)
+            if need_e:
+                ge = gemm(dpre, w1, transpose_w=True)
+        return ge, gw1, gb1, gw2, gb2
+
+
+def mlp_head(e_cat: Tensor, lin1: torch.nn.Linear, lin2: torch.nn.Linear) -> Tensor:
+    """lin2(tanh(lin1(e_cat))) (reference model/layers.py:105-107) on the engine."""
+    return _MLPHeadFn.apply(e_cat, lin1.weight, lin1.bias, lin2.weight, lin2.bias)

@@ -11,6 +11,7 @@ inter-layer ``F.relu`` (model/layers.py:22) into the second layer's input load a
 """
 from __future__ import annotations
 
+import os
 from typing import Callable
 
 import torch
@@ -83,8 +84,22 @@ class Emb_MLP_Layers(_TwoLayerRGCN):
             nn.init.kaiming_uniform_(lin.weight, mode='fan_in')
         self._build_convs(num_relations, hidden_l, num_labels, emb_dim)
 
+    # engine extension (default on, RGCN_B200_ENGINE_HEAD=0 restores the nn.Linear calls): the head's two dense
+    # contractions run on the engine's tcgen05 kernel (rgcn_b200.heads) and x0 lands in the 16-byte addressable
+    # rows the first layer gathers
+    engine_head = os.environ.get('RGCN_B200_ENGINE_HEAD', '1') != '0'
+
     def _input_features(self) -> Tensor:
-        return self.lin2(torch.tanh(self.lin1(self.embedding.weight)))
+        e = self.embedding.weight
+        if self.engine_head and e.is_cuda:
+            from .heads import mlp_head, rows16
+            if not e.requires_grad:                      # frozen summary embeddings: pad their rows once
+                key = (e.data_ptr(), e._version, tuple(e.shape))
+                if getattr(self, '_e16_key', None) != key:
+                    self._e16, self._e16_key = rows16(e.detach()), key
+                e = self._e16
+            return mlp_head(e, self.lin1, self.lin2)
+        return self.lin2(torch.tanh(self.lin1(e)))
 
     def load_embedding(self, embedding: Tensor, freeze: bool = True) -> None:
         self.embedding = nn.Embedding.from_pretrained(embedding, freeze=freeze)

@@ -15,7 +15,7 @@ from rgcn_b200 import _lib
 def _header_functions():
     text = open(os.path.join(REPO, 'include', 'rgcn_b200.h')).read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
-    return sorted(set(re.findall(r'\b(rgcn_[a-z_]+)\s*\(', text)))
+    return sorted(set(re.findall(r'\b(rgcn_[a-z0-9_]+)\s*\(', text)))
 
 
 def test_library_exports_every_declared_symbol():

@@ -251,3 +251,60 @@ def test_kernel_family_switches_keep_parity(env):
     res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600,
                          env={**os.environ, **env})
     assert res.returncode == 0, (env, res.stdout[-500:], res.stderr[-2000:])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('m,k,n,act', [(1, 5, 3, 'none'), (127, 189, 137, 'tanh'), (128, 137, 63, 'none'), (1000, 63, 64, 'tanh'),
+                                        (5000, 32, 256, 'none'), (333, 200, 16, 'tanh')])
+def test_tcgen05_gemm_is_fp32_faithful(m, k, n, act):
+    """C = act(A W^T + b) on the tensor-core kernel (3xTF32) against an fp64 reference: <= 1e-5 relative in the
+    max norm, i.e. fp32-faithful, not TF32-accurate (plain TF32 would sit near 1e-3); M / K / N tails, padded
+    output columns written as zeros."""
+    from rgcn_b200.heads import gemm
+    torch.manual_seed(m + k + n)
+    a = torch.randn(m, k, device=DEV)                     # summary embeddings are N(0, 1) rows (nn.Embedding init)
+    w = (torch.rand(n, k, device=DEV) - 0.5) * 2 * (6.0 / k) ** 0.5      # kaiming-uniform, as the reference inits the head
+    b = torch.randn(n, device=DEV)
+    want = a.double() @ w.double().t() + b.double()
+    want = torch.tanh(want) if act == 'tanh' else want
+    got = gemm(a, w, b, act=act)
+    assert tuple(got.shape) == (m, n)
+    # fp32-faithful: within the parity bound, or (long cancelling dot products) as close to the fp64 truth as
+    # torch's own fp32 product is, up to a small factor
+    fp32 = torch.addmm(b, a, w.t())
+    fp32 = torch.tanh(fp32) if act == 'tanh' else fp32
+    assert rel_err(got, want) < max(TOL, 4 * rel_err(fp32, want)), (rel_err(got, want), rel_err(fp32, want))
+    if m == 127:     # stress: 3x larger operands, long cancelling sums — 3xTF32 stays within a small factor of fp32
+        a3 = a * 3
+        w3 = torch.randn(n, k, device=DEV) * 0.3
+        t64 = a3.double() @ w3.double().t()
+        assert rel_err(gemm(a3, w3), t64) < max(TOL, 6 * rel_err(a3 @ w3.t(), t64))
+    ld = (n + 15) // 16 * 16 if n % 16 else n
+    if ld != n and ld <= 256:
+        padded = gemm(a, w, b, act=act, out_ld=min(ld, (n + 3) // 4 * 4 + 4) if (n + 3) // 4 * 4 + 4 <= ld else (n + 3) // 4 * 4)
+        base = padded._base if padded._base is not None else padded
+        assert float(base[:, n:].abs().max()) == 0.0 if base.size(1) > n else True
+    # the transposed-weight form used by the head's backward: a2 @ W
+    a2 = torch.randn(m, n, device=DEV)
+    got2 = gemm(a2, w, transpose_w=True)
+    assert rel_err(got2, a2.double() @ w.double()) < TOL
+
+
+@pytest.mark.gpu
+def test_engine_mlp_head_matches_torch_head_with_gradients():
+    from rgcn_b200 import Emb_MLP_Layers
+    from rgcn_b200.heads import mlp_head
+    torch.manual_seed(0)
+    n, S, emb, C = 3000, 3, 63, 11
+    m = Emb_MLP_Layers(5, 16, C, n, emb, S).to(DEV)
+    for freeze in (True, False):
+        e = torch.randn(n, S * emb, device=DEV, requires_grad=not freeze)
+        g = torch.randn(n, emb, device=DEV)
+        x_ref = m.lin2(torch.tanh(m.lin1(e)))
+        ref = torch.autograd.grad(x_ref, [p for p in (e, m.lin1.weight, m.lin1.bias, m.lin2.weight, m.lin2.bias) if p.requires_grad], g)
+        x = mlp_head(e, m.lin1, m.lin2)
+        assert x.stride(0) == 64 and x.data_ptr() % 16 == 0          # the first layer's mirror layout
+        got = torch.autograd.grad(x, [p for p in (e, m.lin1.weight, m.lin1.bias, m.lin2.weight, m.lin2.bias) if p.requires_grad], g)
+        assert rel_err(x, x_ref) < TOL
+        for a, b in zip(got, ref):
+            assert rel_err(a, b) < 2e-5, rel_err(a, b)   # (torch's own fp32 matmuls are the looser side here)
