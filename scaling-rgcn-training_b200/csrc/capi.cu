@@ -96,6 +96,7 @@ int64_t fwd_ws(const rgcn_graph* g, int fin, int fout) {
     b += ws_take((int64_t)(g->R + 1) * kp * np, 4);                          // wfrag2 (fp32 pairs)
     b += ws_take((int64_t)g->brc[RGCN_BRC_FWD].num_chunks * kp, 4);          // chunk rows
     b += ws_take((int64_t)g->fwd_out_rows() * np, 4);                        // padded accumulate target
+    if (kp == 64 && np == 64) b += ws_take(wprep_tc_floats(g->R), 4);        // tcgen05 operand images
     return b;
 }
 
@@ -108,6 +109,7 @@ int64_t bwd_ws(const rgcn_graph* g, int fin, int fout) {
     b += ws_take((int64_t)(g->R + 1) * kp * np, 4);                          // W^T frags, fp32 pairs
     b += ws_take((int64_t)g->brc[RGCN_BRC_BWD].num_chunks * np, 4);          // chunk rows of gout (dx pass)
     b += ws_take((int64_t)g->n_own * kp, 4);                                 // padded dx target
+    if (kp == 64 && np == 64) b += ws_take(wprep_tc_floats(g->R), 4);        // tcgen05 operand images
     return b;
 }
 
@@ -169,6 +171,7 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
     const int fout4 = (fout + 3) & ~3;
     const bool direct = ldo % 4 == 0 && ldo >= fout4 && ((uintptr_t)out & 15) == 0;
     float* target = direct ? out : ws.take<float>(n_out * np);
+    float* wtc = (kp == 64 && np == 64) ? ws.take<float>(wprep_tc_floats(g->R)) : nullptr;
     if (!ws.ok) return fail(RGCN_ERR_WORKSPACE, "rgcn_layer_fwd: workspace too small (see rgcn_layer_workspace_bytes)");
     const int64_t tld = direct ? ldo : np;
     const int tn = direct ? fout4 : np;
@@ -241,7 +244,13 @@ int layer_fwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
         } else if ((rc = launch_chunk_prepass(p, st))) {
             return rc;
         }
-        if ((rc = launch_etile_pass(p, g->num_sms, st))) return rc;   // the edge tiles accumulate
+        // the edge tiles accumulate: 64 x 64 column passes on the tcgen05 kernel, the rest on the mma.sync one
+        if (wtc && etile_tc_ok(p)) {
+            if ((rc = launch_wprep_tc(weight, root, g->R, fin, fout, false, wtc, st))) return rc;
+            if ((rc = launch_etile_tc(p, wtc, g->R, g->num_sms, st))) return rc;
+        } else if ((rc = launch_etile_pass(p, g->num_sms, st))) {
+            return rc;
+        }
     } else {
         if ((rc = launch_wprep(wp, st))) return rc;
         if ((rc = launch_chunk_prepass(p, st))) return rc;
@@ -338,8 +347,11 @@ int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
     const bool dx_v4ok = gx && etile_vec4_ok(gout_gather, ldgg, fout, nullptr);
     const bool packed = gx && !direct_target(gx, ldgx, fin) && dx_v4ok && etile_choice(np, dx_v4ok) &&
                         etile_packed_ok(gx, ldgx, fin, kp);
-    const bool direct = gx && (packed || direct_target(gx, ldgx, fin));
+    // (a caller-padded gradient buffer — rows of ceil4(fin) or more floats, 16-byte aligned — is accumulated in place)
+    const bool padded = gx && !packed && ldgx % 4 == 0 && ldgx >= ((fin + 3) & ~3) && ((uintptr_t)gx & 15) == 0;
+    const bool direct = gx && (packed || padded || direct_target(gx, ldgx, fin));
     float* target = gx ? (direct ? gx : ws.take<float>((int64_t)g->n_own * kp)) : nullptr;
+    float* wtc = (gx && kp == 64 && np == 64) ? ws.take<float>(wprep_tc_floats(g->R)) : nullptr;
     if (!ws.ok) return fail(RGCN_ERR_WORKSPACE, "rgcn_layer_bwd: workspace too small (see rgcn_layer_workspace_bytes)");
     // dL/dW (+ its pre-pass) and the dL/dx chain are independent: with both requested the dL/dW pass runs
     // on the side stream, each side keeping to its share of every SM so that they are co-resident
@@ -390,7 +402,7 @@ int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
         p.wfrag = wtfrag;
         p.wfrag2 = wtfrag2;
         p.bias = nullptr; p.nbias = 0;
-        p.out = target; p.ldo = tld; p.nout = direct ? fin : kp; p.tag_out = fin;
+        p.out = target; p.ldo = tld; p.nout = direct ? (packed ? fin : ((fin + 3) & ~3)) : kp; p.tag_out = fin;
         p.kp = np; p.np = kp;
         p.relu_in = false;
         p.transposed = true;
@@ -401,7 +413,12 @@ int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
         if ((rc = launch_chunk_prepass(p, st))) return rc;
         if (et) {
             if ((rc = launch_selfloop_pass(p, g->own_lo, g->n_own, g->R, g->num_sms, st))) return rc;
-            if ((rc = launch_etile_pass(p, g->num_sms, st))) return rc;
+            if (wtc && etile_tc_ok(p)) {
+                if ((rc = launch_wprep_tc(weight, root, g->R, fin, fout, true, wtc, st))) return rc;
+                if ((rc = launch_etile_tc(p, wtc, g->R, g->num_sms, st))) return rc;
+            } else if ((rc = launch_etile_pass(p, g->num_sms, st))) {
+                return rc;
+            }
         } else {
             RGCN_CUDA(cudaMemsetAsync(target, 0, (size_t)g->n_own * tld * 4, st));
             if ((rc = launch_tile_pass(p, g->num_sms, st))) return rc;

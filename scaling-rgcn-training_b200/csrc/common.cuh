@@ -67,6 +67,9 @@ struct Brc {
     int32_t* tile_info = nullptr;  // [NT] rel << 8 | count
     int32_t num_tiles = 0;
     int32_t num_tiles_noself = 0;  // tiles before the self-loop tiles (which sort last)
+    int32_t* stile_e0 = nullptr;   // [NS+1] super tiles (tcgen05 kernel): <= 128 consecutive entries of one relation,
+    int32_t* stile_rel = nullptr;  // [NS]   edge tiles only; super tile j = entries [stile_e0[j], stile_e0[j+1])
+    int32_t num_stiles = 0;
     int64_t bytes = 0;
     void release();
 };
@@ -159,6 +162,14 @@ int launch_ewgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st);
 bool selfloop_pad_ok(int kp, int np);
 int launch_selfloop_pad(const TilePass& p, const float* x_raw, int64_t ld_raw, float* mirror, int64_t ldm, int64_t n_own,
                         int R, int num_sms, cudaStream_t st);
+
+// tcgen05 entry-tile pass (etile_tc.cu): 64 gathered columns x 64 produced columns, 16-byte addressable rows on
+// both sides; wtc = operand images written by launch_wprep_tc
+bool etile_tc_ok(const TilePass& p);
+int64_t wprep_tc_floats(int R);
+int launch_wprep_tc(const float* weight, const float* root, int R, int fin, int fout, bool transpose, float* wtc,
+                    cudaStream_t st);
+int launch_etile_tc(const TilePass& p, const float* wtc, int R, int num_sms, cudaStream_t st);
 
 int launch_copy_cols(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t n, int cols, cudaStream_t st);
 int launch_pad_rows(const float* src, int64_t lds, int cols, float* dst, int64_t ldd, int64_t n, cudaStream_t st);

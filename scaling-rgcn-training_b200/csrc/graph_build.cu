@@ -23,7 +23,7 @@ const char* last_error_cstr() { return g_last_error.c_str(); }
 
 void Brc::release() {
     void* ptrs[] = {perm, seg_ptr0, seg_ptr, seg_own, seg_rel, e_idx, e_w, raw_idx, raw_w,
-                    chunk_beg, chunk_end, chunk_out, bat_seg0, bat_info, units, e_own, tile_e0, tile_info};
+                    chunk_beg, chunk_end, chunk_out, bat_seg0, bat_info, units, e_own, tile_e0, tile_info, stile_e0, stile_rel};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     *this = Brc();
@@ -321,6 +321,61 @@ cudaError_t scan_exclusive(const T* in, T* out, int64_t n, cudaStream_t st) {
     return cudaStreamSynchronize(st);
 }
 
+// Super tiles for the tcgen05 kernel (M = 128 rows per MMA): runs of consecutive entry tiles of one relation, cut
+// every ST_TILES tiles.  Entries of consecutive tiles are contiguous, so a super tile is [stile_e0[j], stile_e0[j+1]).
+constexpr int ST_TILES = 8;   // 8 x 16 = 128 entries
+__global__ void k_stile_runstart(const int32_t* __restrict__ tile_info, int32_t NT, int32_t* __restrict__ start) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= NT) return;
+    start[i] = (i == 0 || (tile_info[i] >> 8) != (tile_info[i - 1] >> 8)) ? (int32_t)i : 0;
+}
+__global__ void k_stile_heads(const int32_t* __restrict__ runstart, int32_t NT, int32_t* __restrict__ head) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= NT) return;
+    head[i] = (((int32_t)i - runstart[i]) % ST_TILES == 0) ? 1 : 0;
+}
+__global__ void k_stile_fill(const int32_t* __restrict__ head, const int32_t* __restrict__ pos,
+                             const int32_t* __restrict__ tile_e0, const int32_t* __restrict__ tile_info, int32_t NT,
+                             int32_t NS, int32_t* __restrict__ stile_e0, int32_t* __restrict__ stile_rel) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= NT) return;
+    if (head[i]) {
+        stile_e0[pos[i]] = tile_e0[i];
+        stile_rel[pos[i]] = tile_info[i] >> 8;
+    }
+    if (i == NT - 1) stile_e0[NS] = tile_e0[i] + (tile_info[i] & 0xff);
+}
+struct MaxOp {
+    __device__ __forceinline__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; }
+};
+int build_stiles(Brc& b, cudaStream_t st) {
+    const int32_t NT = b.num_tiles_noself;
+    b.num_stiles = 0;
+    if (NT <= 0) return 0;
+    Dev<int32_t> runstart, head, pos;
+    Dev<char> tmp;
+    RGCN_CUDA(runstart.alloc(NT));
+    RGCN_CUDA(head.alloc((size_t)NT + 1));
+    RGCN_CUDA(pos.alloc((size_t)NT + 1));
+    k_stile_runstart<<<blocks_for(NT), TPB, 0, st>>>(b.tile_info, NT, runstart.p);
+    size_t tmp_bytes = 0;
+    RGCN_CUDA(cub::DeviceScan::InclusiveScan(nullptr, tmp_bytes, runstart.p, runstart.p, MaxOp(), (int)NT, st));
+    RGCN_CUDA(tmp.alloc(tmp_bytes));
+    RGCN_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tmp_bytes, runstart.p, runstart.p, MaxOp(), (int)NT, st));
+    RGCN_CUDA(cudaMemsetAsync(head.p, 0, ((size_t)NT + 1) * 4, st));
+    k_stile_heads<<<blocks_for(NT), TPB, 0, st>>>(runstart.p, NT, head.p);
+    RGCN_CUDA(scan_exclusive(head.p, pos.p, (int64_t)NT + 1, st));
+    int32_t NS = 0;
+    RGCN_CUDA(cudaMemcpy(&NS, pos.p + NT, 4, cudaMemcpyDeviceToHost));
+    RGCN_CUDA(cudaMalloc(&b.stile_e0, ((size_t)NS + 2) * 4));
+    RGCN_CUDA(cudaMalloc(&b.stile_rel, ((size_t)NS + 2) * 4));
+    k_stile_fill<<<blocks_for(NT), TPB, 0, st>>>(head.p, pos.p, b.tile_e0, b.tile_info, NT, NS, b.stile_e0, b.stile_rel);
+    RGCN_CUDA(cudaGetLastError());
+    RGCN_CUDA(cudaStreamSynchronize(st));
+    b.num_stiles = NS;
+    return 0;
+}
+
 int bit_length(uint64_t v) {
     int b = 0;
     while (v) {
@@ -520,6 +575,10 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const 
     }
     RGCN_CUDA(cudaStreamSynchronize(st));
     RGCN_CUDA(cudaGetLastError());
+    {
+        int rc = build_stiles(b, st);
+        if (rc) return rc;
+    }
     b.bytes = n2 * 12 + (int64_t)S * 16 + (int64_t)E3 * 8 + (int64_t)NC * 8 + (int64_t)NB * 8;
     *out = b;
     return 0;

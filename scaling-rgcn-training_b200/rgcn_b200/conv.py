@@ -153,7 +153,15 @@ class _RGCNLayerFn(torch.autograd.Function):
                 gout_all, work = comm.all_gather_rows_async(gout)
             else:
                 gout_all = comm.all_gather_rows(gout)
-        gx = torch.empty((graph.num_owned, fin), dtype=torch.float32, device=dev) if need_x else None
+        gx = None
+        if need_x:
+            # 64 x 64 column passes run on the tcgen05 kernel, which adds whole 256-byte rows: an odd-width
+            # gradient (emb = 63 next to hidden 64) is accumulated in 64-wide rows and returned as a view
+            wide = 32 < fin <= 64 and 32 < fout <= 64 and fin % 4 != 0 and os.environ.get('RGCN_B200_TC', '1') != '0'
+            if wide:
+                gx = torch.empty((graph.num_owned, 64), dtype=torch.float32, device=dev)[:, :fin]
+            else:
+                gx = torch.empty((graph.num_owned, fin), dtype=torch.float32, device=dev)
         gw = torch.empty_like(weight) if need_w else None
         groot = torch.empty((fin, fout), dtype=torch.float32, device=dev) if need_root else None
         gbias = torch.empty((fout,), dtype=torch.float32, device=dev) if need_bias else None
@@ -164,7 +172,8 @@ class _RGCNLayerFn(torch.autograd.Function):
             with torch.cuda.device(dev):
                 rc = lib.rgcn_layer_bwd_reuse(graph.handle, x.data_ptr(), x.stride(0), fin, weight.data_ptr(), _ptr(root),
                                               gout.data_ptr(), gout.stride(0), _ptr(gout_all),
-                                              gout_all.stride(0) if gout_all is not None else 0, fout, _ptr(gx_t), fin,
+                                              gout_all.stride(0) if gout_all is not None else 0, fout, _ptr(gx_t),
+                                              gx_t.stride(0) if gx_t is not None else fin,
                                               _ptr(gw_t), _ptr(groot_t), _ptr(gbias_t),
                                               ctx.flags | (_lib.F_NO_RELU_MASK if fuse_mask else 0), ws.data_ptr(),
                                               ws_bytes, _ptr(ctx.x_chunk_rows), _stream(dev))

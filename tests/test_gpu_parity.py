@@ -119,7 +119,8 @@ def test_layer_fwd_bwd_on_reference_graphs(name, fin, fout):
     _layer_case(ei, et, n, r, fin, fout, seed=fin + fout)
 
 
-@pytest.mark.parametrize('fin,fout', [(1, 1), (3, 2), (16, 16), (17, 33), (20, 7), (32, 64), (60, 60), (64, 64), (63, 11)])
+@pytest.mark.parametrize('fin,fout', [(1, 1), (3, 2), (16, 16), (17, 33), (20, 7), (32, 64), (60, 60), (64, 64), (63, 11),
+                                      (63, 64), (64, 63), (36, 40)])
 def test_layer_shapes_on_random_multigraph(fin, fout):
     ei, et = random_multigraph(257, 3000, 7, seed=fin * 100 + fout, hub_frac=0.25, dup_frac=0.2)
     _layer_case(ei, et, 257, 7, fin, fout, seed=1)
@@ -529,3 +530,36 @@ def test_fused_adam_matches_torch_adam():
     cpu_param.grad = torch.ones(3)
     with pytest.raises(_lib.EngineError):
         o.step()
+
+
+# ------------------------------------------------------------------ tcgen05 entry-tile pass (hidden 64)
+@pytest.mark.parametrize('name', ['AIFB_sum_in', 'AIFB_bisim_k3'])
+@pytest.mark.parametrize('fin,fout', [(63, 64), (64, 64)])
+def test_hidden64_layer_on_reference_graphs(name, fin, fout):
+    """64 x 64 column passes (forward and dL/dx) run on the tcgen05 kernel: hubs (chunk rows), duplicates, tiles of
+    every fill from 1 to 128 entries, relations with a single entry."""
+    ei, et, n, r = golden_graph(name)
+    _layer_case(ei, et, n, r, fin, fout, seed=fin * 3 + fout)
+
+
+def test_hidden64_am_shape_two_layers_match_mma_sync_path(am16):
+    """config-5 shape (63 -> 64 -> 11, fused ReLU, frozen weights: dL/dx0 only) on the AM-shape graph at 1/16:
+    the tcgen05 passes against the same step with RGCN_B200_TC=0 semantics (generic kernels as the cross-check)."""
+    ei, et, n, r, g = am16
+    torch.manual_seed(9)
+    x = torch.randn(n, 63, device=DEV, requires_grad=True)
+    w1 = (torch.rand(r, 63, 64, device=DEV) - 0.5) * 0.3
+    r1 = (torch.rand(63, 64, device=DEV) - 0.5) * 0.3
+    b1 = torch.rand(64, device=DEV) - 0.5
+    w2 = (torch.rand(r, 64, 11, device=DEV) - 0.5) * 0.3
+    r2 = (torch.rand(64, 11, device=DEV) - 0.5) * 0.3
+    gout = torch.randn(n, 11, device=DEV)
+    res = []
+    for simple in (False, True):
+        x.grad = None
+        h = rgcn_layer(x, w1, r1, b1, g, force_simple=simple)
+        out = rgcn_layer(h, w2, r2, None, g, relu_in=True, force_simple=simple)
+        out.backward(gout)
+        res.append((out.detach().cpu(), x.grad.detach().cpu().clone()))
+    assert rel_err(res[0][0], res[1][0]) < TOL
+    assert rel_err(res[0][1], res[1][1]) < TOL
