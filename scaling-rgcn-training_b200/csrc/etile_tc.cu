@@ -7,17 +7,18 @@
 // runs of the blocked relational CSR, with gathered A rows and scattered D rows.  With the warp-level
 // mma.sync path this shape is tensor-bound (3xTF32: 2.9 TFLOP per pass at 10x AM-shape, ~3x over its HBM
 // time); here one elected thread issues tcgen05.mma.kind::tf32 with the accumulator in tensor memory.
-// One persistent CTA per SM, 12 warps:
+// One persistent CTA per SM, 16 warps:
 //
 //   warp 0      operand loader: the relation's pre-split, pre-swizzled B image (hi | lo, 32 KB, written once
 //               per call by k_wprep_tc) arrives with ONE cp.async.bulk (SASS UBLKCP) per relation change
 //   warp 1      MMA issuer: per 32-column half of K 4 x 3 tcgen05.mma (A_hi.B_hi, A_lo.B_hi, A_hi.B_lo),
 //               tcgen05.commit frees the stage / publishes the accumulator (2 stages x 64 TMEM columns)
 //   warp 2      TMEM allocator
-//   warps 4-7   gather + split: thread t owns row t of the tile — 16-byte cp.async of x[src_t] (zero-fill form
-//               for missing rows) straight into the 128B-swizzled operand tile, one stage ahead; then the
-//               row is split in place into hi = rn_tf32(a), lo = rn_tf32(a - hi) (and ReLU'd when fused)
-//   warps 8-11  epilogue: thread t = TMEM lane t reads its result row (tcgen05.ld), scales it by the entry's
+//   warps 4-11  gather + split: two threads per row of the tile — 16-byte cp.async of x[src_t] (zero-fill form
+//               for missing rows) straight into the 128B-swizzled operand tile, one stage ahead, indices read
+//               three tiles ahead and the rows prefetched to L2 two tiles ahead; then each thread splits its
+//               own chunks in place into hi = rn_tf32(a), lo = rn_tf32(a - hi) (and applies the fused ReLU)
+//   warps 12-15 epilogue: thread t = TMEM lane t reads its result row (tcgen05.ld), scales it by the entry's
 //               1/cnt weight, parks it in shared memory and issues ONE cp.reduce.async.bulk (f32 add, 256 B)
 //               to out[owner_t]
 // Rows on both sides must be 16-byte addressable with >= 64 floats per row (x: the zero-padded mirror for
@@ -38,7 +39,7 @@ constexpr int W_IMG = 4 * 64 * 128;  // B image of a relation: hi half 0 | hi ha
 constexpr int W_BUFS = 2;
 constexpr int OUT_STRIDE = 272;      // bytes per staged result row (256 + 16: STS.128 conflict-free per 8 lanes)
 constexpr int ACC_COLS = 64, ACC_STAGES = 2;
-constexpr int THREADS = 384;
+constexpr int THREADS = 512;
 constexpr int CHUNK_TILES = 4;       // consecutive super tiles a CTA takes at a time (one relation most of the time)
 constexpr int SMEM_BYTES = STAGES * 2 * A_HALF + W_BUFS * W_IMG + TM * OUT_STRIDE + 256 + 1024;
 
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_etile_tc(const TcArgs a) {
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(afull + s, 4);             // one arrival per gather warp
+            mbar_init(afull + s, 8);             // one arrival per gather warp
             mbar_init(aempty + s, 1);
         }
         for (int b = 0; b < W_BUFS; ++b) {
@@ -203,10 +204,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_etile_tc(const TcArgs a) {
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
         int s = 0, acc = 0, b = -1, prev_rel = -1;
         uint32_t ph = 0, aph = 0, wph = 0;
-        for (TileSeq ts(a.num_stiles); ts.cur() >= 0;) {
-            const int rel = a.stile_rel[ts.cur()];
+        TileSeq ts(a.num_stiles);
+        int rel_next = ts.cur() >= 0 ? a.stile_rel[ts.cur()] : -2, rel_next2 = -2;
+        {
+            TileSeq t2 = ts;
+            t2.next();
+            rel_next2 = t2.cur() >= 0 ? a.stile_rel[t2.cur()] : -2;
+        }
+        while (ts.cur() >= 0) {
+            const int rel = rel_next;
             ts.next();
-            const int next_rel = ts.cur() >= 0 ? a.stile_rel[ts.cur()] : -2;
+            const int next_rel = rel_next2;          // (the relation ids are read two tiles ahead)
+            {
+                TileSeq t2 = ts;
+                t2.next();
+                rel_next = next_rel;
+                rel_next2 = (ts.cur() >= 0 && t2.cur() >= 0) ? a.stile_rel[t2.cur()] : -2;
+            }
             if (rel != prev_rel) {          // the loader's next buffer holds this relation
                 if (b < 0) {
                     b = 0;
@@ -252,36 +266,46 @@ __global__ void __launch_bounds__(THREADS, 1) k_etile_tc(const TcArgs a) {
                 aph ^= 1;
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ===== gather + split: thread t <-> row t =====
-        const int t = threadIdx.x - 128;
+    } else if (warp >= 4 && warp < 12) {
+        // ===== gather + split: 256 threads, thread u <-> (row u / 2, four of the eight 16-byte chunks of a half row) =====
+        const int u = threadIdx.x - 128, t = u >> 1, part = u & 1;
         const uint32_t n_rows = (uint32_t)a.n_rows;
         const uint32_t row_off = (uint32_t)(t * 128), sw = (uint32_t)(t & 7);
         int s_issue = 0, s_done = 0;
         uint32_t ph_issue = 0;
-        // one stage = one 32-column half of a tile; `pending` stages have been issued and not yet split
+        // (the raw index word is kept as loaded: nothing is computed from it until the copies need the address, so
+        // the load of tile i+3's indices never stalls the warp)
         struct Row {
-            const float* src;   // row pointer (nullptr: no such row in this tile)
-            bool real;
+            uint32_t raw;   // e_idx word as loaded (bit 31 = end-of-segment flag)
+            bool valid;
         };
-        auto row_of = [&](int tile) {
-            Row r{nullptr, false};
-            const int e0 = a.stile_e0[tile], cnt = a.stile_e0[tile + 1] - e0;
-            if (t < cnt) {
-                const uint32_t idx = a.e_idx[e0 + t] & IDX_MASK;
-                r.real = idx < n_rows;
-                r.src = r.real ? a.feat + (int64_t)idx * a.ldf : a.aux + (int64_t)(idx - n_rows) * 64;
+        // two-level look-ahead: the entry span of a tile is read one step before its index word
+        int span_e0 = 0, span_e1 = 0;
+        auto load_span = [&](int tile) {
+            span_e0 = a.stile_e0[tile];
+            span_e1 = a.stile_e0[tile + 1];
+        };
+        auto row_of_span = [&]() {
+            Row r{0u, false};
+            if (span_e0 + t < span_e1) {
+                r.raw = a.e_idx[span_e0 + t];
+                r.valid = true;
             }
             return r;
         };
-        auto issue = [&](const Row& r, int half) {
+        auto src_of = [&](const Row& r) -> const float* {
+            if (!r.valid) return nullptr;
+            const uint32_t idx = r.raw & IDX_MASK;
+            return idx < n_rows ? a.feat + (int64_t)idx * a.ldf : a.aux + (int64_t)(idx - n_rows) * 64;
+        };
+        auto issue = [&](const float* src, int half) {
             mbar_wait(aempty + s_issue, ph_issue ^ 1);
             const uint32_t dst = a_base + (uint32_t)(s_issue * 2 * A_HALF) + row_off;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int col = half * 32 + 4 * c;
-                const bool ok = r.src != nullptr && col < a.kin;
-                cp_async16_zfill(dst + (((uint32_t)c ^ sw) << 4), ok ? (const void*)(r.src + col) : (const void*)a.feat, ok ? 16 : 0);
+            for (int i = 0; i < 4; ++i) {
+                const int c = 4 * part + i, col = half * 32 + 4 * c;
+                const bool ok = src != nullptr && col < a.kin;
+                cp_async16_zfill(dst + (((uint32_t)c ^ sw) << 4), ok ? (const void*)(src + col) : (const void*)a.feat, ok ? 16 : 0);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             if (++s_issue == STAGES) {
@@ -289,18 +313,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_etile_tc(const TcArgs a) {
                 ph_issue ^= 1;
             }
         };
-        auto finish = [&](bool real) {   // split the oldest issued stage (this thread's own row) and publish it
+        auto finish = [&](bool relu_row) {   // split this thread's own four chunks of the oldest issued stage and publish it
             float4* hi = reinterpret_cast<float4*>(sm + (size_t)s_done * 2 * A_HALF + row_off);
             float4* lo = reinterpret_cast<float4*>(sm + (size_t)s_done * 2 * A_HALF + A_HALF + row_off);
+            float4 v[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int c = i ^ (int)sw;       // rotated chunk order: 8 consecutive lanes hit 8 different bank groups
-                float4 v = hi[c], h, l;
-                if (a.relu && real) {
-                    v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
-                }
-                h.x = rn_tf32(v.x), h.y = rn_tf32(v.y), h.z = rn_tf32(v.z), h.w = rn_tf32(v.w);
-                l.x = rn_tf32(v.x - h.x), l.y = rn_tf32(v.y - h.y), l.z = rn_tf32(v.z - h.z), l.w = rn_tf32(v.w - h.w);
+            for (int i = 0; i < 4; ++i) v[i] = hi[(4 * part + i) ^ (int)sw];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = (4 * part + i) ^ (int)sw;
+                float4 x = v[i], h, l;
+                if (relu_row) x.x = fmaxf(x.x, 0.f), x.y = fmaxf(x.y, 0.f), x.z = fmaxf(x.z, 0.f), x.w = fmaxf(x.w, 0.f);
+                h.x = rn_tf32(x.x), h.y = rn_tf32(x.y), h.z = rn_tf32(x.z), h.w = rn_tf32(x.w);
+                l.x = rn_tf32(x.x - h.x), l.y = rn_tf32(x.y - h.y), l.z = rn_tf32(x.z - h.z), l.w = rn_tf32(x.w - h.w);
                 hi[c] = h;
                 lo[c] = l;
             }
@@ -309,44 +334,114 @@ __global__ void __launch_bounds__(THREADS, 1) k_etile_tc(const TcArgs a) {
             if (lane == 0) mbar_arrive(afull + s_done);
             if (++s_done == STAGES) s_done = 0;
         };
-        TileSeq ts(a.num_stiles);
-        if (ts.cur() >= 0) {
-            Row cur = row_of(ts.cur());
-            issue(cur, 0);
-            while (true) {
+        // Look-ahead, so that no dependent load sits in front of the copies: entry spans and index words are read
+        // LOOK tiles ahead, a row is pulled towards L2 (one 128-byte line per thread) LOOK - 1 tiles ahead — at
+        // 10x AM-shape every gathered row is a TLB miss on top of a DRAM access — and the copies of tile i+1 are
+        // issued before tile i is split.
+        auto prefetch_l2 = [&](const Row& r) {
+            const float* p = src_of(r);
+            if (p != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32 * part) : "memory");
+        };
+        TileSeq ts(a.num_stiles);           // cursor of the tile whose entry span is read next (4 ahead of `cur`)
+        bool span_ok = false;
+        auto advance_span = [&]() {         // returns whether the PREVIOUS span was a tile; loads the next one
+            const bool had = span_ok;
+            span_ok = ts.cur() >= 0;
+            if (span_ok) {
+                load_span(ts.cur());
                 ts.next();
-                const bool more = ts.cur() >= 0;
-                Row nxt{nullptr, false};
-                if (more) nxt = row_of(ts.cur());           // the next tile's index load overlaps this tile's copies
-                issue(cur, 1);
+            }
+            return had;
+        };
+        struct Fetched {
+            Row first;
+            bool second;
+        };
+        advance_span();
+        auto fetch_next = [&]() {           // index word of the tile whose span was read one step ago
+            Fetched f{Row{0u, false}, false};
+            if (span_ok) {
+                f.first = row_of_span();
+                f.second = true;
+            }
+            advance_span();
+            return f;
+        };
+        // queue of LOOK tiles: [0] = the tile being gathered, [1] = the next one (its copies are issued before [0] is
+        // split), [LOOK - 1] = the farthest one, whose row is prefetched towards L2 as soon as its index arrives
+        constexpr int LOOK = 6;
+        Row q[LOOK];
+        bool has[LOOK];
+#pragma unroll
+        for (int i = 0; i < LOOK; ++i) {
+            const Fetched f = fetch_next();
+            q[i] = f.first;
+            has[i] = f.second;
+        }
+        if (has[0]) {
+#pragma unroll
+            for (int i = 1; i < LOOK - 1; ++i)
+                if (has[i]) prefetch_l2(q[i]);
+            const float* src = src_of(q[0]);
+            issue(src, 0);
+            while (true) {
+                const Fetched f = fetch_next();                  // index of the tile LOOK ahead (consumed LOOK - 1 trips later)
+                if (has[LOOK - 1]) prefetch_l2(q[LOOK - 1]);     // its predecessor's row -> L2
+                const bool relu_row = a.relu && q[0].valid && (q[0].raw & IDX_MASK) < n_rows;
+                issue(src, 1);
                 asm volatile("cp.async.wait_group 1;" ::: "memory");
-                finish(cur.real);                            // half 0 of the current tile
-                if (more) {
-                    issue(nxt, 0);
+                finish(relu_row);                                // half 0 of the current tile
+                const float* src1 = has[1] ? src_of(q[1]) : nullptr;
+                if (has[1]) {
+                    issue(src1, 0);
                     asm volatile("cp.async.wait_group 1;" ::: "memory");
                 } else {
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
                 }
-                finish(cur.real);                            // half 1
-                if (!more) break;
-                cur = nxt;
+                finish(relu_row);                                // half 1
+                if (!has[1]) break;
+#pragma unroll
+                for (int i = 0; i < LOOK - 1; ++i) {
+                    q[i] = q[i + 1];
+                    has[i] = has[i + 1];
+                }
+                q[LOOK - 1] = f.first;
+                has[LOOK - 1] = f.second;
+                src = src1;
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 12) {
         // ===== epilogue: thread t <-> TMEM lane t <-> row t =====
-        const int ew = warp - 8, t = ew * 32 + lane;
+        const int ew = warp - 12, t = ew * 32 + lane;
         float* my_row = reinterpret_cast<float*>(out_stage + t * OUT_STRIDE);
         int acc = 0;
         uint32_t aph = 0;
-        for (TileSeq ts(a.num_stiles); ts.cur() >= 0; ts.next()) {
-            const int tile = ts.cur();
-            const int e0 = a.stile_e0[tile], cnt = a.stile_e0[tile + 1] - e0;
-            int own = -1;
-            float w = 0.f;
-            if (t < cnt) {
-                own = a.e_own[e0 + t];
-                w = a.e_w[e0 + t];
+        // the row's owner / weight are read two tiles ahead of their use (a DRAM round trip in front of every
+        // tile's scatter would otherwise bound the whole pipeline)
+        struct Meta {
+            int own;
+            float w;
+        };
+        TileSeq ahead(a.num_stiles);
+        auto fetch_meta = [&]() {
+            Meta m{-1, 0.f};
+            if (ahead.cur() >= 0) {
+                const int tile = ahead.cur();
+                const int e0 = a.stile_e0[tile], cnt = a.stile_e0[tile + 1] - e0;
+                if (t < cnt) {
+                    m.own = a.e_own[e0 + t];
+                    m.w = a.e_w[e0 + t];
+                }
+                ahead.next();
             }
+            return m;
+        };
+        Meta m0 = fetch_meta(), m1 = fetch_meta();
+        for (TileSeq ts(a.num_stiles); ts.cur() >= 0; ts.next()) {
+            const Meta m2 = fetch_meta();
+            const int own = m0.own;
+            const float w = m0.w;
+            m0 = m1, m1 = m2;
             mbar_wait(acc_full + acc, aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * ACC_COLS);
