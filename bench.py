@@ -271,6 +271,9 @@ def run_engine(args):
     if args.workload == 'am10x_h64_bases30_frozenW':        # BASELINE.json configs[4]
         from rgcn_b200 import workloads
         return workloads.run(args, rank, world, device, METRIC, UNIT)
+    if args.workload == 'multi_summary':                    # BASELINE.json configs[2]
+        from rgcn_b200 import workloads
+        return workloads.run_multi_summary(args, rank, world, device, METRIC, UNIT)
     if world > 1:
         from rgcn_b200 import partition
         return partition.run_partitioned_bench(args, rank, world, device, METRIC, UNIT)
@@ -517,7 +520,7 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', choices=['engine', 'reference'], default='engine')
-    ap.add_argument('--workload', choices=['am_63_16_11', 'am10x_h64_bases30_frozenW'], default='am_63_16_11',
+    ap.add_argument('--workload', choices=['am_63_16_11', 'am10x_h64_bases30_frozenW', 'multi_summary'], default='am_63_16_11',
                     help='am_63_16_11 = BASELINE.json configs[3] (the headline); am10x_... = configs[4]')
     ap.add_argument('--scale', type=float, default=1.0, help='AM-shape scale (1.0 = the BASELINE.json config)')
     ap.add_argument('--ref-scale', type=float, default=1 / 32, help='bounded sample for the CPU reference arm')

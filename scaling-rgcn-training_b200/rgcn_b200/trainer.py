@@ -212,3 +212,77 @@ class Trainer:
         td = org.training_data
         test = evaluate(model, activation, td, td.x_test, td.y_test)
         return acc, loss, f1_w, f1_m, test[0], test[1], test[2], model
+
+
+PARALLEL_SEMANTICS = ('parallel multi-summary pre-training: one summary graph per rank and round, every step the 6 R-GCN '
+                      'weight gradients are averaged over the ranks (one flat all-reduce), embeddings stay local; the '
+                      'reference trains the summaries ONE AFTER ANOTHER with carried weights and a fresh Adam each '
+                      '(model/modelTrainer.py:76-82) — same per-graph step arithmetic, different weight trajectory')
+
+
+def train_summaries_parallel(sum_graphs: list, num_classes: int, hidden_l: int, epochs: int, emb_dim: int, lr: float,
+                             weight_d: float, device, layers_cls=None, group=None, fused_adam: bool = True,
+                             seed: int = 0) -> dict:
+    """BASELINE.json configs[2]: multi-summary pre-training with one summary graph per GPU.
+
+    Rank r of P trains summary graphs r, r + P, ... (one per ROUND); within a round every rank runs the reference's
+    iteration body (modelTrainer.py:61-69: BCE on sigmoid outputs for summary models) on ITS graph and embedding,
+    and the gradients of the shared R-GCN parameters (rgcn1/rgcn2 weight, root, bias) are averaged over the ranks that
+    hold a graph in this round before the optimiser step, so every rank applies the same update to the same weights.
+    Returns {'model', 'losses' (this rank's, per round), 'embeddings' {graph index: tensor}, 'semantics'}; each graph
+    also gets ``.embedding`` like modelTrainer.py:82.  Works on any torch.distributed backend (gloo in the CPU test)."""
+    import torch.distributed as dist
+    if layers_cls is None:
+        from .layers import Emb_Layers as layers_cls
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    first = sum_graphs[0]
+    torch.manual_seed(seed)                                   # identical replicated weights on every rank
+    model = layers_cls(2 * len(first.relations) + 1, hidden_l, num_classes, first.num_nodes, emb_dim, len(sum_graphs))
+    shared = [p for conv in (model.rgcn1, model.rgcn2) for p in (conv.weight, conv.root, conv.bias)]
+    loss_f, activation = get_losst('', sumModel=True)
+    rounds = (len(sum_graphs) + world - 1) // world
+    losses, embeddings = [], {}
+    for rnd in range(rounds):
+        gi = rnd * world + rank
+        mine = sum_graphs[gi] if gi < len(sum_graphs) else None
+        active = float(min(world, len(sum_graphs) - rnd * world))
+        if mine is not None:
+            torch.manual_seed(seed + 1000 + gi)               # the fresh N(0,1) embedding of this graph
+            model.reset_embedding(mine.num_nodes, emb_dim)
+        model = model.to(device)
+        td = mine.training_data.to(device) if mine is not None else None
+        use_fused = fused_adam and torch.device(device).type == 'cuda'
+        opt = make_optimizer(model, lr, weight_d, fused=use_fused)
+        curve = []
+        for _ in range(epochs):
+            model.train()
+            opt.zero_grad()
+            if mine is not None:
+                out = model(td, activation)
+                loss = loss_f(out[td.x_train], td.y_train.to(torch.float32))
+                loss.backward()
+                curve.append(float(loss.item()))
+            if world > 1:
+                flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in shared])
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+                flat /= active
+                off = 0
+                for p in shared:
+                    g = flat[off:off + p.numel()].view_as(p)
+                    off += p.numel()
+                    if p.grad is None:
+                        p.grad = g.clone()
+                    else:
+                        p.grad.copy_(g)
+            if mine is None:                                  # an idle rank still follows the shared weights
+                for p in model.parameters():
+                    if not any(p is q for q in shared):
+                        p.grad = None
+            opt.step()
+        losses.append(curve)
+        if mine is not None:
+            mine.embedding = model.embedding.weight.detach().clone()
+            embeddings[gi] = mine.embedding
+    return {'model': model, 'losses': losses, 'embeddings': embeddings, 'semantics': PARALLEL_SEMANTICS,
+            'rounds': rounds, 'world': world}

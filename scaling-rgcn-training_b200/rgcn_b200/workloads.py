@@ -207,3 +207,90 @@ def run(args, rank: int, world: int, device, metric: str, unit: str) -> None:
         torch.cuda.synchronize(device)
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2]: multi-summary pre-training, one summary graph per GPU
+# ----------------------------------------------------------------------------------------------------------------
+MULTI_SUMMARY = 'multi_summary_pretraining_8_aifb_summaries'
+
+
+def _golden_summary_graphs(count: int, classes: int):
+    """`count` AIFB-sized summary graphs: the real AIFB attr / bisim summaries shipped as fixtures (tests/golden/,
+    made by the reference's own Graph.init_graph), cycled, each with its own seeded fractional labels."""
+    import types
+    import numpy as np
+    from .data import Data
+    here = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    names = ['AIFB_sum_in', 'AIFB_sum_in_out', 'AIFB_bisim_k3']
+    out = []
+    for k in range(count):
+        g = dict(np.load(os.path.join(here, 'tests', 'golden', f'graph_{names[k % len(names)]}.npz'), allow_pickle=False))
+        buf = torch.from_numpy(np.concatenate([g['edge_index'], g['edge_type'][None]], 0).astype(np.int64).T.copy())
+        edge = buf.t()
+        n, r = int(g['num_nodes']), int(g['num_relations'])
+        sg = types.SimpleNamespace(num_nodes=n, relations={f'p{i}': i for i in range((r - 1) // 2)}, name=names[k % len(names)])
+        td = Data(edge_index=edge[:2])
+        td.edge_type = edge[2]
+        gen = torch.Generator().manual_seed(100 + k)
+        td.x_train = torch.randperm(n, generator=gen)[:max(2, n // 2)]
+        td.y_train = torch.rand(td.x_train.numel(), classes, generator=gen)     # summary labels are fractions (BCE)
+        sg.training_data = td
+        out.append(sg)
+    return out
+
+
+def run_multi_summary(args, rank: int, world: int, device, metric: str, unit: str) -> None:
+    import bench as B
+    from . import _lib
+    from .trainer import PARALLEL_SEMANTICS, train_summaries_parallel
+    graphs = _golden_summary_graphs(8, 26)
+    epochs = max(args.steps, 1)
+    edges = sum(g.training_data.edge_type.numel() for g in graphs)
+    # warm-up: CSR builds, lazy module loads (the graphs are cached by tensor identity inside RGCNConv)
+    for g in graphs:
+        g.training_data.to(device)
+    train_summaries_parallel(graphs, 26, 16, 2, 63, 0.01, 5e-5, device, seed=0)
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    sampler = B.ClockSampler(device.index)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    res = train_summaries_parallel(graphs, 26, 16, epochs, 63, 0.01, 5e-5, device, seed=0)
+    t1.record()
+    torch.cuda.synchronize(device)
+    ms = torch.tensor([t0.elapsed_time(t1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = float(ms.item())
+    value = edges * epochs / (total_ms * 1e-3)
+    first, last = res['losses'][0][0], res['losses'][-1][-1]
+    if rank == 0:
+        line = {
+            'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': epochs, 'warmup': 2,
+            'ms_per_step': total_ms / epochs, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'real AIFB summary graphs (tests/golden fixtures), seeded labels',
+            'config': {'workload': MULTI_SUMMARY, 'summaries': [g.name for g in graphs], 'directed_edges_all_summaries': edges,
+                       'epochs': epochs, 'rounds': res['rounds'], 'emb': 63, 'hidden': 16, 'classes': 26,
+                       'step': 'Trainer.train iteration body per summary (fwd, BCE on sigmoid, bwd, FusedAdam, loss.item()); '
+                               'value = edges of all summaries x epochs / wall time of the whole pre-training',
+                       'semantics': PARALLEL_SEMANTICS if world > 1 else
+                       'sequential with carried weights and a fresh Adam per summary = the reference (modelTrainer.py:76-82)',
+                       'loss_first_last_rank0': [first, last],
+                       'l2_policy': 'L2-resident working set (52 MB per summary step): reported, not graded against HBM'},
+            'clocks': clocks, 'gpu_launches': int(_lib.launch_count() - l0), 'e2e': {
+                'value': value, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 4 * min(world, 8),
+                'ms_per_step': total_ms / epochs, 'what': 'same run: the loss of every summary is read back every epoch'},
+            'roofline': None, 'cpu_baseline': None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.cuda.synchronize(device)
+        dist.barrier()
+        dist.destroy_process_group()
