@@ -70,6 +70,9 @@ class MLPHead(nn.Module):
             nn.init.kaiming_uniform_(lin.weight, mode='fan_in')
 
     def forward(self, e_cat: torch.Tensor) -> torch.Tensor:
+        if e_cat.is_cuda and os.environ.get('RGCN_B200_ENGINE_HEAD', '1') != '0':
+            from .heads import mlp_head                       # the engine's tcgen05 contraction (csrc/gemm_tc.cu)
+            return mlp_head(e_cat, self.lin1, self.lin2)
         return self.lin2(torch.tanh(self.lin1(e_cat)))
 
 
@@ -148,7 +151,8 @@ def run(args, rank: int, world: int, device, metric: str, unit: str) -> None:
     e2e = None
     if not args.no_e2e:
         head = MLPHead().to(device)
-        e_cat = torch.randn(hi - lo, SUMS * EMB, generator=torch.Generator().manual_seed(3)).to(device)
+        from .heads import rows16
+        e_cat = rows16(torch.randn(hi - lo, SUMS * EMB, generator=torch.Generator().manual_seed(3)).to(device))   # frozen: rows padded once
         x_all, y_all = labelled_split(n, CLASSES)
         mine = (x_all >= lo) & (x_all < hi)
         x_h, y_h = (x_all[mine] - lo).contiguous().pin_memory(), y_all[mine].contiguous().pin_memory()
@@ -177,7 +181,7 @@ def run(args, rank: int, world: int, device, metric: str, unit: str) -> None:
             dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
         e2e = {'value': e / (e2e_ms * 1e-3), 'unit': unit, 'h2d_bytes_per_step': int(h2d.item()),
                'd2h_bytes_per_step': 4 * world, 'ms_per_step': e2e_ms,
-               'what': 'x0 = lin2(tanh(lin1(E_cat))) (MLP transfer head, the only trainable part; torch library GEMMs), '
+               'what': 'x0 = lin2(tanh(lin1(E_cat))) (MLP transfer head, the only trainable part; forward and dL/dh on the engine tcgen05 kernel, parameter-gradient reductions in torch), '
                        'the two frozen basis layers, CE loss on the labelled batch from pinned host memory, backward '
                        'into the head, FusedAdam on the head, loss.item()'}
     if rank == 0:
