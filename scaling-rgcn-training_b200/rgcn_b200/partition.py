@@ -195,11 +195,17 @@ class NvlComm(RowComm):
             self.multicast = int(self._ctl_h.multicast_ptr) != 0
         except Exception:
             self.multicast = False
-        # multicast (multimem.*) or plain peer pointers: measured on 2 B200s the peer-pointer kernels move the
-        # 16-wide rows at 560 GB/s against 305 GB/s through the 2-member multicast group; with more ranks the
-        # multicast store sends the shard once instead of P-1 times (RGCN_B200_NVL_MODE: 1 multicast, 2 peers)
+        # multicast (multimem.*) or plain peer pointers (RGCN_B200_NVL_MODE: 1 multicast, 2 peers).  Measured
+        # (tools/probe_nvl.py, 16-wide rows of the AM-shape graph, ms per exchange incl. the barrier):
+        #   ranks   all-gather mc / peers    reduce-scatter mc / peers
+        #     2        0.174 / 0.095            0.177 / 0.102
+        #     4        0.175 / 0.147            0.172 / 0.161
+        #     8        0.169 / 0.163            0.165 / 0.183
+        # a multicast exchange costs the same at every rank count (every copy of the buffer, the local one
+        # included, is written through the switch: 107 MB in 0.17 ms = 630 GB/s of link ingress); peer pointers
+        # keep the local share off the links, which wins up to 4 ranks
         mode = os.environ.get('RGCN_B200_NVL_MODE')
-        self.mode = int(mode) if mode else (1 if self.multicast and self.world > 2 else 2)
+        self.mode = int(mode) if mode else (1 if self.multicast and self.world > 4 else 2)
         _lib.set_option(_lib.OPT_NVL_MODE, self.mode)
         self.handoff = None          # (data_ptr of an exchanged tensor, its gathered rows): see all_gather_rows
 
