@@ -279,14 +279,15 @@ def bench_heads(n, r, data, x_train_h, y_train_h, device, world, args, peak):
     # Trainer step per experiment model (labelled batch from pinned host memory, loss.item())
     steps = {}
     e_stack = e_cat.view(n, S, EMB).permute(1, 0, 2).contiguous()
-    models = {'summation': None, 'mlp': mlp, 'mlp_torch_head': mlp, 'attention': None}
+    models = {'summation': None, 'mlp': mlp, 'mlp_torch_head': mlp, 'attention': None, 'attention_torch_head': None}
     for name in models:
         if name == 'summation':
             m = Emb_Layers(r, HIDDEN, CLASSES, n, EMB, S)
             m.load_embedding(e_cat[:, :EMB].contiguous(), freeze=True)
-        elif name == 'attention':
+        elif name.startswith('attention'):
             m = Emb_ATT_Layers(r, HIDDEN, CLASSES, n, EMB, S)
             m.load_embedding(e_stack, freeze=True)
+            m.engine_head = name == 'attention'
         else:
             m = mlp
             m.engine_head = name == 'mlp'
@@ -304,11 +305,13 @@ def bench_heads(n, r, data, x_train_h, y_train_h, device, world, args, peak):
             return loss.item()
         steps[name] = time_steps(step, min(args.steps, 10), 3, world, device) / min(args.steps, 10)
         del opt
-        if name in ('summation', 'attention'):
+        if name == 'summation' or name.startswith('attention'):
             del m
+            torch.cuda.empty_cache()
     out['trainer_step_ms'] = steps
     out['what'] = ('frozen transferred summary embeddings (S = 3), -e_freeze True; mlp = engine tcgen05 head, mlp_torch_head = '
-                   'nn.Linear calls, attention = nn.MultiheadAttention (torch)')
+                   'nn.Linear calls, attention = engine head (tcgen05 projections + one softmax kernel, query position 0 only), '
+                   'attention_torch_head = nn.MultiheadAttention')
     return out
 
 

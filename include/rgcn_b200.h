@@ -244,6 +244,20 @@ int rgcn_gemm3x_tf32(const float* a, int64_t lda, int64_t m, int32_t k, const fl
                      int32_t n_pad, int32_t k_pad, const float* bias_padded, int32_t act, float* c, int64_t ldc,
                      int32_t n_store, void* stream);
 
+/* Per-node core of the attention transfer head (reference model/layers.py:59-61: nn.MultiheadAttention over the
+ * num_sums stacked summary embeddings, q = k = v, only attn_output[0] kept).  q [N, heads*head_dim] = the projected
+ * query rows of summary 0 (bias added, unscaled); kv [num_sums*N, 2*heads*head_dim] = projected keys | values, row
+ * s*N + b for summary s; keep_scaled (nullable) [N, heads, num_sums] = dropout keep mask times 1/(1-p).
+ * fwd: probs [N, heads, num_sums] = softmax_s(q.k_s / sqrt(head_dim)) (before dropout), o [N, heads*head_dim].
+ * bwd: gq, gkv from dL/do (go); every element of gq / gkv is written. */
+int rgcn_attn_head_fwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, int32_t num_sums,
+                       int64_t num_nodes, int32_t heads, int32_t head_dim, const float* keep_scaled, float* probs,
+                       float* o, int64_t ldo, void* stream);
+int rgcn_attn_head_bwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, int32_t num_sums,
+                       int64_t num_nodes, int32_t heads, int32_t head_dim, const float* keep_scaled,
+                       const float* probs, const float* go, int64_t ldgo, float* gq, int64_t ldgq, float* gkv,
+                       int64_t ldgkv, void* stream);
+
 /* Instrumentation (no reference counterpart).  rgcn_kernel_launch_count: engine kernels launched
  * by this process so far.  rgcn_profile_enable(1): every pass launch is bracketed by a CUDA-event
  * pair on its own stream; rgcn_profile_collect synchronises those events, returns up to

@@ -8,6 +8,12 @@ zero-padded 64-wide rows, i.e. the 16-byte addressable layout the first R-GCN la
 layer needs no padding copy of x0.  Backward: ``dL/dh`` through the same kernel (W2 as the transposed
 operand); the parameter gradients are reductions over all nodes with tiny outputs (137 x 189) and go
 through torch matmuls on the saved activations.
+
+Attention head: ``x0 = MHA(E, E, E)[0]`` with S heads over the S stacked summary embeddings.  Only query position 0 is
+kept by the reference, so the engine projects Q from summary 0 alone and K | V from all S summaries (two tcgen05
+contractions), runs the per-(node, head) S-way softmax in one kernel (csrc/attn_head.cu) and writes ``out_proj``'s
+result into the same 64-wide mirror rows.  Training-mode dropout draws the reference's own mask (a dropout over a
+ones tensor of the [N * heads, S, S] attention-weight shape, the call nn.MultiheadAttention makes) and keeps row 0.
 """
 from __future__ import annotations
 
@@ -117,3 +123,99 @@ class _MLPHeadFn(torch.autograd.Function):
 def mlp_head(e_cat: Tensor, lin1: torch.nn.Linear, lin2: torch.nn.Linear) -> Tensor:
     """lin2(tanh(lin1(e_cat))) (reference model/layers.py:105-107) on the engine."""
     return _MLPHeadFn.apply(e_cat, lin1.weight, lin1.bias, lin2.weight, lin2.bias)
+
+
+def _flat_rows16(e: Tensor) -> Tensor:
+    """e [S, N, emb] as [S * N, emb] rows with 16-byte addressable rows: a view when e already is one padded block
+    (Emb_ATT_Layers caches frozen embeddings that way), else a padded copy."""
+    s, n, emb = e.shape
+    if e.stride(2) == 1 and e.stride(1) % 4 == 0 and e.stride(0) == n * e.stride(1) and e.data_ptr() % 16 == 0:
+        return e.as_strided((s * n, emb), (e.stride(1), 1))
+    return rows16(e.reshape(s * n, emb))
+
+
+def stack_rows16(e: Tensor) -> Tensor:
+    """[S, N, emb] -> the same values as a view of one zero-padded [S, N, ceil4(emb)] block."""
+    s, n, emb = e.shape
+    buf = torch.zeros((s, n, _pad(emb, 4)), dtype=torch.float32, device=e.device)
+    buf[:, :, :emb] = e
+    return buf[:, :, :emb]
+
+
+class _AttentionHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, e: Tensor, w_in: Tensor, b_in: Tensor, w_out: Tensor, b_out: Tensor, keep: Optional[Tensor],
+                heads: int) -> Tensor:
+        lib = _lib.load()
+        s, n, emb = e.shape
+        d = emb // heads
+        e_flat = _flat_rows16(e)
+        q = gemm(e_flat[:n], w_in[:emb], b_in[:emb] if b_in is not None else None)
+        kv = gemm(e_flat, w_in[emb:], b_in[emb:] if b_in is not None else None)       # [S * N, 2 emb]: keys | values
+        probs = torch.empty((n, heads, s), dtype=torch.float32, device=e.device)
+        ldo = _pad(emb, 4)
+        o = torch.empty((n, ldo), dtype=torch.float32, device=e.device)       # pad columns are never read (TMA bounds)
+        with torch.cuda.device(e.device):
+            rc = lib.rgcn_attn_head_fwd(q.data_ptr(), q.stride(0), kv.data_ptr(), kv.stride(0), s, n, heads, d,
+                                        keep.data_ptr() if keep is not None else None, probs.data_ptr(), o.data_ptr(), ldo,
+                                        _stream(e.device))
+        _lib.check(rc, 'rgcn_attn_head_fwd')
+        o = o[:, :emb]
+        x0 = gemm(o, w_out, b_out, out_ld=ldo)
+        ctx.save_for_backward(e_flat, q, kv, probs, o, w_in, w_out, keep)
+        ctx.dims = (s, n, emb, heads, d, b_in is not None)
+        return x0
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        lib = _lib.load()
+        e_flat, q, kv, probs, o, w_in, w_out, keep = ctx.saved_tensors
+        s, n, emb, heads, d, has_b_in = ctx.dims
+        need_e, need_w_in, need_b_in, need_w_out, need_b_out = ctx.needs_input_grad[:5]
+        g = g.contiguous()
+        gw_out = g.t() @ o if need_w_out else None
+        gb_out = g.sum(0) if need_b_out else None
+        ge = gw_in = gb_in = None
+        if need_e or need_w_in or need_b_in:
+            go = gemm(g, w_out, transpose_w=True)                                       # dL/do [N, emb]
+            gq = torch.empty((n, _pad(emb, 4)), dtype=torch.float32, device=g.device)
+            gkv = torch.empty((s * n, _pad(2 * emb, 4)), dtype=torch.float32, device=g.device)
+            with torch.cuda.device(g.device):
+                rc = lib.rgcn_attn_head_bwd(q.data_ptr(), q.stride(0), kv.data_ptr(), kv.stride(0), s, n, heads, d,
+                                            keep.data_ptr() if keep is not None else None, probs.data_ptr(),
+                                            go.data_ptr(), go.stride(0), gq.data_ptr(), gq.stride(0), gkv.data_ptr(),
+                                            gkv.stride(0), _stream(g.device))
+            _lib.check(rc, 'rgcn_attn_head_bwd')
+            gq, gkv = gq[:, :emb], gkv[:, :2 * emb]
+            if need_w_in:
+                gw_in = torch.cat([gq.t() @ e_flat[:n], gkv.t() @ e_flat], 0)
+            if need_b_in and has_b_in:
+                gb_in = torch.cat([gq.sum(0), gkv.sum(0)], 0)
+            if need_e:
+                ge = gemm(gkv, w_in[emb:], transpose_w=True).contiguous()
+                ge[:n] += gemm(gq, w_in[:emb], transpose_w=True)
+                ge = ge.view(s, n, emb)
+        return ge, gw_in, gb_in, gw_out, gb_out, None, None
+
+
+def attention_keep_mask(num_nodes: int, heads: int, num_sums: int, p: float, device) -> Tensor:
+    """The dropout keep mask (scaled by 1 / (1 - p)) of query position 0, drawn the way nn.MultiheadAttention draws it:
+    one dropout over the [N * heads, L = S, S] attention weights (torch/nn/functional.py multi_head_attention_forward),
+    so the same generator state gives the same mask as the reference module."""
+    ones = torch.ones((num_nodes * heads, num_sums, num_sums), dtype=torch.float32, device=device)
+    return torch.nn.functional.dropout(ones, p=p, training=True)[:, 0, :].contiguous()
+
+
+def attention_head(e: Tensor, att: torch.nn.MultiheadAttention) -> Tensor:
+    """att(e, e, e)[0][0] (reference model/layers.py:59-61; e [S, N, emb], S heads) on the engine."""
+    s, n, emb = e.shape
+    if att.in_proj_weight is None or att.batch_first or att.bias_k is not None or att.add_zero_attn or emb % att.num_heads:
+        raise _lib.EngineError('attention_head: serves the reference configuration (packed in_proj, sequence-first, '
+                               'no bias_k / zero_attn)')
+    if s > 8 or emb // att.num_heads > 64:
+        raise _lib.EngineError('attention_head: at most 8 summaries and head_dim <= 64')
+    keep = None
+    if att.training and att.dropout > 0.0:
+        keep = attention_keep_mask(n, att.num_heads, s, att.dropout, e.device)
+    return _AttentionHeadFn.apply(e, att.in_proj_weight, att.in_proj_bias, att.out_proj.weight, att.out_proj.bias, keep,
+                                  att.num_heads)

@@ -114,8 +114,20 @@ class Emb_ATT_Layers(_TwoLayerRGCN):
         self.att = nn.MultiheadAttention(embed_dim=emb_dim, num_heads=num_embs, dropout=0.2)
         self._build_convs(num_relations, hidden_l, num_labels, emb_dim)
 
+    # engine extension (default on, RGCN_B200_ENGINE_HEAD=0 restores the nn.MultiheadAttention call): projections on
+    # the tcgen05 kernel, the per-node softmax in one kernel, query position 0 only (rgcn_b200.heads.attention_head)
+    engine_head = os.environ.get('RGCN_B200_ENGINE_HEAD', '1') != '0'
+
     def _input_features(self) -> Tensor:
         e = self.embedding
+        if self.engine_head and e.is_cuda:
+            from .heads import attention_head, stack_rows16
+            if not e.requires_grad:                      # frozen summary embeddings: pad their rows once
+                key = (e.data_ptr(), e._version, tuple(e.shape))
+                if getattr(self, '_e16_key', None) != key:
+                    self._e16, self._e16_key = stack_rows16(e.detach()), key
+                e = self._e16
+            return attention_head(e, self.att)
         attended, _ = self.att(e, e, e, average_attn_weights=True)
         return attended[0]
 

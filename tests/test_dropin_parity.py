@@ -308,3 +308,34 @@ def test_engine_mlp_head_matches_torch_head_with_gradients():
         assert rel_err(x, x_ref) < TOL
         for a, b in zip(got, ref):
             assert rel_err(a, b) < 2e-5, rel_err(a, b)   # (torch's own fp32 matmuls are the looser side here)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n,S,emb', [(3000, 3, 63), (257, 2, 32), (1000, 5, 40), (1, 3, 63)])
+def test_engine_attention_head_matches_torch_mha_with_gradients(n, S, emb):
+    """x0 = att(e, e, e)[0][0] (reference model/layers.py:59-61): the engine head (query position 0 only, tcgen05
+    projections, one softmax kernel) against nn.MultiheadAttention itself, eval mode and — same generator state, hence
+    the same dropout mask — training mode; all parameter gradients and the embedding gradient."""
+    from rgcn_b200.heads import attention_head
+    torch.manual_seed(n + S)
+    att = torch.nn.MultiheadAttention(embed_dim=emb, num_heads=S, dropout=0.2).to(DEV)
+    with torch.no_grad():
+        att.in_proj_bias.uniform_(-0.3, 0.3)
+        att.out_proj.bias.uniform_(-0.3, 0.3)
+    params = [att.in_proj_weight, att.in_proj_bias, att.out_proj.weight, att.out_proj.bias]
+    for training in (False, True):
+        att.train(training)
+        for freeze in (True, False):
+            e = torch.randn(S, n, emb, device=DEV, requires_grad=not freeze)
+            g = torch.randn(n, emb, device=DEV)
+            wrt = ([e] if not freeze else []) + params
+            torch.manual_seed(7)
+            x_ref = att(e, e, e, average_attn_weights=True)[0][0]
+            ref = torch.autograd.grad(x_ref, wrt, g)
+            torch.manual_seed(7)
+            x = attention_head(e, att)
+            assert x.stride(0) == (emb + 3) // 4 * 4 and x.data_ptr() % 16 == 0
+            got = torch.autograd.grad(x, wrt, g)
+            assert rel_err(x, x_ref) < TOL, (training, rel_err(x, x_ref))
+            for a, b in zip(got, ref):
+                assert a.shape == b.shape and rel_err(a, b) < 2e-5, (training, freeze, rel_err(a, b))
