@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RGCN_B200_ABI_VERSION 5
+#define RGCN_B200_ABI_VERSION 6
 
 typedef enum {
     RGCN_OK = 0,
@@ -228,6 +228,18 @@ int rgcn_nvl_store_rows(float* src, int64_t lds, int32_t cols, const float* relu
                         int64_t row0, int64_t rows, void* stream);
 int rgcn_nvl_reduce_rows(const float* src_multicast, void* const* host_peers, int32_t num_peers, int64_t lds,
                          int64_t row0, int64_t rows, float* dst, int64_t ldd, int32_t width, void* stream);
+
+/* Sparse forms of the two exchanges (peer pointers only).  Which ranks reach a row is a property of the partitioned
+ * graph: a rank's partial output is non-zero only in the rows its own edges reach, and it reads gout only in those
+ * rows.  peer_mask[r]: bit p = rank p reaches row row0 + r (this rank's owned rows; its own bit set).
+ * reduce_rows_sparse: dst[r] = sum over the set bits p (ascending) of peer_p[(row0 + r) * lds ..] — bit-identical to
+ * the dense peer-pointer sum when the skipped rows are zero.  store_rows_sparse: rgcn_nvl_store_rows, each row
+ * written only into the copies of the ranks whose bit is set. */
+int rgcn_nvl_reduce_rows_sparse(void* const* host_peers, int32_t num_peers, const uint32_t* peer_mask, int64_t lds,
+                                int64_t row0, int64_t rows, float* dst, int64_t ldd, int32_t width, void* stream);
+int rgcn_nvl_store_rows_sparse(float* src, int64_t lds, int32_t cols, const float* relu_pre, int64_t ld_pre,
+                               void* const* host_peers, int32_t num_peers, const uint32_t* peer_mask, int64_t ldd,
+                               int64_t row0, int64_t rows, void* stream);
 
 /* Dense contractions of the path on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMA operand
  * loads, accumulators in tensor memory), fp32-faithful through the error-compensated 3xTF32 split:

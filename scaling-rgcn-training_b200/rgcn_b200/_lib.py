@@ -19,6 +19,7 @@ EXPORTS = (
     'rgcn_kernel_launch_count', 'rgcn_profile_enable', 'rgcn_profile_collect', 'rgcn_pad_rows',
     'rgcn_eval_counts', 'rgcn_adam_step', 'rgcn_adam_step_dev', 'rgcn_layer_chunk_rows_bytes', 'rgcn_layer_fwd_keep',
     'rgcn_layer_bwd_reuse', 'rgcn_set_option', 'rgcn_graph_create_push', 'rgcn_nvl_store_rows', 'rgcn_nvl_reduce_rows', 'rgcn_gemm_prepack', 'rgcn_gemm3x_tf32', 'rgcn_attn_head_fwd', 'rgcn_attn_head_bwd',
+    'rgcn_nvl_reduce_rows_sparse', 'rgcn_nvl_store_rows_sparse',
 )
 
 BRC_FWD, BRC_BWD, BRC_FWD_REL = 0, 1, 2
@@ -88,6 +89,10 @@ def load():
     lib.rgcn_pad_rows.argtypes = [vp, i64, i32, vp, i64, i64, vp]
     lib.rgcn_nvl_store_rows.restype = C.c_int
     lib.rgcn_nvl_store_rows.argtypes = [vp, i64, i32, vp, i64, vp, vp, i32, i64, i64, i64, vp]
+    lib.rgcn_nvl_reduce_rows_sparse.restype = C.c_int
+    lib.rgcn_nvl_reduce_rows_sparse.argtypes = [vp, i32, vp, i64, i64, i64, vp, i64, i32, vp]
+    lib.rgcn_nvl_store_rows_sparse.restype = C.c_int
+    lib.rgcn_nvl_store_rows_sparse.argtypes = [vp, i64, i32, vp, i64, vp, i32, vp, i64, i64, i64, vp]
     lib.rgcn_nvl_reduce_rows.restype = C.c_int
     lib.rgcn_nvl_reduce_rows.argtypes = [vp, vp, i32, i64, i64, i64, vp, i64, i32, vp]
     lib.rgcn_gemm_prepack.restype = C.c_int

@@ -58,6 +58,17 @@ class RGCNGraph:
                                             C.byref(handle))
         _lib.check(rc, 'rgcn_graph_create')
         self._h = handle
+        # source-partitioned: the rows of the full node set this rank's passes reach (destinations of the edges whose
+        # source is owned + the owned rows) — what its partial output can be non-zero in and what it gathers of gout;
+        # the sparse exchanges of partition.NvlComm are planned from it
+        self.touched = None
+        if self.push:
+            t = torch.zeros(self.num_nodes, dtype=torch.bool, device=self.device)
+            if self.num_edges:
+                own = (src >= self.own_lo) & (src < self.own_hi)
+                t[dst[own]] = True
+            t[self.own_lo:self.own_hi] = True
+            self.touched = t
         self._finalizer = weakref.finalize(self, lib.rgcn_graph_destroy, handle)
 
     @property

@@ -208,6 +208,24 @@ class NvlComm(RowComm):
         self.mode = int(mode) if mode else (1 if self.multicast and self.world > 4 else 2)
         _lib.set_option(_lib.OPT_NVL_MODE, self.mode)
         self.handoff = None          # (data_ptr of an exchanged tensor, its gathered rows): see all_gather_rows
+        self.sparse = None           # set_touched(): (peer_mask [n_own] int32, number of remote rows this rank reaches)
+        self.touched_frac = None
+
+    def set_touched(self, touched: Tensor, min_saving: float = 0.15) -> bool:
+        """Plan the sparse exchanges from the graph (collective: every rank calls it).  touched [num_nodes] bool = the
+        rows this rank's passes reach (RGCNGraph.touched): its partial output is zero elsewhere and it gathers gout
+        from nowhere else.  The reduce-scatter then reads an owned row only from the ranks that reach it and the
+        all-gather stores an owned row only into those ranks' copies — both over peer pointers.  Kept only when the remote rows drop
+        by at least min_saving on average (RGCN_B200_NVL_SPARSE=0 / 1 forces the choice); returns whether it is on."""
+        plan = sparse_plan(touched, self.ranges, self.rank, self.group)
+        self.touched_frac = plan['touched_frac_mean']
+        env = os.environ.get('RGCN_B200_NVL_SPARSE')
+        on = plan['remote_saving_mean'] >= min_saving if env is None else env != '0'
+        if on:
+            self.sparse = (plan['peer_mask'].to(self.device), int(plan['row_list'].numel()))
+        else:
+            self.sparse = None
+        return on
 
     def barrier(self) -> None:
         self._ctl_h.barrier(0)
@@ -245,6 +263,17 @@ class NvlComm(RowComm):
         buf, _, mc, peers = self._symm(('ag', key if key is not None else f, ld), self.rows, ld)
         if not self.steady_state:
             self.barrier()
+        if self.sparse is not None:
+            # every owned row goes only into the copies of the ranks that reach it (ReLU mask fused)
+            rc = self._lib.rgcn_nvl_store_rows_sparse(t.data_ptr(), t.stride(0), f,
+                                                      relu_pre.data_ptr() if relu_pre is not None else None,
+                                                      relu_pre.stride(0) if relu_pre is not None else 0,
+                                                      peers, self.world, self.sparse[0].data_ptr(), ld, self.lo, n_own,
+                                                      self._stream())
+            self._check(rc, 'rgcn_nvl_store_rows_sparse')
+            self.barrier()
+            self.bytes_gathered += (self.sparse[1] + n_own) * ld * 4
+            return buf[:, :f] if ld != f else buf
         rc = self._lib.rgcn_nvl_store_rows(t.data_ptr(), t.stride(0), f,
                                            relu_pre.data_ptr() if relu_pre is not None else None,
                                            relu_pre.stride(0) if relu_pre is not None else 0,
@@ -269,12 +298,18 @@ class NvlComm(RowComm):
         self.barrier()
         n_own = self.hi - self.lo
         out = torch.empty((n_own, cols), dtype=torch.float32, device=self.device)
-        rc = self._lib.rgcn_nvl_reduce_rows(mc if mc else None, peers, self.world, cols, self.lo, n_own, out.data_ptr(),
-                                            cols, cols, self._stream())
-        self._check(rc, 'rgcn_nvl_reduce_rows')
+        if self.sparse is not None:
+            rc = self._lib.rgcn_nvl_reduce_rows_sparse(peers, self.world, self.sparse[0].data_ptr(), cols, self.lo, n_own,
+                                                       out.data_ptr(), cols, cols, self._stream())
+            self._check(rc, 'rgcn_nvl_reduce_rows_sparse')
+            self.bytes_reduced += int(self.touched_frac * buf.numel() * 4)
+        else:
+            rc = self._lib.rgcn_nvl_reduce_rows(mc if mc else None, peers, self.world, cols, self.lo, n_own, out.data_ptr(),
+                                                cols, cols, self._stream())
+            self._check(rc, 'rgcn_nvl_reduce_rows')
+            self.bytes_reduced += buf.numel() * 4
         if not self.steady_state:
             self.barrier()
-        self.bytes_reduced += buf.numel() * 4
         return out
 
     def all_reduce_sum_(self, tensors: List[Tensor]) -> None:
@@ -302,6 +337,34 @@ class NvlComm(RowComm):
         for t in tensors:
             t.copy_(res[off:off + t.numel()].view_as(t))
             off += t.numel()
+
+
+def sparse_plan(touched: Tensor, ranges, rank: int, group=None) -> dict:
+    """Host logic of NvlComm.set_touched (any backend; gloo in the CPU tests).  touched [N] bool per rank ->
+    peer_mask [n_own] int32 (bit p: rank p reaches owned row i), row_list int32 (the remote rows this rank reaches,
+    ascending = grouped by owner), offsets [world + 1] into row_list by owner, and the traffic it saves."""
+    world = dist.get_world_size(group)
+    n = touched.numel()
+    lo, hi = ranges[rank]
+    mine = touched.to(torch.uint8).contiguous()
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    mask = torch.zeros(hi - lo, dtype=torch.int32, device=touched.device)
+    for p, t in enumerate(parts):
+        mask |= t[lo:hi].to(torch.int32) << p
+    mask |= 1 << rank
+    remote = touched.clone()
+    remote[lo:hi] = False
+    rows = torch.nonzero(remote).flatten().to(torch.int32)
+    bounds = torch.tensor([a for a, _ in ranges] + [ranges[-1][1]], dtype=torch.int64)
+    offsets = torch.searchsorted(rows.to(torch.int64).cpu(), bounds).tolist()
+    offsets[0], offsets[-1] = 0, rows.numel()
+    fracs = torch.stack([t.to(torch.float32).mean() for t in parts]).cpu()
+    dense_remote = torch.tensor([1.0 - (b - a) / max(n, 1) for a, b in ranges])
+    sparse_remote = torch.clamp(fracs - (1.0 - dense_remote), min=0.0)
+    saving = 1.0 - float((sparse_remote / torch.clamp(dense_remote, min=1e-9)).mean())
+    return {'peer_mask': mask, 'row_list': rows, 'offsets': [int(v) for v in offsets],
+            'touched_frac_mean': float(fracs.mean()), 'remote_saving_mean': saving}
 
 
 def comm_backend(backend: Optional[str] = None) -> str:
@@ -338,6 +401,8 @@ class PartitionedRGCN(nn.Module):
         super().__init__()
         from .conv import RGCNConv
         self.graph, self.comm = graph, comm
+        if getattr(graph, 'touched', None) is not None and hasattr(comm, 'set_touched'):
+            comm.set_touched(graph.touched)
         gen = torch.Generator().manual_seed(seed)          # same replicated weights on every rank
         full = torch.randn(comm.num_nodes, emb_dim, generator=gen)
         self.embedding = nn.Parameter(full[comm.lo:comm.hi].clone())
@@ -578,7 +643,13 @@ def run_partitioned_bench(args, rank: int, world: int, device, metric: str, unit
         if mode == 'push':
             coll = ('per layer: reduce_scatter(partial out) fwd, all_gather(gout) bwd; one all_reduce of dW/droot/dbias; '
                     'the 63-wide layer-1 input is never exchanged; ' +
-                    ('engine kernels over NVSwitch multicast (multimem.st / multimem.ld_reduce), one device barrier each'
+                    (('engine kernels over NVLink peer memory, SPARSE: only the rows a rank\'s own edges reach cross the '
+                      'links (reduce-scatter reads an owned row from the ranks that reach it; all-gather stores it only into '
+                      'their copies), one device barrier each'
+                      if getattr(comm, 'sparse', None) is not None else
+                      'engine kernels over NVSwitch multicast (multimem.st / multimem.ld_reduce), one device barrier each'
+                      if getattr(comm, 'mode', 2) != 2 else
+                      'engine kernels over NVLink peer pointers, one device barrier each')
                      if backend == 'nvl' else 'NCCL calls'))
             limiting = 'all_gather(gout of layer 1, 16 wide) + reduce_scatter(partial h1, 16 wide)'
         else:
@@ -593,6 +664,8 @@ def run_partitioned_bench(args, rank: int, world: int, device, metric: str, unit
                        'partition': f'{"source" if mode == "push" else "dst"}-partitioned x{world}, ' +
                                     ('node ranges balanced by out-degree' if backend == 'nvl' else 'equal node ranges'),
                        'collectives': coll, 'comm_backend': backend, 'limiting_collective': limiting,
+                       'exchange_sparse': getattr(comm, 'sparse', None) is not None,
+                       'rows_reached_per_rank_frac_mean': getattr(comm, 'touched_frac', None),
                        'all_gather_bytes_per_step_per_rank': gathered,
                        'reduce_scatter_bytes_per_step_per_rank': reduced,
                        'max_rank_edges': int(mx.item()), 'mean_rank_edges': e / world,

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert set(declared) == set(_lib.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.rgcn_abi_version() == 5
+    assert lib.rgcn_abi_version() == 6
 
 
 def test_library_has_sm100a_code_only():

@@ -65,6 +65,17 @@ def _worker(rank, world, port, ret):
         out2.backward(gout2[comm.lo:comm.hi])
         errs += [rel(out2, ref2[comm.lo:comm.hi]), rel(p2[0].grad, f2[0].grad[comm.lo:comm.hi])]
         errs += [rel(a.grad, b.grad) for a, b in zip(p2[1:], f2[1:])]
+        # the same two layers with the SPARSE exchanges planned from the graph (only the rows a rank reaches cross
+        # the links): bit-identical to the dense peer-pointer exchanges, hence the same errors
+        os.environ['RGCN_B200_NVL_SPARSE'] = '1'
+        assert nvl.set_touched(g.touched) and nvl.sparse is not None
+        assert nvl.sparse[1] == int(g.touched.sum()) - (comm.hi - comm.lo)
+        p3 = [x[comm.lo:comm.hi].clone().requires_grad_()] + [t.clone().requires_grad_() for t in (w, root, bias, w2)]
+        out3 = rgcn_layer(rgcn_layer(p3[0], p3[1], p3[2], p3[3], g, comm=nvl, comm_key=1), p3[4], None, None, g,
+                          relu_in=True, comm=nvl, comm_key=2)
+        out3.backward(gout2[comm.lo:comm.hi])
+        errs += [rel(out3, ref2[comm.lo:comm.hi]), rel(p3[0].grad, f2[0].grad[comm.lo:comm.hi])]
+        errs += [rel(a.grad, b.grad) for a, b in zip(p3[1:], f2[1:])]
         ret[rank] = max(errs)
     finally:
         dist.destroy_process_group()

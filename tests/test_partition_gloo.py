@@ -98,6 +98,37 @@ def _worker(rank, world, port, ret):
         mine = comm.reduce_scatter_rows(partial)
         assert mine.shape == (comm.chunk, 3) and comm.bytes_reduced == partial.numel() * 4
         assert torch.allclose(mine[:hi - lo], ref[lo:hi], atol=1e-5), 'reduce-scattered partial outputs'
+        # sparse exchange plan (host logic of NvlComm.set_touched): which ranks reach an owned row / which remote
+        # rows this rank reaches, and that exchanging ONLY those reproduces the dense exchanges
+        from rgcn_b200.partition import sparse_plan
+        touched = torch.zeros(n_odd, dtype=torch.bool)
+        touched[ei[1][mine_src]] = True
+        touched[lo:hi] = True
+        plan = sparse_plan(touched, comm.ranges, rank)
+        all_touched = [torch.zeros(n_odd, dtype=torch.bool) for _ in range(world)]
+        for p_, (a, b) in enumerate(comm.ranges):
+            m_ = (ei[0] >= a) & (ei[0] < b)
+            all_touched[p_][ei[1][m_]] = True
+            all_touched[p_][a:b] = True
+        want_mask = sum(all_touched[p_][lo:hi].to(torch.int32) << p_ for p_ in range(world))
+        assert torch.equal(plan['peer_mask'], want_mask) and plan['peer_mask'].dtype == torch.int32
+        rows = plan['row_list'].long()
+        assert torch.equal(rows, torch.nonzero(touched & ~torch.isin(torch.arange(n_odd), torch.arange(lo, hi))).flatten())
+        offs = plan['offsets']
+        assert len(offs) == world + 1 and offs[0] == 0 and offs[-1] == rows.numel() and offs[rank] == offs[rank + 1]
+        for p_, (a, b) in enumerate(comm.ranges):
+            seg = rows[offs[p_]:offs[p_ + 1]]
+            assert bool(((seg >= a) & (seg < b)).all())
+        # every non-zero row of this rank's partial is a touched row; masked sum == dense sum
+        assert not bool(partial[:n_odd][~touched].any())
+        parts = [torch.empty_like(partial) for _ in range(world)]
+        dist.all_gather(parts, partial)
+        sparse_sum = torch.zeros(hi - lo, 3)
+        for p_ in range(world):
+            sel = ((plan['peer_mask'] >> p_) & 1).bool()
+            sparse_sum[sel] += parts[p_][lo:hi][sel]
+        assert torch.equal(sparse_sum, sum(q[lo:hi] for q in parts))
+        assert 0.0 <= plan['remote_saving_mean'] <= 1.0 and 0.0 < plan['touched_frac_mean'] <= 1.0
         ret[rank] = 'ok'
     finally:
         dist.destroy_process_group()
