@@ -40,6 +40,8 @@ class FrozenBasisRGCN(nn.Module):
         super().__init__()
         from .conv import RGCNConv
         self.graph, self.comm = graph, comm
+        if comm is not None and getattr(graph, 'touched', None) is not None and hasattr(comm, 'set_touched'):
+            comm.set_touched(graph.touched)
         torch.manual_seed(seed)                               # same replicated weights on every rank
         self.rgcn1 = RGCNConv(EMB, HIDDEN, num_relations, num_bases=BASES)
         self.rgcn2 = RGCNConv(HIDDEN, CLASSES, num_relations, num_bases=BASES)
@@ -194,6 +196,8 @@ def run(args, rank: int, world: int, device, metric: str, unit: str) -> None:
                        'frozen': 'weight/comp/root/bias of both layers (requires_grad False); dL/dx0 only',
                        'partition': (f'source-partitioned x{world}' if world > 1 else 'one GPU'),
                        'comm_backend': ('nvl' if isinstance(comm, NvlComm) else 'nccl') if comm is not None else None,
+                       'exchange_sparse': getattr(comm, 'sparse', None) is not None,
+                       'rows_reached_per_rank_frac_mean': getattr(comm, 'touched_frac', None),
                        'step_algorithmic_bytes': step_bytes,
                        'step_roofline_frac': step_bytes / (ms * 1e-3) / 1e9 / peak / max(world, 1),
                        'peak_source': peak_src, 'graph_build_ms_once': setup_ms,
