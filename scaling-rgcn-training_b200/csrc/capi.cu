@@ -110,6 +110,7 @@ int64_t bwd_ws(const rgcn_graph* g, int fin, int fout) {
     b += ws_take((int64_t)g->brc[RGCN_BRC_BWD].num_chunks * np, 4);          // chunk rows of gout (dx pass)
     b += ws_take((int64_t)g->n_own * kp, 4);                                 // padded dx target
     if (kp == 64 && np == 64) b += ws_take(wprep_tc_floats(g->R), 4);        // tcgen05 operand images
+    if (np == 16 && kp > np) b += ws_take((int64_t)(g->R + 1) * 16 * kp, 4); // dW^T accumulators (k_ewgrad_t)
     return b;
 }
 
@@ -352,7 +353,28 @@ int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
     const bool direct = gx && (packed || padded || direct_target(gx, ldgx, fin));
     float* target = gx ? (direct ? gx : ws.take<float>((int64_t)g->n_own * kp)) : nullptr;
     float* wtc = (gx && kp == 64 && np == 64) ? ws.take<float>(wprep_tc_floats(g->R)) : nullptr;
+    float* wt_scratch = (need_w && np == 16 && kp > np) ? ws.take<float>((int64_t)(g->R + 1) * 16 * kp) : nullptr;
     if (!ws.ok) return fail(RGCN_ERR_WORKSPACE, "rgcn_layer_bwd: workspace too small (see rgcn_layer_workspace_bytes)");
+    // dL/dW of a layer that is wider on its input side (63 -> 16) runs on the TRANSPOSED structure: the narrow gout
+    // rows are gathered (as dL/dx does), the wide x rows are read by owner id and stay in L2 (k_ewgrad_t)
+    WGradPass wt{};
+    wt.brc = &g->brc[RGCN_BRC_BWD];
+    wt.n_nodes = g->N; wt.self_rel = g->R;
+    wt.feat = x_own; wt.ldf = ldx; wt.kin = fin;
+    wt.aux = gaux;
+    wt.gout = gout_gather; wt.ldg = ldgg; wt.nout = fout;
+    wt.gweight = gweight; wt.groot = groot; wt.gbias = gbias;
+    wt.kp = kp; wt.np = np; wt.relu_in = relu;
+    const bool wg_t = need_w && wt_scratch && etile_choice(kp, true) && ewgrad_t_ok(wt);
+    bool bwd_pre_done = false;
+    if (wg_t) {   // both sides read the chunk rows of gout: before the fork
+        TilePass pre{};
+        pre.brc = &g->brc[RGCN_BRC_BWD];
+        pre.n_nodes = g->N;
+        pre.feat = gout_gather; pre.ldf = ldgg; pre.kin = fout; pre.aux = gaux; pre.kp = np; pre.relu_in = false;
+        if ((rc = launch_chunk_prepass(pre, st))) return rc;
+        bwd_pre_done = true;
+    }
     // dL/dW (+ its pre-pass) and the dL/dx chain are independent: with both requested the dL/dW pass runs
     // on the side stream, each side keeping to its share of every SM so that they are co-resident
     Fork fk(g, st);
@@ -362,7 +384,10 @@ int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
         if ((rc = fk.begin())) return rc;
         st_w = g->side;
     }
-    if (need_w) {
+    if (wg_t) {
+        wt.ctas_per_sm = ovl ? opts().wg_ctas : 0;
+        if ((rc = launch_ewgrad_t_pass(wt, wt_scratch, g->num_sms, st_w))) return rc;
+    } else if (need_w) {
         // chunk rows of x in the relation-major ordering, then dW / droot / dbias
         TilePass pre{};
         pre.brc = &g->brc[RGCN_BRC_FWD_REL];
@@ -410,7 +435,7 @@ int layer_bwd(const rgcn_graph* g, const float* x, int64_t ldx, int32_t fin, con
         p.packed = packed && v4;
         p.out_rows = g->n_own;
         p.ctas_per_sm = ovl ? opts().dx_ctas : 0;
-        if ((rc = launch_chunk_prepass(p, st))) return rc;
+        if (!bwd_pre_done && (rc = launch_chunk_prepass(p, st))) return rc;
         if (et) {
             if ((rc = launch_selfloop_pass(p, g->own_lo, g->n_own, g->R, g->num_sms, st))) return rc;
             if (wtc && etile_tc_ok(p)) {

@@ -159,6 +159,9 @@ bool etile_vec4_ok(const float* feat, int64_t ldf, int kin, const float* aux);
 int launch_etile_pass(const TilePass& p, int num_sms, cudaStream_t st);   // edge tiles only: run launch_selfloop_pass first
 int launch_selfloop_pass(const TilePass& p, int64_t own_lo, int64_t n_own, int R, int num_sms, cudaStream_t st);
 int launch_ewgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st);
+// dL/dW on the transposed structure (wide owner rows, narrow gathered rows): see k_ewgrad_t
+bool ewgrad_t_ok(const WGradPass& p);
+int launch_ewgrad_t_pass(const WGradPass& p, float* scratch, int num_sms, cudaStream_t st);
 bool selfloop_pad_ok(int kp, int np);
 int launch_selfloop_pad(const TilePass& p, const float* x_raw, int64_t ld_raw, float* mirror, int64_t ldm, int64_t n_own,
                         int R, int num_sms, cudaStream_t st);

@@ -870,6 +870,213 @@ __global__ void __launch_bounds__(EW * 32, (KT * NT >= 32) ? 1 : 2) k_ewgrad(con
 
 
 // ---------------------------------------------------------------------------------------------
+// dL/dW on the TRANSPOSED structure (BWD: owner = src, gathered = dst) for layers that are wider on the input
+// side than on the output side (63 -> 16):
+//     T_r[16 x 8NT] += sum over the tile's entries  (w_e gout[dst_e])^T (x) x[src_e]          ( = dW_r^T )
+// The relation-major form above gathers the WIDE rows x[src] at random (256 B per entry); here the random
+// gather is the narrow gout row (64 B, the same rows the dL/dx pass gathers) and the wide row is read by OWNER
+// id, which ascends inside every (range, relation) group.  All warps walk the tile sequence together — a warp's
+// work is `upw` consecutive units inside each window of gridDim * EW * upw units — so the x rows of the few
+// node ranges in flight (4 MB each) are served from L2: x is read from HBM once, not once per entry.
+// Lane (g,t): A = gathered rows (M = gout column g / g+8, K slot = entry t / t+4); B = owner rows, read with
+// LDG.128: columns 32b + 4g .. +3 of entry t serve n-tiles 4b .. 4b+3 at column g, i.e. D column (n = 4b + j, c)
+// is x column 32b + 4c + j — undone by k_ewgrad_t_finish, which also transposes T into dW / droot.
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(EW * 32, 2) k_ewgrad_t(const ETileArgs a, const int upw) {
+    using MS = MetaStage<0>;
+    constexpr int UTU = MS::UTU, SPAN = MS::SPAN, MW = MS::MW, NB = NT / 4, LDT = NT * 8;
+    extern __shared__ __align__(16) uint32_t dyn_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int gw = blockIdx.x * EW + warp, nw = gridDim.x * EW;
+    uint32_t* meta = dyn_smem + warp * MS::WARP_WORDS;
+    const uint64_t pol_x = policy_evict_last();
+    float d[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) d[n][0] = d[n][1] = d[n][2] = d[n][3] = 0.f;
+    float asum0 = 0.f, asum1 = 0.f;
+    int cur_rel = -1;
+
+    // row g (even t) or row g + 8 (odd t) of n-tile n as ONE 16-byte reduction: the lane pair (t, t^1) swaps halves
+    auto flush = [&](int rel) {
+        float* dst = a.gweight + (int64_t)rel * 16 * LDT + (int64_t)((t & 1) ? g + 8 : g) * LDT + ((t & 1) ? 2 * (t - 1) : 2 * t);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const bool odd = t & 1;
+            const float s0 = odd ? d[n][0] : d[n][2], s1 = odd ? d[n][1] : d[n][3];
+            const float r0 = __shfl_xor_sync(FULL, s0, 1), r1 = __shfl_xor_sync(FULL, s1, 1);
+            if (odd) red_add_v4(dst + 8 * n, r0, r1, d[n][2], d[n][3]);
+            else red_add_v4(dst + 8 * n, d[n][0], d[n][1], r0, r1);
+            d[n][0] = d[n][1] = d[n][2] = d[n][3] = 0.f;
+        }
+    };
+
+    const float* const feat_g = pin(a.feat + g);
+    const float* const aux_g = pin(a.aux + g);
+    const float* const x_g = pin(a.gout + 4 * g);
+    const uint32_t n_rows = pin((uint32_t)a.n_rows), ldf = pin((uint32_t)a.ldf), ldx = pin((uint32_t)a.ldg);
+    const int kin = pin(a.kin);
+    const int total_units = (a.num_tiles + UTU - 1) / UTU;
+    // unit u of this warp -> global unit: window (u / upw), this warp's block of upw units inside it
+    auto unit_of = [&](int u) { return ((u / upw) * nw + gw) * upw + (u % upw); };
+    const int win_units = nw * upw;
+    int num_units = 0;   // units of this warp that exist
+    {
+        const int full = total_units / win_units, rem = total_units - full * win_units;
+        num_units = full * upw + max(0, min(upw, rem - gw * upw));
+    }
+    if (num_units == 0) return;
+
+    auto unit_span = [&](int u, int& first, int& end) {
+        const int u0 = unit_of(u) * UTU, u1 = min(a.num_tiles, u0 + UTU);
+        first = a.tile_e0[u0];
+        end = a.tile_e0[u1 - 1] + (a.tile_info[u1 - 1] & 0xff);
+    };
+    auto stage_unit = [&](int u, int first, int end, uint32_t* m) {
+        const int eb = first & ~3;
+        const int nchunk = (end - eb + 3) >> 2;
+        for (int c = lane; c < nchunk; c += 32) {
+            cp_async16(m + 4 * c, a.e_idx + eb + 4 * c);
+            cp_async16(m + SPAN + 4 * c, a.e_w + eb + 4 * c);
+            cp_async16(m + 2 * SPAN + 4 * c, a.e_own + eb + 4 * c);
+        }
+        const int u0 = unit_of(u) * UTU;
+        if (lane < UTU / 4) cp_async16(m + 3 * SPAN + 4 * lane, a.tile_e0 + u0 + 4 * lane);
+        else if (lane < UTU / 2) cp_async16(m + 3 * SPAN + UTU + 4 * (lane - UTU / 4), a.tile_info + u0 + 4 * (lane - UTU / 4));
+    };
+    // a tile is kept as (first entry relative to the staged span, entry count, relation): indices, owners and
+    // weights are re-read from the staged metadata where they are used, so two tiles in flight cost 6 registers
+    struct Tile {
+        int o0, cnt, rel;
+    };
+    auto tile_ref = [&](const uint32_t* m, int i, int eb) {
+        Tile tl;
+        const int info = (int)m[3 * SPAN + UTU + i];
+        tl.o0 = (int)m[3 * SPAN + i] - eb + t;
+        tl.rel = info >> 8;
+        tl.cnt = info & 0xff;
+        return tl;
+    };
+    const bool c_lo = g < kin, c_hi = g + 8 < kin;
+    // K step ks of a tile: entries t + 8 ks (slot t) and t + 4 + 8 ks (slot t + 4)
+    auto load_half = [&](const uint32_t* m, const Tile& tl, int ks, float (&av)[4], float4 (&bv)[2][NB]) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int q = 2 * ks + r;
+            const bool valid = t + 4 * q < tl.cnt;
+            const int o = tl.o0 + 4 * q;
+            const uint32_t idx = valid ? (m[o] & IDX_MASK) : 0u;
+            const uint32_t own = valid ? m[2 * SPAN + o] : 0u;
+            const float* p = idx < n_rows ? feat_g + idx * ldf : aux_g + (idx - n_rows) * 16u;
+            av[2 * r] = (c_lo && valid) ? __ldg(p) : 0.f;
+            av[2 * r + 1] = (c_hi && valid) ? __ldg(p + 8) : 0.f;
+            const float* xp = x_g + own * ldx;
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+                bv[r][b] = valid ? ldg128_hint(reinterpret_cast<const float4*>(xp + 32 * b), pol_x) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto compute_half = [&](const uint32_t* m, const Tile& tl, int ks, const float (&av)[4], const float4 (&bv)[2][NB]) {
+        const int oa = tl.o0 + 8 * ks, ob = oa + 4;
+        const float wa = (t + 8 * ks < tl.cnt) ? __uint_as_float(m[SPAN + oa]) : 0.f;
+        const float wb = (t + 4 + 8 * ks < tl.cnt) ? __uint_as_float(m[SPAN + ob]) : 0.f;
+        if (tl.rel == a.self_rel) {
+            asum0 += av[0] + av[2];
+            asum1 += av[1] + av[3];
+        }
+        uint32_t ah[4], al[4];
+        split_fast(av[0] * wa, ah[0], al[0]);
+        split_fast(av[1] * wa, ah[1], al[1]);
+        split_fast(av[2] * wb, ah[2], al[2]);
+        split_fast(av[3] * wb, ah[3], al[3]);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const float xa[4] = {bv[0][b].x, bv[0][b].y, bv[0][b].z, bv[0][b].w};
+            const float xb[4] = {bv[1][b].x, bv[1][b].y, bv[1][b].z, bv[1][b].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t bh0, bl0, bh1, bl1;
+                split_rn(xa[j], bh0, bl0);
+                split_rn(xb[j], bh1, bl1);
+                float(&dd)[4] = d[4 * b + j];
+                mma_tf32(dd, al[0], al[1], al[2], al[3], bh0, bh1);
+                mma_tf32(dd, ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+                mma_tf32(dd, ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+            }
+        }
+    };
+    auto wanted = [&](int rel) { return rel == a.self_rel ? (a.groot != nullptr || a.gbias != nullptr) : a.out != nullptr; };
+    auto enter = [&](int rel) {
+        if (rel != cur_rel) {
+            if (cur_rel >= 0 && wanted(cur_rel)) flush(cur_rel);
+            cur_rel = rel;
+        }
+    };
+
+    int cur_first, cur_end, nxt_first = 0, nxt_end = 0;
+    unit_span(0, cur_first, cur_end);
+    stage_unit(0, cur_first, cur_end, meta);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (1 < num_units) unit_span(1, nxt_first, nxt_end);
+    for (int u = 0, buf = 0; u < num_units; ++u, buf ^= 1) {
+        const uint32_t* m = meta + buf * MW;
+        const int eb = cur_first & ~3;
+        const int ut0 = unit_of(u) * UTU;
+        const int nt = min(a.num_tiles, ut0 + UTU) - ut0;
+        if (u + 1 < num_units) stage_unit(u + 1, nxt_first, nxt_end, meta + (buf ^ 1) * MW);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        cur_first = nxt_first;
+        cur_end = nxt_end;
+        if (u + 2 < num_units) unit_span(u + 2, nxt_first, nxt_end);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        // (a variant that kept the next tile's K step in flight under this tile's MMAs spilled at 128 registers and
+        // ran 20 % slower; latency is hidden by the 16 resident warps instead)
+        for (int i = 0; i < nt; ++i) {
+            const Tile tl = tile_ref(m, i, eb);
+            enter(tl.rel);
+            if (!wanted(tl.rel)) continue;
+            float av0[4], av1[4];
+            float4 bv0[2][NB], bv1[2][NB];
+            load_half(m, tl, 0, av0, bv0);
+            load_half(m, tl, 1, av1, bv1);
+            compute_half(m, tl, 0, av0, bv0);
+            compute_half(m, tl, 1, av1, bv1);
+        }
+        __syncwarp();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (cur_rel >= 0 && wanted(cur_rel)) flush(cur_rel);
+    if (a.gbias) {   // gout column g / g+8 summed over this lane's K slots of the self-loop tiles
+        asum0 += __shfl_xor_sync(FULL, asum0, 1);
+        asum0 += __shfl_xor_sync(FULL, asum0, 2);
+        asum1 += __shfl_xor_sync(FULL, asum1, 1);
+        asum1 += __shfl_xor_sync(FULL, asum1, 2);
+        if (t == 0 && g < kin && asum0 != 0.f) atomicAdd(a.gbias + g, asum0);
+        if (t == 0 && g + 8 < kin && asum1 != 0.f) atomicAdd(a.gbias + g + 8, asum1);
+    }
+}
+
+// T[r][c][v] (c = gout column, v = 8n + c' with x column 32(n/4) + 4c' + n%4)  ->  dW[r][x column][c] / droot
+__global__ void __launch_bounds__(256) k_ewgrad_t_finish(const float* __restrict__ T, int ldt, int R, int fin, int fout,
+                                                         float* __restrict__ gweight, float* __restrict__ groot) {
+    const int per = fin * fout;
+    const int64_t total = (int64_t)(R + 1) * per;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / per), e = (int)(i - (int64_t)r * per);
+        const int xc = e / fout, c = e - xc * fout;
+        const int v = 8 * (4 * (xc >> 5) + (xc & 3)) + ((xc & 31) >> 2);
+        const float val = T[((int64_t)r * 16 + c) * ldt + v];
+        if (r < R) {
+            if (gweight) gweight[i] = val;
+        } else if (groot) {
+            groot[e] = val;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // self loop + bias:  out[i] = act(x[i]) . root + bias  with PLAIN vector stores.  Runs before the
 // edge tiles of a pass, so it also replaces the zero fill of the accumulate target; the self-loop
 // tiles (which sort last in every BRC) are then skipped by k_etile.
@@ -1422,6 +1629,72 @@ int launch_ewgrad_pass(const WGradPass& p, int num_sms, cudaStream_t st) {
     ProfScope prof(TAG_WGRAD, p.kin, p.nout, st);
     note_launch(1);
     RGCN_DISPATCH_E(run_ewgrad, p.kp, p.np, a, p.relu_in, p.vec4, num_sms, p.ctas_per_sm, st);
+}
+
+
+bool ewgrad_t_ok(const WGradPass& p) {
+    // opt-in (RGCN_B200_WGRAD_T=1): measured at AM shape it moves 1.94 GB of DRAM traffic instead of 3.0 GB but,
+    // latency-bound at 16 warps per SM, takes 0.65 ms against 0.64 ms for the relation-major form
+    static const bool on = [] {
+        const char* e = getenv("RGCN_B200_WGRAD_T");
+        return e && e[0] == '1';
+    }();
+    // gathered side exactly 16 padded columns, owner side 32 or 64 with 16-byte addressable rows that hold the
+    // whole padded width; 32-bit element offsets on both
+    return on && !p.relu_in && p.np == 16 && (p.kp == 32 || p.kp == 64) && p.kp > p.np && p.ldf % 4 == 0 && p.ldf >= p.kp &&
+           ((uintptr_t)p.feat & 15) == 0;
+}
+
+// p.feat / ldf / kin = the OWNER-side rows (x of the owned nodes), p.gout / ldg / nout = the rows gathered through
+// p.brc (the transposed structure: gout of all nodes), p.aux = that structure's chunk rows of gout [num_chunks, 16],
+// scratch = (R + 1) * 16 * kp floats
+int launch_ewgrad_t_pass(const WGradPass& p, float* scratch, int num_sms, cudaStream_t st) {
+    const Brc& b = *p.brc;
+    const int R = p.self_rel;
+    RGCN_CUDA(cudaMemsetAsync(scratch, 0, (size_t)(R + 1) * 16 * p.kp * 4, st));
+    ProfScope prof(TAG_WGRAD, p.kin, p.nout, st);
+    if (b.num_tiles > 0) {
+        ETileArgs a = base_args(b);
+        a.feat = p.gout;
+        a.ldf = p.ldg;
+        a.kin = p.nout;
+        a.aux = p.aux ? p.aux : p.gout;
+        a.n_rows = p.n_nodes;
+        a.self_rel = R;
+        a.gout = p.feat;
+        a.ldg = p.ldf;
+        a.nout = p.kin;
+        a.gweight = scratch;
+        a.out = p.gweight;        // only as the "relation tiles wanted" flag
+        a.groot = p.groot;
+        a.gbias = p.gbias;
+        note_launch(1);
+        auto launch = [&](auto kern) -> int {
+            int per_sm = 1;
+            const int smem = MetaStage<0>::CTA_BYTES;
+            if (smem > 48 * 1024) RGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            RGCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EW * 32, smem));
+            per_sm = std::max(per_sm, 1);
+            if (p.ctas_per_sm > 0) per_sm = std::min(per_sm, p.ctas_per_sm);
+            const int64_t units = ((int64_t)a.num_tiles + UT - 1) / UT;
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + EW - 1) / EW, (int64_t)num_sms * per_sm));
+            static const int upw = [] {
+                const char* e = getenv("RGCN_B200_WGRAD_T_UPW");
+                return e ? std::min(64, std::max(1, atoi(e))) : 1;
+            }();
+            kern<<<grid, EW * 32, smem, st>>>(a, upw);
+            RGCN_CUDA(cudaGetLastError());
+            return 0;
+        };
+        int rc = p.kp == 64 ? launch(k_ewgrad_t<8>) : launch(k_ewgrad_t<4>);
+        if (rc) return rc;
+    }
+    note_launch(1);
+    const int64_t total = (int64_t)(R + 1) * p.kin * p.nout;
+    k_ewgrad_t_finish<<<(int)std::min<int64_t>((total + 255) / 256, 1024), 256, 0, st>>>(scratch, p.kp, R, p.kin, p.nout, p.gweight,
+                                                                                       p.groot);
+    RGCN_CUDA(cudaGetLastError());
+    return 0;
 }
 
 }  // namespace rgcn
