@@ -258,14 +258,15 @@ int rgcn_gemm3x_tf32(const float* a, int64_t lda, int64_t m, int32_t k, const fl
 
 /* Per-node core of the attention transfer head (reference model/layers.py:59-61: nn.MultiheadAttention over the
  * num_sums stacked summary embeddings, q = k = v, only attn_output[0] kept).  q [N, heads*head_dim] = the projected
- * query rows of summary 0 (bias added, unscaled); kv [num_sums*N, 2*heads*head_dim] = projected keys | values, row
- * s*N + b for summary s; keep_scaled (nullable) [N, heads, num_sums] = dropout keep mask times 1/(1-p).
+ * query rows of summary 0 (bias added, unscaled); kv [num_sums*N, >= v_offset + heads*head_dim] = projected keys
+ * (columns 0..) and values (columns v_offset..), row s*N + b for summary s (v_offset = ceil4(heads*head_dim) and
+ * 16-byte addressable rows everywhere select the shared-memory-staged kernels); keep_scaled (nullable) [N, heads, num_sums] = dropout keep mask times 1/(1-p).
  * fwd: probs [N, heads, num_sums] = softmax_s(q.k_s / sqrt(head_dim)) (before dropout), o [N, heads*head_dim].
  * bwd: gq, gkv from dL/do (go); every element of gq / gkv is written. */
-int rgcn_attn_head_fwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, int32_t num_sums,
+int rgcn_attn_head_fwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, int64_t v_offset, int32_t num_sums,
                        int64_t num_nodes, int32_t heads, int32_t head_dim, const float* keep_scaled, float* probs,
                        float* o, int64_t ldo, void* stream);
-int rgcn_attn_head_bwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, int32_t num_sums,
+int rgcn_attn_head_bwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, int64_t v_offset, int32_t num_sums,
                        int64_t num_nodes, int32_t heads, int32_t head_dim, const float* keep_scaled,
                        const float* probs, const float* go, int64_t ldgo, float* gq, int64_t ldgq, float* gkv,
                        int64_t ldgkv, void* stream);

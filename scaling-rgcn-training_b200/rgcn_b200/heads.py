@@ -142,6 +142,21 @@ def stack_rows16(e: Tensor) -> Tensor:
     return buf[:, :, :emb]
 
 
+def _kv_weights(w_in: Tensor, b_in: Optional[Tensor], emb: int) -> Tuple[Tensor, Optional[Tensor], int]:
+    """in_proj rows of K and V as one operand whose two halves start at multiples of 4 columns (zero rows between):
+    the projected K | V rows are then 16-byte addressable on both sides of the split."""
+    ep = _pad(emb, 4)
+    w = torch.zeros((2 * ep, emb), dtype=torch.float32, device=w_in.device)
+    w[:emb] = w_in[emb:2 * emb].detach()
+    w[ep:ep + emb] = w_in[2 * emb:].detach()
+    b = None
+    if b_in is not None:
+        b = torch.zeros(2 * ep, dtype=torch.float32, device=w_in.device)
+        b[:emb] = b_in[emb:2 * emb].detach()
+        b[ep:ep + emb] = b_in[2 * emb:].detach()
+    return w, b, ep
+
+
 class _AttentionHeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, e: Tensor, w_in: Tensor, b_in: Tensor, w_out: Tensor, b_out: Tensor, keep: Optional[Tensor],
@@ -150,27 +165,27 @@ class _AttentionHeadFn(torch.autograd.Function):
         s, n, emb = e.shape
         d = emb // heads
         e_flat = _flat_rows16(e)
+        w_kv, b_kv, ep = _kv_weights(w_in, b_in, emb)
         q = gemm(e_flat[:n], w_in[:emb], b_in[:emb] if b_in is not None else None)
-        kv = gemm(e_flat, w_in[emb:], b_in[emb:] if b_in is not None else None)       # [S * N, 2 emb]: keys | values
+        kv = gemm(e_flat, w_kv, b_kv)                         # [S * N, 2 ep]: keys at column 0, values at column ep
         probs = torch.empty((n, heads, s), dtype=torch.float32, device=e.device)
-        ldo = _pad(emb, 4)
-        o = torch.empty((n, ldo), dtype=torch.float32, device=e.device)       # pad columns are never read (TMA bounds)
+        o = torch.empty((n, ep), dtype=torch.float32, device=e.device)       # pad columns are never read (TMA bounds)
         with torch.cuda.device(e.device):
-            rc = lib.rgcn_attn_head_fwd(q.data_ptr(), q.stride(0), kv.data_ptr(), kv.stride(0), s, n, heads, d,
-                                        keep.data_ptr() if keep is not None else None, probs.data_ptr(), o.data_ptr(), ldo,
+            rc = lib.rgcn_attn_head_fwd(q.data_ptr(), q.stride(0), kv.data_ptr(), kv.stride(0), ep, s, n, heads, d,
+                                        keep.data_ptr() if keep is not None else None, probs.data_ptr(), o.data_ptr(), ep,
                                         _stream(e.device))
         _lib.check(rc, 'rgcn_attn_head_fwd')
         o = o[:, :emb]
-        x0 = gemm(o, w_out, b_out, out_ld=ldo)
-        ctx.save_for_backward(e_flat, q, kv, probs, o, w_in, w_out, keep)
-        ctx.dims = (s, n, emb, heads, d, b_in is not None)
+        x0 = gemm(o, w_out, b_out, out_ld=ep)
+        ctx.save_for_backward(e_flat, q, kv, probs, o, w_in, w_out, keep, w_kv)
+        ctx.dims = (s, n, emb, heads, d, b_in is not None, ep)
         return x0
 
     @staticmethod
     def backward(ctx, g: Tensor):
         lib = _lib.load()
-        e_flat, q, kv, probs, o, w_in, w_out, keep = ctx.saved_tensors
-        s, n, emb, heads, d, has_b_in = ctx.dims
+        e_flat, q, kv, probs, o, w_in, w_out, keep, w_kv = ctx.saved_tensors
+        s, n, emb, heads, d, has_b_in, ep = ctx.dims
         need_e, need_w_in, need_b_in, need_w_out, need_b_out = ctx.needs_input_grad[:5]
         g = g.contiguous()
         gw_out = g.t() @ o if need_w_out else None
@@ -178,21 +193,26 @@ class _AttentionHeadFn(torch.autograd.Function):
         ge = gw_in = gb_in = None
         if need_e or need_w_in or need_b_in:
             go = gemm(g, w_out, transpose_w=True)                                       # dL/do [N, emb]
-            gq = torch.empty((n, _pad(emb, 4)), dtype=torch.float32, device=g.device)
-            gkv = torch.empty((s * n, _pad(2 * emb, 4)), dtype=torch.float32, device=g.device)
+            gq = torch.empty((n, ep), dtype=torch.float32, device=g.device)
+            gkv = torch.empty((s * n, 2 * ep), dtype=torch.float32, device=g.device)
             with torch.cuda.device(g.device):
-                rc = lib.rgcn_attn_head_bwd(q.data_ptr(), q.stride(0), kv.data_ptr(), kv.stride(0), s, n, heads, d,
+                rc = lib.rgcn_attn_head_bwd(q.data_ptr(), q.stride(0), kv.data_ptr(), kv.stride(0), ep, s, n, heads, d,
                                             keep.data_ptr() if keep is not None else None, probs.data_ptr(),
                                             go.data_ptr(), go.stride(0), gq.data_ptr(), gq.stride(0), gkv.data_ptr(),
                                             gkv.stride(0), _stream(g.device))
             _lib.check(rc, 'rgcn_attn_head_bwd')
-            gq, gkv = gq[:, :emb], gkv[:, :2 * emb]
+            gq = gq[:, :emb]
             if need_w_in:
-                gw_in = torch.cat([gq.t() @ e_flat[:n], gkv.t() @ e_flat], 0)
+                gkv_w = gkv.t() @ e_flat                                                # [2 ep, emb]; the pad rows are dropped
+                gw_in = torch.cat([gq.t() @ e_flat[:n], gkv_w[:emb], gkv_w[ep:ep + emb]], 0)
             if need_b_in and has_b_in:
-                gb_in = torch.cat([gq.sum(0), gkv.sum(0)], 0)
+                gkv_b = gkv.sum(0)
+                gb_in = torch.cat([gq.sum(0), gkv_b[:emb], gkv_b[ep:ep + emb]], 0)
             if need_e:
-                ge = gemm(gkv, w_in[emb:], transpose_w=True).contiguous()
+                if ep != emb:                                 # the pad columns meet zero weight rows: they must be finite
+                    gkv[:, emb:ep].zero_()
+                    gkv[:, ep + emb:].zero_()
+                ge = gemm(gkv, w_kv, transpose_w=True).contiguous()
                 ge[:n] += gemm(gq, w_in[:emb], transpose_w=True)
                 ge = ge.view(s, n, emb)
         return ge, gw_in, gb_in, gw_out, gb_out, None, None

@@ -340,3 +340,32 @@ def test_engine_attention_head_matches_torch_mha_with_gradients(n, S, emb):
             assert rel_err(x, x_ref) < TOL, (training, rel_err(x, x_ref))
             for a, b in zip(got, ref):
                 assert a.shape == b.shape and rel_err(a, b) < 2e-5, (training, freeze, rel_err(a, b))
+
+
+_ATTN_CASE = '''
+import sys
+sys.path[:0] = [{repo!r}, {pkg!r}]
+import torch
+from rgcn_b200.heads import attention_head
+torch.manual_seed(0)
+att = torch.nn.MultiheadAttention(embed_dim=63, num_heads=3, dropout=0.2).cuda()
+e = torch.randn(3, 777, 63, device='cuda', requires_grad=True)
+g = torch.randn(777, 63, device='cuda')
+wrt = [e, att.in_proj_weight, att.in_proj_bias, att.out_proj.weight, att.out_proj.bias]
+torch.manual_seed(3)
+ref = torch.autograd.grad(att(e, e, e)[0][0], wrt, g)
+torch.manual_seed(3)
+got = torch.autograd.grad(attention_head(e, att), wrt, g)
+worst = max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(got, ref))
+print('WORST', worst)
+assert worst < 2e-5, worst
+'''
+
+
+@pytest.mark.gpu
+def test_attention_head_per_thread_fallback_kernels():
+    """RGCN_B200_ATTN_STAGED=0: the per-thread kernels that serve shapes whose tiles do not fit shared memory."""
+    code = _ATTN_CASE.format(repo=REPO, pkg=PKG)
+    res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600,
+                         env={**os.environ, 'RGCN_B200_ATTN_STAGED': '0'})
+    assert res.returncode == 0, (res.stdout[-500:], res.stderr[-2000:])
