@@ -19,7 +19,7 @@ EXPORTS = (
     'rgcn_kernel_launch_count', 'rgcn_profile_enable', 'rgcn_profile_collect', 'rgcn_pad_rows',
     'rgcn_eval_counts', 'rgcn_adam_step', 'rgcn_adam_step_dev', 'rgcn_layer_chunk_rows_bytes', 'rgcn_layer_fwd_keep',
     'rgcn_layer_bwd_reuse', 'rgcn_set_option', 'rgcn_graph_create_push', 'rgcn_nvl_store_rows', 'rgcn_nvl_reduce_rows', 'rgcn_gemm_prepack', 'rgcn_gemm3x_tf32', 'rgcn_attn_head_fwd', 'rgcn_attn_head_bwd',
-    'rgcn_nvl_reduce_rows_sparse', 'rgcn_nvl_store_rows_sparse',
+    'rgcn_nvl_reduce_rows_sparse', 'rgcn_nvl_store_rows_sparse', 'rgcn_gram3x_tf32',
 )
 
 BRC_FWD, BRC_BWD, BRC_FWD_REL = 0, 1, 2
@@ -99,6 +99,8 @@ def load():
     lib.rgcn_gemm_prepack.argtypes = [vp, i64, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.rgcn_gemm3x_tf32.restype = C.c_int
     lib.rgcn_gemm3x_tf32.argtypes = [vp, i64, i64, i32, vp, vp, i32, i32, vp, i32, vp, i64, i32, vp]
+    lib.rgcn_gram3x_tf32.restype = C.c_int
+    lib.rgcn_gram3x_tf32.argtypes = [vp, i64, i32, vp, i64, i32, i64, vp, i64, vp]
     lib.rgcn_attn_head_fwd.restype = C.c_int
     lib.rgcn_attn_head_fwd.argtypes = [vp, i64, vp, i64, i64, i32, i64, i32, i32, vp, vp, vp, i64, vp]
     lib.rgcn_attn_head_bwd.restype = C.c_int

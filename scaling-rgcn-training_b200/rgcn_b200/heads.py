@@ -91,6 +91,35 @@ def gemm(a: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: str = 'n
     return out[:, :n] if ld != n else out
 
 
+def padded_like(rows: int, cols: int, device) -> Tensor:
+    """An uninitialised [rows, cols] view of a [rows, ceil4(cols)] buffer (16-byte addressable rows)."""
+    return torch.empty((rows, _pad(cols, 4)), dtype=torch.float32, device=device)[:, :cols]
+
+
+def gram(a: Tensor, b: Tensor) -> Tensor:
+    """a^T @ b for a [M, n1], b [M, n2] with M = all nodes: the parameter-gradient reduction of a head, on the
+    engine's split-K tcgen05 kernel (csrc/gram_tc.cu).  Operands that are not 16-byte addressable are copied."""
+    lib = _lib.load()
+    if not a.is_cuda or not b.is_cuda or a.dtype != torch.float32 or b.dtype != torch.float32 or a.size(0) != b.size(0):
+        raise _lib.EngineError('gram: two CUDA fp32 matrices with the same number of rows (no CPU path)')
+    n1, n2 = a.size(1), b.size(1)
+
+    def cost(m_side, n_side):                    # tensor-core work: 128-column blocks of the M side x the padded N side
+        return float('inf') if n_side > 192 else ((m_side + 127) // 128) * (128 + _pad(n_side, 32))
+    swap = cost(n2, n1) < cost(n1, n2)
+    if swap:
+        a, b, n1, n2 = b, a, n2, n1
+    if n2 > 192:
+        raise _lib.EngineError('gram: one side must be at most 192 wide')
+    a, b = rows16(a), rows16(b)
+    c = torch.empty((n1, n2), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = lib.rgcn_gram3x_tf32(a.data_ptr(), a.stride(0), n1, b.data_ptr(), b.stride(0), n2, a.size(0), c.data_ptr(), n2,
+                                  _stream(a.device))
+    _lib.check(rc, 'rgcn_gram3x_tf32')
+    return c.t().contiguous() if swap else c
+
+
 class _MLPHeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, e_cat: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor) -> Tensor:

@@ -369,3 +369,24 @@ def test_attention_head_per_thread_fallback_kernels():
     res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600,
                          env={**os.environ, 'RGCN_B200_ATTN_STAGED': '0'})
     assert res.returncode == 0, (res.stdout[-500:], res.stderr[-2000:])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('m,n1,n2', [(7, 5, 3), (33, 63, 63), (1000, 137, 189), (5000, 128, 63), (100000, 63, 137), (4097, 200, 192),
+                                      (640000, 126, 63)])
+def test_tcgen05_gram_is_fp32_faithful(m, n1, n2):
+    """C = A^T B (both operands MN-major on the tensor cores, split over the rows, 3xTF32 with BOTH operands split in
+    shared memory) against an fp64 reference; row / column tails, two 128-column blocks, either orientation."""
+    from rgcn_b200.heads import gram, padded_like
+    torch.manual_seed(m + n1 + n2)
+    a = padded_like(m, n1, DEV)
+    b = padded_like(m, n2, DEV)
+    a.copy_(torch.randn(m, n1, device=DEV))
+    b.copy_(torch.randn(m, n2, device=DEV) * 0.1 + 0.02)
+    want = a.double().t() @ b.double()
+    got = gram(a, b)
+    assert tuple(got.shape) == (n1, n2)
+    fp32 = a.t() @ b
+    assert rel_err(got, want) < max(TOL, 4 * rel_err(fp32, want)), (rel_err(got, want), rel_err(fp32, want))
+    # unpadded operands are copied, not rejected
+    assert rel_err(gram(a.contiguous(), b.contiguous()), want) < max(TOL, 4 * rel_err(fp32, want))
