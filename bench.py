@@ -305,13 +305,26 @@ def bench_heads(n, r, data, x_train_h, y_train_h, device, world, args, peak):
             return loss.item()
         steps[name] = time_steps(step, min(args.steps, 10), 3, world, device) / min(args.steps, 10)
         del opt
+        if name in ('mlp', 'attention'):
+            # the same step captured once in a CUDA graph (the eager step spends ~8 ms per step on the host side)
+            from rgcn_b200.trainer import GraphedTrainStep
+            data.x_train, data.y_train = x_train_h.to(device), y_train_h.to(device)
+            graphed = GraphedTrainStep(m, data, make_optimizer(m, capturable=True), ce_loss, identity)
+            graphed.prefetch(x_train_h, y_train_h)
+
+            def graphed_step():
+                loss = graphed()
+                graphed.prefetch(x_train_h, y_train_h)
+                return loss.item()
+            steps[name + '_graphed'] = time_steps(graphed_step, min(args.steps, 10), 3, world, device) / min(args.steps, 10)
+            del graphed
         if name == 'summation' or name.startswith('attention'):
             del m
             torch.cuda.empty_cache()
     out['trainer_step_ms'] = steps
     out['what'] = ('frozen transferred summary embeddings (S = 3), -e_freeze True; mlp = engine tcgen05 head, mlp_torch_head = '
                    'nn.Linear calls, attention = engine head (tcgen05 projections + one softmax kernel, query position 0 only), '
-                   'attention_torch_head = nn.MultiheadAttention')
+                   'attention_torch_head = nn.MultiheadAttention; *_graphed = the engine-head step captured in one CUDA graph (GraphedTrainStep)')
     return out
 
 

@@ -243,7 +243,9 @@ int rgcn_nvl_store_rows_sparse(float* src, int64_t lds, int32_t cols, const floa
 
 /* Dense contractions of the path on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMA operand
  * loads, accumulators in tensor memory), fp32-faithful through the error-compensated 3xTF32 split:
- *   C[m, n_store] = act( A[m, k] . W[n, k]^T + bias )       act 0 = identity, 1 = tanh
+ *   C[m, n_store] = act( A[m, k] . W[n, k]^T + bias )       act 0 = identity, 1 = tanh,
+ *                                                            2 = multiply by (1 - aux^2), the tanh backward
+ *                                                            (aux [m, ldaux]: the saved tanh output; else null)
  * — the two nn.Linear calls of the reference's MLP transfer head (model/layers.py:105-107).
  * rgcn_gemm_prepack splits W ([n, k], leading dimension ldw; transpose = 1: W is given as [k, n]) once per call
  * into hi / lo parts, zero-padded to [n_pad, k_pad] (n_pad % 16 == 0, <= 256; k_pad % 32 == 0).
@@ -253,8 +255,8 @@ int rgcn_nvl_store_rows_sparse(float* src, int64_t lds, int32_t cols, const floa
 int rgcn_gemm_prepack(const float* w, int64_t ldw, int32_t n, int32_t k, int32_t n_pad, int32_t k_pad,
                       int32_t transpose, float* w_hi, float* w_lo, void* stream);
 int rgcn_gemm3x_tf32(const float* a, int64_t lda, int64_t m, int32_t k, const float* w_hi, const float* w_lo,
-                     int32_t n_pad, int32_t k_pad, const float* bias_padded, int32_t act, float* c, int64_t ldc,
-                     int32_t n_store, void* stream);
+                     int32_t n_pad, int32_t k_pad, const float* bias_padded, int32_t act, const float* aux,
+                     int64_t ldaux, float* c, int64_t ldc, int32_t n_store, void* stream);
 
 /* c[n1, n2] = a[rows, n1]^T . b[rows, n2] (fp32-faithful 3xTF32 on tcgen05, split over the rows, c zeroed inside):
  * the parameter-gradient reductions of the transfer heads (autograd of reference model/layers.py:59-61, 103-107).

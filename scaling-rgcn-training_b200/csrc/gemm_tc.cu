@@ -40,7 +40,10 @@ struct GemmArgs {
     int BN;             // padded N (multiple of 16, <= 256)
     int n_store;        // columns written per row of C (<= ldc); columns >= N receive act(0 + 0) = 0 for both acts
     const float* bias;  // [BN] padded with zeros, or null
-    int act;            // 0 identity, 1 tanh
+    int act;            // 0 identity, 1 tanh, 2 multiply by (1 - aux^2): the tanh backward, aux = the saved tanh output
+    const float* aux;   // [M, >= N] (act 2)
+    int64_t ldaux;
+    int n_aux;          // readable columns of aux
     float* C;
     int64_t ldc;
     int stages;
@@ -270,6 +273,18 @@ k_gemm3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
                         if (g.act == 1) x = tanhf(x);
                         v[i] = x;
                     }
+                    if (g.act == 2) {   // tanh backward: times (1 - h^2), h read 16 bytes at a time (rows of aux are 16-byte addressable)
+                        const float* hrow = g.aux + row * g.ldaux + c0;
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (c0 + i + 3 < g.n_aux) h = __ldg(reinterpret_cast<const float4*>(hrow + i));
+                            v[i] *= 1.f - h.x * h.x;
+                            v[i + 1] *= 1.f - h.y * h.y;
+                            v[i + 2] *= 1.f - h.z * h.z;
+                            v[i + 3] *= 1.f - h.w * h.w;
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
                         const int c = c0 + i;
@@ -356,11 +371,12 @@ extern "C" int rgcn_gemm_prepack(const float* w, int64_t ldw, int32_t n, int32_t
 }
 
 extern "C" int rgcn_gemm3x_tf32(const float* a, int64_t lda, int64_t m, int32_t k, const float* w_hi, const float* w_lo,
-                                int32_t n_pad, int32_t k_pad, const float* bias_padded, int32_t act, float* c, int64_t ldc,
-                                int32_t n_store, void* stream) {
+                                int32_t n_pad, int32_t k_pad, const float* bias_padded, int32_t act, const float* aux,
+                                int64_t ldaux, float* c, int64_t ldc, int32_t n_store, void* stream) {
     if (!a || !w_hi || !w_lo || !c || m < 0 || k <= 0 || lda < k || (lda % 4) || ((uintptr_t)a & 15) || (n_pad % 16) ||
         n_pad <= 0 || n_pad > 256 || (k_pad % 32) || k_pad < k || n_store <= 0 || n_store > n_pad || ldc < n_store ||
-        (ldc % 4) || ((uintptr_t)c & 15) || act < 0 || act > 1)
+        (ldc % 4) || ((uintptr_t)c & 15) || act < 0 || act > 2 ||
+        (act == 2 && (!aux || ldaux <= 0 || (ldaux % 4) || ((uintptr_t)aux & 15))))
         return fail(RGCN_ERR_INVALID_ARG, "rgcn_gemm3x_tf32: bad argument (rows of A and C 16-byte addressable, n_pad % 16 == 0 <= 256)");
     if (m == 0) return 0;
     CUtensorMap ma, mh, ml;
@@ -376,6 +392,9 @@ extern "C" int rgcn_gemm3x_tf32(const float* a, int64_t lda, int64_t m, int32_t 
     g.n_store = n_store;
     g.bias = bias_padded;
     g.act = act;
+    g.aux = aux;
+    g.ldaux = ldaux;
+    g.n_aux = (int)std::min<int64_t>(ldaux, n_pad);   // (whole quads: ldaux % 4 == 0)
     g.C = c;
     g.ldc = ldc;
     const int stage_bytes = 2 * A_TILE + 2 * n_pad * BK * 4;

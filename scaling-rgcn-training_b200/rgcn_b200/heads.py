@@ -6,8 +6,8 @@ graph (AM-shape: 1.67 M x 189 x 137 and x 137 x 63).  Forward runs on the engine
 accumulators in tensor memory, bias / tanh in the epilogue); ``lin2``'s result is written straight into
 zero-padded 64-wide rows, i.e. the 16-byte addressable layout the first R-GCN layer gathers from, so the
 layer needs no padding copy of x0.  Backward: ``dL/dh`` through the same kernel (W2 as the transposed
-operand); the parameter gradients are reductions over all nodes with tiny outputs (137 x 189) and go
-through torch matmuls on the saved activations.
+operand); the parameter gradients are reductions over all nodes with tiny outputs (137 x 189): the engine's
+split-K tcgen05 kernel (csrc/gram_tc.cu, ``gram``; RGCN_B200_GRAM=0 restores the torch matmuls).
 
 Attention head: ``x0 = MHA(E, E, E)[0]`` with S heads over the S stacked summary embeddings.  Only query position 0 is
 kept by the reference, so the engine projects Q from summary 0 alone and K | V from all S summaries (two tcgen05
@@ -17,6 +17,7 @@ ones tensor of the [N * heads, S, S] attention-weight shape, the call nn.Multihe
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -65,8 +66,9 @@ def rows16(a: Tensor) -> Tensor:
 
 
 def gemm(a: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: str = 'none', out_ld: Optional[int] = None,
-         transpose_w: bool = False) -> Tensor:
+         transpose_w: bool = False, aux: Optional[Tensor] = None) -> Tensor:
     """act(a @ W^T + bias) on the tcgen05 kernel.  a [m, k]; weight [n, k] (transpose_w: weight is [k, n]).
+    act: 'none', 'tanh', or 'dtanh' = multiply by (1 - aux^2) with aux [m, n] the saved tanh output.
     Returns a [m, n] VIEW of an [m, out_ld] buffer whose extra columns are zero (out_ld default = n rounded up to 4)."""
     lib = _lib.load()
     if not a.is_cuda or a.dtype != torch.float32:
@@ -83,10 +85,16 @@ def gemm(a: Tensor, weight: Tensor, bias: Optional[Tensor] = None, act: str = 'n
         bp = torch.zeros(n_pad, dtype=torch.float32, device=a.device)
         bp[:n] = bias.detach()
     out = torch.empty((m, ld), dtype=torch.float32, device=a.device)
+    code = {'none': 0, 'tanh': 1, 'dtanh': 2}[act]
+    if code == 2:
+        if aux is None or aux.shape != (m, n) or not aux.is_cuda:
+            raise ValueError("gemm: act='dtanh' needs aux [m, n]")
+        aux = rows16(aux)
     with torch.cuda.device(a.device):
         rc = lib.rgcn_gemm3x_tf32(a.data_ptr(), a.stride(0), m, k, hi.data_ptr(), lo.data_ptr(), n_pad, k_pad,
-                                  bp.data_ptr() if bp is not None else None, 1 if act == 'tanh' else 0, out.data_ptr(), ld, ld,
-                                  _stream(a.device))
+                                  bp.data_ptr() if bp is not None else None, code,
+                                  aux.data_ptr() if code == 2 else None, aux.stride(0) if code == 2 else 0,
+                                  out.data_ptr(), ld, ld, _stream(a.device))
     _lib.check(rc, 'rgcn_gemm3x_tf32')
     return out[:, :n] if ld != n else out
 
@@ -133,15 +141,17 @@ class _MLPHeadFn(torch.autograd.Function):
     def backward(ctx, g: Tensor):
         a, h, w1, w2 = ctx.saved_tensors
         need_e, need_w1, need_b1, need_w2, need_b2 = ctx.needs_input_grad
-        g = g.contiguous()
-        gw2 = g.t() @ h if need_w2 else None                  # [emb, mid]: reduction over all nodes, tiny output
+        g = rows16(g)                                         # (one padding copy when the layer hands over packed rows)
+        use_gram = os.environ.get('RGCN_B200_GRAM', '1') != '0'
+        red = gram if use_gram else (lambda p, q: p.t() @ q)  # [out, in] = reduction over all nodes, tiny result
+        gw2 = red(g, h) if need_w2 else None                  # [emb, mid]
         gb2 = g.sum(0) if need_b2 else None
         ge = gw1 = gb1 = None
         if need_e or need_w1 or need_b1:
-            dh = gemm(g, w2, transpose_w=True)                # g @ W2 -> [N, mid] on the tensor-core kernel
-            dpre = dh * (1.0 - h * h)
+            # (g @ W2) * (1 - h^2) -> [N, mid]: the tanh backward rides in the epilogue of the tensor-core kernel
+            dpre = gemm(g, w2, transpose_w=True, act='dtanh', aux=h)
             if need_w1:
-                gw1 = dpre.t() @ a
+                gw1 = red(dpre, a)
             if need_b1:
                 gb1 = dpre.sum(0)
             if need_e:
@@ -216,8 +226,10 @@ class _AttentionHeadFn(torch.autograd.Function):
         e_flat, q, kv, probs, o, w_in, w_out, keep, w_kv = ctx.saved_tensors
         s, n, emb, heads, d, has_b_in, ep = ctx.dims
         need_e, need_w_in, need_b_in, need_w_out, need_b_out = ctx.needs_input_grad[:5]
-        g = g.contiguous()
-        gw_out = g.t() @ o if need_w_out else None
+        g = rows16(g)
+        use_gram = os.environ.get('RGCN_B200_GRAM', '1') != '0'
+        red = gram if use_gram else (lambda p, q: p.t() @ q)
+        gw_out = red(g, o) if need_w_out else None
         gb_out = g.sum(0) if need_b_out else None
         ge = gw_in = gb_in = None
         if need_e or need_w_in or need_b_in:
@@ -232,8 +244,8 @@ class _AttentionHeadFn(torch.autograd.Function):
             _lib.check(rc, 'rgcn_attn_head_bwd')
             gq = gq[:, :emb]
             if need_w_in:
-                gkv_w = gkv.t() @ e_flat                                                # [2 ep, emb]; the pad rows are dropped
-                gw_in = torch.cat([gq.t() @ e_flat[:n], gkv_w[:emb], gkv_w[ep:ep + emb]], 0)
+                gkv_w = red(gkv, e_flat)                                                # [2 ep, emb]; the pad rows are dropped
+                gw_in = torch.cat([red(gq, e_flat[:n]), gkv_w[:emb], gkv_w[ep:ep + emb]], 0)
             if need_b_in and has_b_in:
                 gkv_b = gkv.sum(0)
                 gb_in = torch.cat([gq.sum(0), gkv_b[:emb], gkv_b[ep:ep + emb]], 0)

@@ -289,6 +289,10 @@ def test_tcgen05_gemm_is_fp32_faithful(m, k, n, act):
     a2 = torch.randn(m, n, device=DEV)
     got2 = gemm(a2, w, transpose_w=True)
     assert rel_err(got2, a2.double() @ w.double()) < TOL
+    # ... with the tanh backward in the epilogue: (a2 @ W) * (1 - h^2)
+    h = torch.tanh(torch.randn(m, k, device=DEV))
+    got3 = gemm(a2, w, transpose_w=True, act='dtanh', aux=h)
+    assert rel_err(got3, (a2.double() @ w.double()) * (1 - h.double() ** 2)) < TOL
 
 
 @pytest.mark.gpu

@@ -45,4 +45,20 @@ with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) a
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=25, max_name_column_width=70))
+print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=40, max_name_column_width=70))
+# timeline of the last step: every device activity in start order, with the idle gap in front of it
+import json
+import tempfile
+path = os.path.join(tempfile.gettempdir(), 'heads_trace.json')
+prof.export_chrome_trace(path)
+ev = [e for e in json.load(open(path))['traceEvents'] if e.get('cat') in ('kernel', 'gpu_memcpy', 'gpu_memset') and 'dur' in e]
+ev.sort(key=lambda e: e['ts'])
+ev = ev[len(ev) * 2 // 3:]
+t0, end, busy = ev[0]['ts'], ev[0]['ts'], 0.0
+print('--- last step: start_us  dur_us  gap_before_us  stream  name')
+for e in ev:
+    gap = e['ts'] - end
+    print('%9.1f %8.1f %8.1f  %s  %s' % (e['ts'] - t0, e['dur'], max(gap, 0.0), e.get('args', {}).get('stream', '?'), e['name'][:90]))
+    busy += e['dur']
+    end = max(end, e['ts'] + e['dur'])
+print('span_us', end - t0, 'sum_of_durations_us', busy)
