@@ -111,6 +111,10 @@ class _RGCNLayerFn(torch.autograd.Function):
         if push:   # sum of the ranks' partials, each rank keeping its own rows
             out_buf = comm.reduce_scatter_rows(out_buf, comm_key)[:graph.num_owned]
             out = out_buf[:, :fout] if ldo != fout else out_buf
+        # an odd-width input that arrives in zero-padded 16-byte addressable rows (the engine's transfer heads write x0
+        # that way) gets its gradient in the same layout: the head's backward reads it without a padding copy
+        ctx.gx_ld = x.stride(0) if (comm is None and mirror is None and fin % 4 != 0 and x.stride(0) % 4 == 0
+                                    and x.stride(0) >= fin and x.data_ptr() % 16 == 0) else 0
         if mirror is not None:
             x = mirror              # what backward re-gathers; the caller's tensor is not kept
         ctx.graph, ctx.flags, ctx.comm, ctx.fin, ctx.comm_key = graph, flags, comm, fin, comm_key
@@ -158,7 +162,9 @@ class _RGCNLayerFn(torch.autograd.Function):
             # 64 x 64 column passes run on the tcgen05 kernel, which adds whole 256-byte rows: an odd-width
             # gradient (emb = 63 next to hidden 64) is accumulated in 64-wide rows and returned as a view
             wide = 32 < fin <= 64 and 32 < fout <= 64 and fin % 4 != 0 and os.environ.get('RGCN_B200_TC', '1') != '0'
-            if wide:
+            if ctx.gx_ld:
+                gx = torch.empty((graph.num_owned, ctx.gx_ld), dtype=torch.float32, device=dev)[:, :fin]
+            elif wide:
                 gx = torch.empty((graph.num_owned, 64), dtype=torch.float32, device=dev)[:, :fin]
             else:
                 gx = torch.empty((graph.num_owned, fin), dtype=torch.float32, device=dev)
