@@ -47,6 +47,8 @@ struct GemmArgs {
     float* C;
     int64_t ldc;
     int stages;
+    int w_resident;     // 1: the split W tiles of ALL K blocks stay in shared memory for the CTA's lifetime (loaded once);
+                        //    the ring then holds A tiles only — more bytes of A in flight per SM
 };
 
 // round to nearest tf32 (10-bit mantissa), result as an fp32 bit pattern: both parts of a split are then exactly
@@ -132,14 +134,20 @@ k_gemm3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
     const int w_tile = g.BN * BK * 4;
-    const int stage_bytes = 2 * A_TILE + 2 * w_tile;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + (size_t)g.stages * stage_bytes);
+    const int stage_bytes = 2 * A_TILE + (g.w_resident ? 0 : 2 * w_tile);
+    const uint32_t w_res = base + (uint32_t)(g.stages * stage_bytes);      // resident W: [K_blocks][hi | lo]
+    const int w_res_bytes = g.w_resident ? g.K_blocks * 2 * w_tile : 0;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + (size_t)g.stages * stage_bytes + w_res_bytes);
     uint64_t* full = bars;                       // TMA bytes landed            [stages]
     uint64_t* split = bars + g.stages;           // A split into hi / lo        [stages]
     uint64_t* empty = bars + 2 * g.stages;       // MMAs of the stage retired   [stages]
     uint64_t* acc_full = bars + 3 * g.stages;    // accumulator complete        [ACC_STAGES]
     uint64_t* acc_empty = acc_full + ACC_STAGES; // accumulator drained         [ACC_STAGES]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+    uint64_t* w_full = acc_empty + ACC_STAGES;   // resident W landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+    // epilogue staging: per warp a [32 rows x 16 columns] slab, 16-byte chunks XOR-swizzled by the row so that both the
+    // per-row writes and the transposed reads are conflict-free
+    float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t num_tiles = (g.M + BM - 1) / BM;
 
@@ -153,6 +161,7 @@ k_gemm3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
             mbar_init(acc_full + a, 1);
             mbar_init(acc_empty + a, 4);     // one arrival per epilogue warp
         }
+        mbar_init(w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -169,16 +178,26 @@ k_gemm3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            if (g.w_resident) {
+                uint8_t* wr = sm + (size_t)g.stages * stage_bytes;
+                mbar_expect_tx(w_full, (uint32_t)w_res_bytes);
+                for (int kb = 0; kb < g.K_blocks; ++kb) {
+                    tma_load_2d(wr + (size_t)kb * 2 * w_tile, &map_whi, kb * BK, 0, w_full);
+                    tma_load_2d(wr + (size_t)kb * 2 * w_tile + w_tile, &map_wlo, kb * BK, 0, w_full);
+                }
+            }
             int s = 0;
             uint32_t ph = 0;
             for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 for (int kb = 0; kb < g.K_blocks; ++kb) {
                     mbar_wait(empty + s, ph ^ 1);
                     uint8_t* st = sm + (size_t)s * stage_bytes;
-                    mbar_expect_tx(full + s, (uint32_t)(A_TILE + 2 * w_tile));
+                    mbar_expect_tx(full + s, (uint32_t)(g.w_resident ? A_TILE : A_TILE + 2 * w_tile));
                     tma_load_2d(st, &map_a, kb * BK, (int)(t * BM), full + s);
-                    tma_load_2d(st + 2 * A_TILE, &map_whi, kb * BK, 0, full + s);
-                    tma_load_2d(st + 2 * A_TILE + w_tile, &map_wlo, kb * BK, 0, full + s);
+                    if (!g.w_resident) {
+                        tma_load_2d(st + 2 * A_TILE, &map_whi, kb * BK, 0, full + s);
+                        tma_load_2d(st + 2 * A_TILE + w_tile, &map_wlo, kb * BK, 0, full + s);
+                    }
                     if (++s == g.stages) {
                         s = 0;
                         ph ^= 1;
@@ -191,6 +210,7 @@ k_gemm3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
         const uint32_t idesc = umma_idesc(g.BN);
         int s = 0, a = 0;
         uint32_t ph = 0, aph = 0;
+        if (g.w_resident && blockIdx.x < num_tiles) mbar_wait(w_full, 0);
         for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             mbar_wait(acc_empty + a, aph ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -201,7 +221,8 @@ k_gemm3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
                     const uint32_t st = base + (uint32_t)(s * stage_bytes);
-                    const uint32_t a_hi = st, a_lo = st + A_TILE, w_hi = st + 2 * A_TILE, w_lo = w_hi + w_tile;
+                    const uint32_t a_hi = st, a_lo = st + A_TILE;
+                    const uint32_t w_hi = g.w_resident ? w_res + (uint32_t)(kb * 2 * w_tile) : st + 2 * A_TILE, w_lo = w_hi + w_tile;
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {       // tf32: K = 8 (32 bytes) per instruction
                         const uint32_t ko = (uint32_t)(k * 32);
@@ -261,17 +282,28 @@ k_gemm3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
             mbar_wait(acc_full + a, aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t row = t * BM + ew * 32 + lane;
-            float* crow = g.C + row * g.ldc;
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * ACC_COLS);
+                    const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * ACC_COLS);
             for (int c0 = 0; c0 < g.BN; c0 += 16) {
                 float v[16];
                 tmem_ld16(taddr0 + (uint32_t)c0, v);
                 if (row < g.M) {
+                    // (bias as four 16-byte loads and the activation branch outside the element loop: element-wise
+                    // `v[i] + (bias ? ldg : 0)` compiled to 16 dependent load -> add -> branch steps per chunk and made
+                    // the epilogue the bound of the whole kernel, ~1.2 us per 16 columns)
+                    if (g.bias) {
+                        const float4* bp = reinterpret_cast<const float4*>(g.bias + c0);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float x = v[i] + (g.bias ? __ldg(g.bias + c0 + i) : 0.f);
-                        if (g.act == 1) x = tanhf(x);
-                        v[i] = x;
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 b = __ldg(bp + i);
+                            v[4 * i] += b.x;
+                            v[4 * i + 1] += b.y;
+                            v[4 * i + 2] += b.z;
+                            v[4 * i + 3] += b.w;
+                        }
+                    }
+                    if (g.act == 1) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
                     }
                     if (g.act == 2) {   // tanh backward: times (1 - h^2), h read 16 bytes at a time (rows of aux are 16-byte addressable)
                         const float* hrow = g.aux + row * g.ldaux + c0;
@@ -285,17 +317,32 @@ k_gemm3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
                             v[i + 3] *= 1.f - h.w * h.w;
                         }
                     }
+                }
+                // a thread holds 16 columns of ITS row: stored from here a warp instruction would touch 32 rows with 16
+                // bytes each.  Through the slab every store instruction writes 8 rows x 64 contiguous bytes instead.
+                float4* slab = reinterpret_cast<float4*>(epi_stage + ew * 512);
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        const int c = c0 + i;
+                for (int j = 0; j < 4; ++j)
+                    slab[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int r = it * 8 + (lane >> 2), q = lane & 3;
+                    const float4 o = slab[r * 4 + (q ^ ((r >> 1) & 3))];
+                    const int64_t grow = t * BM + ew * 32 + r;
+                    const int c = c0 + 4 * q;
+                    if (grow < g.M) {
+                        float* cp = g.C + grow * g.ldc + c;
                         if (c + 3 < g.n_store) {
-                            *reinterpret_cast<float4*>(crow + c) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            *reinterpret_cast<float4*>(cp) = o;
                         } else {
-                            for (int j = 0; j < 4; ++j)
-                                if (c + j < g.n_store) crow[c + j] = v[i + j];
+                            if (c < g.n_store) cp[0] = o.x;
+                            if (c + 1 < g.n_store) cp[1] = o.y;
+                            if (c + 2 < g.n_store) cp[2] = o.z;
                         }
                     }
                 }
+                __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -375,7 +422,7 @@ extern "C" int rgcn_gemm3x_tf32(const float* a, int64_t lda, int64_t m, int32_t 
                                 int64_t ldaux, float* c, int64_t ldc, int32_t n_store, void* stream) {
     if (!a || !w_hi || !w_lo || !c || m < 0 || k <= 0 || lda < k || (lda % 4) || ((uintptr_t)a & 15) || (n_pad % 16) ||
         n_pad <= 0 || n_pad > 256 || (k_pad % 32) || k_pad < k || n_store <= 0 || n_store > n_pad || ldc < n_store ||
-        (ldc % 4) || ((uintptr_t)c & 15) || act < 0 || act > 2 ||
+        (ldc % 4) || ((uintptr_t)c & 15) || ((uintptr_t)bias_padded & 15) || act < 0 || act > 2 ||
         (act == 2 && (!aux || ldaux <= 0 || (ldaux % 4) || ((uintptr_t)aux & 15))))
         return fail(RGCN_ERR_INVALID_ARG, "rgcn_gemm3x_tf32: bad argument (rows of A and C 16-byte addressable, n_pad % 16 == 0 <= 256)");
     if (m == 0) return 0;
@@ -397,11 +444,21 @@ extern "C" int rgcn_gemm3x_tf32(const float* a, int64_t lda, int64_t m, int32_t 
     g.n_aux = (int)std::min<int64_t>(ldaux, n_pad);   // (whole quads: ldaux % 4 == 0)
     g.C = c;
     g.ldc = ldc;
-    const int stage_bytes = 2 * A_TILE + 2 * n_pad * BK * 4;
-    const int budget = 227 * 1024 - 1024 /*alignment*/ - 256 /*barriers*/;
-    g.stages = std::max(2, std::min(6, budget / stage_bytes));
-    const int smem = g.stages * stage_bytes + 1024 + 256;
-    if (g.stages * stage_bytes + 1280 > 227 * 1024) return fail(RGCN_ERR_UNSUPPORTED, "rgcn_gemm3x_tf32: tile does not fit shared memory");
+    const int w_tile = n_pad * BK * 4;
+    const int budget = 227 * 1024 - 1024 /*alignment*/ - 256 /*barriers*/ - 8192 /*epilogue slabs*/;
+    // W resident (all K blocks, hi + lo) when at least 3 A stages still fit: the ring then carries A only.  Measured
+    // (ncu, AM shape): with W in the ring 3 stages = 48 KB of A in flight per SM bound the kernel at 1.7 TB/s
+    static const bool res_on = [] {
+        const char* e = getenv("RGCN_B200_GEMM_WRES");
+        return !(e && e[0] == '0');
+    }();
+    const int w_res_bytes = g.K_blocks * 2 * w_tile;
+    g.w_resident = res_on && w_res_bytes + 3 * 2 * A_TILE <= budget;
+    const int stage_bytes = 2 * A_TILE + (g.w_resident ? 0 : 2 * w_tile);
+    const int ring_budget = budget - (g.w_resident ? w_res_bytes : 0);
+    g.stages = std::max(2, std::min(8, ring_budget / stage_bytes));
+    const int smem = g.stages * stage_bytes + (g.w_resident ? w_res_bytes : 0) + 1024 + 256 + 8192;
+    if (smem > 227 * 1024) return fail(RGCN_ERR_UNSUPPORTED, "rgcn_gemm3x_tf32: tile does not fit shared memory");
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
