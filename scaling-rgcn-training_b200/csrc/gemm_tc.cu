@@ -18,7 +18,8 @@
 //                              tile), both exactly representable, so the product keeps ~22 mantissa bits
 //                              (error-compensated 3xTF32, the dropped lo.lo term is ~2^-22, zero-mean)
 //                              whatever rounding the hardware applies
-//   warps 8-11  epilogue       tcgen05.ld 32x32b (SASS LDTM) -> + bias -> tanh (optional) -> global rows
+//   warps 8-15  epilogue       tcgen05.ld 32x32b (SASS LDTM) -> + bias -> tanh / tanh backward (optional) -> a
+//                              swizzled shared-memory slab -> global rows, 8 rows x 64 contiguous bytes per store
 //
 // W is split once per call by rgcn_gemm_prepack (tiny); rows of A must be 16-byte addressable (TMA), the
 // K tail and the M tail are zero-filled by the TMA unit itself.
@@ -31,7 +32,8 @@ namespace {
 
 constexpr int BM = 128, BK = 32;            // tile rows, K block (32 fp32 = one 128-byte swizzle row)
 constexpr int A_TILE = BM * BK * 4;         // 16 KB
-constexpr int NUM_THREADS = 384;
+constexpr int NUM_THREADS = 512;            // 16 warps: producer, MMA, TMEM allocator, (idle), 4 splitters, 8 epilogue
+constexpr int EPI_WARPS = 8;
 constexpr int ACC_COLS = 256, ACC_STAGES = 2;
 
 struct GemmArgs {
@@ -159,7 +161,7 @@ k_gemm3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
         }
         for (int a = 0; a < ACC_STAGES; ++a) {
             mbar_init(acc_full + a, 1);
-            mbar_init(acc_empty + a, 4);     // one arrival per epilogue warp
+            mbar_init(acc_empty + a, EPI_WARPS);   // one arrival per epilogue warp
         }
         mbar_init(w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -275,15 +277,25 @@ k_gemm3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
         }
     } else if (warp >= 8) {
         // ===== epilogue: TMEM -> registers -> bias / tanh -> C =====
-        const int ew = warp - 8;                 // TMEM lanes 32 ew .. 32 ew + 31 (warp % 4 == ew)
+        // two warps per TMEM lane quarter, each taking every other 16-column chunk: a single warp per scheduler
+        // issues its dependent chain at ~5 cycles per instruction, which bound the kernel (0.46 us per chunk)
+        const int ew = warp & 3;                 // TMEM lanes 32 ew .. 32 ew + 31 (warp % 4 == ew)
+        const int half = (warp - 8) >> 2;        // chunk parity
         int a = 0;
         uint32_t aph = 0;
         for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             mbar_wait(acc_full + a, aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t row = t * BM + ew * 32 + lane;
-                    const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * ACC_COLS);
-            for (int c0 = 0; c0 < g.BN; c0 += 16) {
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * ACC_COLS);
+            // the four store rows of this lane (slab row 8 it + lane / 4), columns c0 + 4 (lane % 4) ..
+            float* cp4[4];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int64_t grow = t * BM + ew * 32 + it * 8 + (lane >> 2);
+                cp4[it] = grow < g.M ? g.C + grow * g.ldc + 4 * (lane & 3) : nullptr;
+            }
+            for (int c0 = 16 * half; c0 < g.BN; c0 += 32) {
                 float v[16];
                 tmem_ld16(taddr0 + (uint32_t)c0, v);
                 if (row < g.M) {
@@ -320,7 +332,7 @@ k_gemm3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
                 }
                 // a thread holds 16 columns of ITS row: stored from here a warp instruction would touch 32 rows with 16
                 // bytes each.  Through the slab every store instruction writes 8 rows x 64 contiguous bytes instead.
-                float4* slab = reinterpret_cast<float4*>(epi_stage + ew * 512);
+                float4* slab = reinterpret_cast<float4*>(epi_stage + (warp - 8) * 512);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     slab[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -329,10 +341,9 @@ k_gemm3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
                 for (int it = 0; it < 4; ++it) {
                     const int r = it * 8 + (lane >> 2), q = lane & 3;
                     const float4 o = slab[r * 4 + (q ^ ((r >> 1) & 3))];
-                    const int64_t grow = t * BM + ew * 32 + r;
                     const int c = c0 + 4 * q;
-                    if (grow < g.M) {
-                        float* cp = g.C + grow * g.ldc + c;
+                    if (cp4[it]) {
+                        float* cp = cp4[it] + c0;
                         if (c + 3 < g.n_store) {
                             *reinterpret_cast<float4*>(cp) = o;
                         } else {
@@ -445,7 +456,7 @@ extern "C" int rgcn_gemm3x_tf32(const float* a, int64_t lda, int64_t m, int32_t 
     g.C = c;
     g.ldc = ldc;
     const int w_tile = n_pad * BK * 4;
-    const int budget = 227 * 1024 - 1024 /*alignment*/ - 256 /*barriers*/ - 8192 /*epilogue slabs*/;
+    const int budget = 227 * 1024 - 1024 /*alignment*/ - 256 /*barriers*/ - 16384 /*epilogue slabs*/;
     // W resident (all K blocks, hi + lo) when at least 3 A stages still fit: the ring then carries A only.  Measured
     // (ncu, AM shape): with W in the ring 3 stages = 48 KB of A in flight per SM bound the kernel at 1.7 TB/s
     static const bool res_on = [] {
@@ -457,7 +468,7 @@ extern "C" int rgcn_gemm3x_tf32(const float* a, int64_t lda, int64_t m, int32_t 
     const int stage_bytes = 2 * A_TILE + (g.w_resident ? 0 : 2 * w_tile);
     const int ring_budget = budget - (g.w_resident ? w_res_bytes : 0);
     g.stages = std::max(2, std::min(8, ring_budget / stage_bytes));
-    const int smem = g.stages * stage_bytes + (g.w_resident ? w_res_bytes : 0) + 1024 + 256 + 8192;
+    const int smem = g.stages * stage_bytes + (g.w_resident ? w_res_bytes : 0) + 1024 + 256 + 16384;
     if (smem > 227 * 1024) return fail(RGCN_ERR_UNSUPPORTED, "rgcn_gemm3x_tf32: tile does not fit shared memory");
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
