@@ -29,6 +29,7 @@ struct ProfScope {   // records a CUDA-event pair around a launch when profiling
     ~ProfScope();
     cudaStream_t st_;
     int idx_;
+    bool nvtx_;   // an NVTX range (RGCN_B200_NVTX=1) named after the pass, for timeline tools
 };
 
 #define RGCN_CUDA(call)                                                                      \

@@ -1,6 +1,10 @@
 // profile.cu — launch counting and optional per-pass CUDA-event timing (used by bench.py to time
 // the dominant kernel live, on the stream it is launched on, inside the timed region).
+#include <nvtx3/nvToolsExt.h>
+
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -21,7 +25,26 @@ std::atomic<int64_t> g_launches{0};
 
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-ProfScope::ProfScope(int tag, int d0, int d1, cudaStream_t st) : st_(st), idx_(-1) {
+namespace {
+const char* const kTagNames[] = {"pass", "wprep", "chunk_prepass", "tile_fwd", "tile_dx", "wgrad", "copy_cols", "relu_mask",
+                                 "simple", "map_gather", "self_loop", "nvl_store", "nvl_reduce", "gemm"};   // TAG_* order
+bool nvtx_on() {
+    static const bool on = [] {
+        const char* e = getenv("RGCN_B200_NVTX");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+}  // namespace
+
+ProfScope::ProfScope(int tag, int d0, int d1, cudaStream_t st) : st_(st), idx_(-1), nvtx_(false) {
+    if (nvtx_on()) {
+        char name[64];
+        snprintf(name, sizeof(name), "rgcn:%s_%dx%d", tag >= 0 && tag < (int)(sizeof(kTagNames) / sizeof(kTagNames[0])) ? kTagNames[tag] : "pass",
+                 d0, d1);
+        nvtxRangePushA(name);
+        nvtx_ = true;
+    }
     if (!g_enabled.load(std::memory_order_relaxed)) return;
     Rec r{tag, d0, d1, nullptr, nullptr};
     if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
@@ -31,6 +54,7 @@ ProfScope::ProfScope(int tag, int d0, int d1, cudaStream_t st) : st_(st), idx_(-
     idx_ = (int)g_recs.size() - 1;
 }
 ProfScope::~ProfScope() {
+    if (nvtx_) nvtxRangePop();
     if (idx_ < 0) return;
     std::lock_guard<std::mutex> lk(g_mu);
     cudaEventRecord(g_recs[idx_].b, st_);

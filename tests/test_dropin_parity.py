@@ -244,7 +244,8 @@ assert worst < 1e-5, worst
                                  dict(RGCN_B200_VEC4='0', RGCN_B200_ETILE='0'), dict(RGCN_B200_ETILE='0'),
                                  dict(RGCN_B200_PAD='0'), dict(RGCN_B200_PACKED='0'), dict(RGCN_B200_BULK='0'),
                                  dict(RGCN_B200_OVERLAP='0'), dict(RGCN_B200_STAGE='0'), dict(RGCN_B200_WGRAD_T='1'),
-                                 dict(RGCN_B200_WGRAD_T='1', RGCN_B200_WGRAD_T_UPW='3', RGCN_B200_RANGE_NODES='64')])
+                                 dict(RGCN_B200_WGRAD_T='1', RGCN_B200_WGRAD_T_UPW='3', RGCN_B200_RANGE_NODES='64'),
+                                 dict(RGCN_B200_NVTX='1')])
 def test_kernel_family_switches_keep_parity(env):
     """The switches are read once per process, so each combination runs in its own interpreter (the fused
     pad + self-loop pass must only be taken when the mirror is gathered by the vector entry-tile kernels)."""
