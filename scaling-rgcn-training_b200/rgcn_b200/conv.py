@@ -113,8 +113,8 @@ class _RGCNLayerFn(torch.autograd.Function):
             out = out_buf[:, :fout] if ldo != fout else out_buf
         # an odd-width input that arrives in zero-padded 16-byte addressable rows (the engine's transfer heads write x0
         # that way) gets its gradient in the same layout: the head's backward reads it without a padding copy
-        ctx.gx_ld = x.stride(0) if (comm is None and mirror is None and fin % 4 != 0 and x.stride(0) % 4 == 0
-                                    and x.stride(0) >= fin and x.data_ptr() % 16 == 0) else 0
+        ctx.gx_ld = x.stride(0) if (comm is None and mirror is None and fin % 4 != 0
+                                    and x.stride(0) == (fin + 3) // 4 * 4 and x.data_ptr() % 16 == 0) else 0
         if mirror is not None:
             x = mirror              # what backward re-gathers; the caller's tensor is not kept
         ctx.graph, ctx.flags, ctx.comm, ctx.fin, ctx.comm_key = graph, flags, comm, fin, comm_key
