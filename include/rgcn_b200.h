@@ -260,9 +260,11 @@ int rgcn_gemm3x_tf32(const float* a, int64_t lda, int64_t m, int32_t k, const fl
 
 /* c[n1, n2] = a[rows, n1]^T . b[rows, n2] (fp32-faithful 3xTF32 on tcgen05, split over the rows, c zeroed inside):
  * the parameter-gradient reductions of the transfer heads (autograd of reference model/layers.py:59-61, 103-107).
- * Rows of a and b 16-byte addressable (ld % 4 == 0, aligned base); n2 <= 192; ldc >= n2. */
+ * Rows of a and b 16-byte addressable (ld % 4 == 0, aligned base); n2 <= 192; ldc >= n2.
+ * a_colsum [n1] / b_colsum [n2] (nullable): the column sums of a / b over the rows — the bias gradients that go with
+ * c — accumulated while the operands pass through shared memory. */
 int rgcn_gram3x_tf32(const float* a, int64_t lda, int32_t n1, const float* b, int64_t ldb, int32_t n2, int64_t rows,
-                     float* c, int64_t ldc, void* stream);
+                     float* c, int64_t ldc, float* a_colsum, float* b_colsum, void* stream);
 
 /* Per-node core of the attention transfer head (reference model/layers.py:59-61: nn.MultiheadAttention over the
  * num_sums stacked summary embeddings, q = k = v, only attn_output[0] kept).  q [N, heads*head_dim] = the projected

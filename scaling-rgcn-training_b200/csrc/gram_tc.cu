@@ -16,7 +16,8 @@
 //                              operand descriptors MN-major; tcgen05.commit frees the stage / publishes an accumulator
 //   warp 2      TMEM allocator (2 x 256 columns)
 //   warps 4-11  splitter       BOTH operands are activations: each tile is split in shared memory into
-//                              hi = rn_tf32(v) (in place) and lo = rn_tf32(v - hi)
+//                              hi = rn_tf32(v) (in place) and lo = rn_tf32(v - hi); the column sums of A and B (the
+//                              bias gradients that go with C) are accumulated on the way
 //   warps 12-15 drain          tcgen05.ld -> += shared-memory tile; at the end red.global.add.f32 into C
 #include <cuda.h>
 
@@ -43,6 +44,8 @@ struct GramArgs {
     float* C;
     int64_t ldc;
     int stages;
+    float* a_colsum;       // nullable [n1]: sum over the rows of every column of A (the bias gradient that goes with C)
+    float* b_colsum;       // nullable [n2]
 };
 
 __device__ __forceinline__ float rn_tf32(float x) {
@@ -132,6 +135,7 @@ k_gram3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
     uint64_t* acc_full = bars + 3 * g.stages;    // accumulator complete      [ACC_STAGES]
     uint64_t* acc_empty = acc_full + ACC_STAGES; // accumulator drained       [ACC_STAGES]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+    float* colsum_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [GM + MAX_BN]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mb = blockIdx.y;                   // which 128 columns of A
     const int64_t r0 = (int64_t)blockIdx.x * g.rows_per_cta;
@@ -155,6 +159,7 @@ k_gram3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    for (int i = threadIdx.x; i < GM + MAX_BN; i += NUM_THREADS) colsum_s[i] = 0.f;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -217,28 +222,60 @@ k_gram3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
     } else if (warp >= 4 && warp < 12) {
         // ===== splitter (8 warps): hi = rn_tf32(v) in place, lo = rn_tf32(v - hi), for both tiles =====
         const int tid = threadIdx.x - 128;       // 0..255
+        // column sums ride on the split: chunk q = tid + 256 i of a tile is (box tid / 128 + 2 i, row (tid % 128) / 8,
+        // 16-byte chunk tid % 8); the TMA swizzle XORs the 32-byte chunk index with row % 4, so the four floats of the
+        // chunk are columns 32 box + 8 ((tid % 8) / 2 ^ (row & 3)) + 4 (tid & 1) .. + 3 — fixed per thread and i
+        const bool want_a = g.a_colsum != nullptr, want_b = g.b_colsum != nullptr && mb == 0;
+        const int row_in_box = (tid & 127) >> 3;
+        const int col_in_box = 8 * (((tid & 7) >> 1) ^ (row_in_box & 3)) + 4 * (tid & 1);
+        constexpr int A_IT = A_TILE / 16 / 256, B_IT = (MAX_BN / 32) * BOX / 16 / 256;
+        float4 sa[A_IT], sb[B_IT];
+#pragma unroll
+        for (int i = 0; i < A_IT; ++i) sa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < B_IT; ++i) sb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         int s = 0;
         uint32_t ph = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(full + s, ph);
             uint8_t* st = sm + (size_t)s * stage_bytes;
-            auto split_tile = [&](float4* hi, float4* lo, int quads) {
-                for (int q = tid; q < quads; q += 256) {
-                    float4 v = hi[q], h, l;
-                    h.x = rn_tf32(v.x), h.y = rn_tf32(v.y), h.z = rn_tf32(v.z), h.w = rn_tf32(v.w);
-                    l.x = rn_tf32(v.x - h.x), l.y = rn_tf32(v.y - h.y), l.z = rn_tf32(v.z - h.z), l.w = rn_tf32(v.w - h.w);
-                    hi[q] = h;
-                    lo[q] = l;
-                }
+            auto split_one = [&](float4* hi, float4* lo, int q, float4& acc) {
+                float4 v = hi[q], h, l;
+                h.x = rn_tf32(v.x), h.y = rn_tf32(v.y), h.z = rn_tf32(v.z), h.w = rn_tf32(v.w);
+                l.x = rn_tf32(v.x - h.x), l.y = rn_tf32(v.y - h.y), l.z = rn_tf32(v.z - h.z), l.w = rn_tf32(v.w - h.w);
+                hi[q] = h;
+                lo[q] = l;
+                acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
             };
-            split_tile(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + A_TILE), A_TILE / 16);
-            split_tile(reinterpret_cast<float4*>(st + 2 * A_TILE), reinterpret_cast<float4*>(st + 2 * A_TILE + b_tile), b_tile / 16);
+#pragma unroll
+            for (int i = 0; i < A_IT; ++i)
+                split_one(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + A_TILE), tid + 256 * i, sa[i]);
+#pragma unroll
+            for (int i = 0; i < B_IT; ++i)
+                if (tid + 256 * i < b_tile / 16)
+                    split_one(reinterpret_cast<float4*>(st + 2 * A_TILE), reinterpret_cast<float4*>(st + 2 * A_TILE + b_tile),
+                              tid + 256 * i, sb[i]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core reads
             __syncwarp();
             if (lane == 0) mbar_arrive(split + s);
             if (++s == g.stages) {
                 s = 0;
                 ph ^= 1;
+            }
+        }
+        if (want_a) {
+#pragma unroll
+            for (int i = 0; i < A_IT; ++i) {
+                float* p = colsum_s + 32 * ((tid >> 7) + 2 * i) + col_in_box;
+                atomicAdd(p, sa[i].x), atomicAdd(p + 1, sa[i].y), atomicAdd(p + 2, sa[i].z), atomicAdd(p + 3, sa[i].w);
+            }
+        }
+        if (want_b) {
+#pragma unroll
+            for (int i = 0; i < B_IT; ++i) {
+                if (tid + 256 * i >= b_tile / 16) continue;
+                float* p = colsum_s + GM + 32 * ((tid >> 7) + 2 * i) + col_in_box;
+                atomicAdd(p, sb[i].x), atomicAdd(p + 1, sb[i].y), atomicAdd(p + 2, sb[i].z), atomicAdd(p + 3, sb[i].w);
             }
         }
     } else if (warp >= 12 && num_kb > 0) {
@@ -281,6 +318,14 @@ k_gram3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(ACC_COLS * ACC_STAGES) : "memory");
     }
+    if (num_kb > 0) {   // this CTA's share of the column sums
+        if (g.a_colsum)
+            for (int i = threadIdx.x; i < GM; i += NUM_THREADS)
+                if (mb * GM + i < g.n1 && colsum_s[i] != 0.f) atomicAdd(g.a_colsum + mb * GM + i, colsum_s[i]);
+        if (g.b_colsum && mb == 0)
+            for (int i = threadIdx.x; i < g.n2; i += NUM_THREADS)
+                if (colsum_s[GM + i] != 0.f) atomicAdd(g.b_colsum + i, colsum_s[GM + i]);
+    }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -317,12 +362,14 @@ int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64
 using namespace rgcn;
 
 extern "C" int rgcn_gram3x_tf32(const float* a, int64_t lda, int32_t n1, const float* b, int64_t ldb, int32_t n2, int64_t rows,
-                                float* c, int64_t ldc, void* stream) {
+                                float* c, int64_t ldc, float* a_colsum, float* b_colsum, void* stream) {
     if (!a || !b || !c || n1 <= 0 || n2 <= 0 || n2 > MAX_BN || rows < 0 || lda < n1 || ldb < n2 || (lda % 4) || (ldb % 4) ||
         ((uintptr_t)a & 15) || ((uintptr_t)b & 15) || ldc < n2 || rows >= (1ll << 31))
         return fail(RGCN_ERR_INVALID_ARG, "rgcn_gram3x_tf32: bad argument (rows of A and B 16-byte addressable, n2 <= 192)");
     cudaStream_t st = (cudaStream_t)stream;
     RGCN_CUDA(cudaMemset2DAsync(c, (size_t)ldc * 4, 0, (size_t)n2 * 4, (size_t)n1, st));
+    if (a_colsum) RGCN_CUDA(cudaMemsetAsync(a_colsum, 0, (size_t)n1 * 4, st));
+    if (b_colsum) RGCN_CUDA(cudaMemsetAsync(b_colsum, 0, (size_t)n2 * 4, st));
     if (rows == 0) return 0;
     CUtensorMap ma, mbm;
     int rc;
@@ -335,11 +382,13 @@ extern "C" int rgcn_gram3x_tf32(const float* a, int64_t lda, int32_t n1, const f
     g.BN = (n2 + 31) / 32 * 32;
     g.C = c;
     g.ldc = ldc;
+    g.a_colsum = a_colsum;
+    g.b_colsum = b_colsum;
     const int stage_bytes = 2 * A_TILE + 2 * (g.BN / 32) * BOX;
     const int acc_bytes = g.BN * GM * 4;
-    const int budget = 227 * 1024 - 1024 - 256 - acc_bytes;
+    const int budget = 227 * 1024 - 1024 - 256 - 2048 /*column sums*/ - acc_bytes;
     g.stages = std::max(2, std::min(8, budget / stage_bytes));
-    const int smem = g.stages * stage_bytes + acc_bytes + 1024 + 256;
+    const int smem = g.stages * stage_bytes + acc_bytes + 1024 + 256 + 2048;
     if (smem > 227 * 1024) return fail(RGCN_ERR_UNSUPPORTED, "rgcn_gram3x_tf32: tile does not fit shared memory");
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

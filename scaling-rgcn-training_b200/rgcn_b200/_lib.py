@@ -100,7 +100,7 @@ def load():
     lib.rgcn_gemm3x_tf32.restype = C.c_int
     lib.rgcn_gemm3x_tf32.argtypes = [vp, i64, i64, i32, vp, vp, i32, i32, vp, i32, vp, i64, vp, i64, i32, vp]
     lib.rgcn_gram3x_tf32.restype = C.c_int
-    lib.rgcn_gram3x_tf32.argtypes = [vp, i64, i32, vp, i64, i32, i64, vp, i64, vp]
+    lib.rgcn_gram3x_tf32.argtypes = [vp, i64, i32, vp, i64, i32, i64, vp, i64, vp, vp, vp]
     lib.rgcn_attn_head_fwd.restype = C.c_int
     lib.rgcn_attn_head_fwd.argtypes = [vp, i64, vp, i64, i64, i32, i64, i32, i32, vp, vp, vp, i64, vp]
     lib.rgcn_attn_head_bwd.restype = C.c_int

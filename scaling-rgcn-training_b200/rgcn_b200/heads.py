@@ -104,9 +104,10 @@ def padded_like(rows: int, cols: int, device) -> Tensor:
     return torch.empty((rows, _pad(cols, 4)), dtype=torch.float32, device=device)[:, :cols]
 
 
-def gram(a: Tensor, b: Tensor) -> Tensor:
+def gram(a: Tensor, b: Tensor, colsums: bool = False):
     """a^T @ b for a [M, n1], b [M, n2] with M = all nodes: the parameter-gradient reduction of a head, on the
-    engine's split-K tcgen05 kernel (csrc/gram_tc.cu).  Operands that are not 16-byte addressable are copied."""
+    engine's split-K tcgen05 kernel (csrc/gram_tc.cu).  Operands that are not 16-byte addressable are copied.
+    colsums=True: returns (a^T b, a.sum(0), b.sum(0)) — the bias gradients, accumulated inside the same kernel."""
     lib = _lib.load()
     if not a.is_cuda or not b.is_cuda or a.dtype != torch.float32 or b.dtype != torch.float32 or a.size(0) != b.size(0):
         raise _lib.EngineError('gram: two CUDA fp32 matrices with the same number of rows (no CPU path)')
@@ -121,11 +122,16 @@ def gram(a: Tensor, b: Tensor) -> Tensor:
         raise _lib.EngineError('gram: one side must be at most 192 wide')
     a, b = rows16(a), rows16(b)
     c = torch.empty((n1, n2), dtype=torch.float32, device=a.device)
+    sa = torch.empty(n1, dtype=torch.float32, device=a.device) if colsums else None
+    sb = torch.empty(n2, dtype=torch.float32, device=a.device) if colsums else None
     with torch.cuda.device(a.device):
         rc = lib.rgcn_gram3x_tf32(a.data_ptr(), a.stride(0), n1, b.data_ptr(), b.stride(0), n2, a.size(0), c.data_ptr(), n2,
-                                  _stream(a.device))
+                                  sa.data_ptr() if colsums else None, sb.data_ptr() if colsums else None, _stream(a.device))
     _lib.check(rc, 'rgcn_gram3x_tf32')
-    return c.t().contiguous() if swap else c
+    c = c.t().contiguous() if swap else c
+    if not colsums:
+        return c
+    return (c, sb, sa) if swap else (c, sa, sb)
 
 
 class _MLPHeadFn(torch.autograd.Function):
@@ -143,17 +149,21 @@ class _MLPHeadFn(torch.autograd.Function):
         need_e, need_w1, need_b1, need_w2, need_b2 = ctx.needs_input_grad
         g = rows16(g)                                         # (one padding copy when the layer hands over packed rows)
         use_gram = os.environ.get('RGCN_B200_GRAM', '1') != '0'
-        red = gram if use_gram else (lambda p, q: p.t() @ q)  # [out, in] = reduction over all nodes, tiny result
-        gw2 = red(g, h) if need_w2 else None                  # [emb, mid]
-        gb2 = g.sum(0) if need_b2 else None
+
+        def red(p, q):          # (p^T q, p.sum(0)): [out, in] weight gradient + bias gradient, reductions over all nodes
+            if use_gram:
+                c, sp, _ = gram(p, q, colsums=True)
+                return c, sp
+            return p.t() @ q, p.sum(0)
+        gw2 = gb2 = None
+        if need_w2 or need_b2:
+            gw2, gb2 = red(g, h)                              # [emb, mid], [emb]
         ge = gw1 = gb1 = None
         if need_e or need_w1 or need_b1:
             # (g @ W2) * (1 - h^2) -> [N, mid]: the tanh backward rides in the epilogue of the tensor-core kernel
             dpre = gemm(g, w2, transpose_w=True, act='dtanh', aux=h)
-            if need_w1:
-                gw1 = red(dpre, a)
-            if need_b1:
-                gb1 = dpre.sum(0)
+            if need_w1 or need_b1:
+                gw1, gb1 = red(dpre, a)
             if need_e:
                 ge = gemm(dpre, w1, transpose_w=True)
         return ge, gw1, gb1, gw2, gb2
@@ -228,9 +238,15 @@ class _AttentionHeadFn(torch.autograd.Function):
         need_e, need_w_in, need_b_in, need_w_out, need_b_out = ctx.needs_input_grad[:5]
         g = rows16(g)
         use_gram = os.environ.get('RGCN_B200_GRAM', '1') != '0'
-        red = gram if use_gram else (lambda p, q: p.t() @ q)
-        gw_out = red(g, o) if need_w_out else None
-        gb_out = g.sum(0) if need_b_out else None
+
+        def red(p, q):          # (p^T q, p.sum(0))
+            if use_gram:
+                c, sp, _ = gram(p, q, colsums=True)
+                return c, sp
+            return p.t() @ q, p.sum(0)
+        gw_out = gb_out = None
+        if need_w_out or need_b_out:
+            gw_out, gb_out = red(g, o)
         ge = gw_in = gb_in = None
         if need_e or need_w_in or need_b_in:
             go = gemm(g, w_out, transpose_w=True)                                       # dL/do [N, emb]
@@ -243,12 +259,12 @@ class _AttentionHeadFn(torch.autograd.Function):
                                             gkv.stride(0), _stream(g.device))
             _lib.check(rc, 'rgcn_attn_head_bwd')
             gq = gq[:, :emb]
-            if need_w_in:
-                gkv_w = red(gkv, e_flat)                                                # [2 ep, emb]; the pad rows are dropped
-                gw_in = torch.cat([red(gq, e_flat[:n]), gkv_w[:emb], gkv_w[ep:ep + emb]], 0)
-            if need_b_in and has_b_in:
-                gkv_b = gkv.sum(0)
-                gb_in = torch.cat([gq.sum(0), gkv_b[:emb], gkv_b[ep:ep + emb]], 0)
+            if need_w_in or (need_b_in and has_b_in):
+                gkv_w, gkv_b = red(gkv, e_flat)                                         # [2 ep, emb], [2 ep]; pad rows dropped
+                gq_w, gq_b = red(gq, e_flat[:n])
+                gw_in = torch.cat([gq_w, gkv_w[:emb], gkv_w[ep:ep + emb]], 0)
+                if has_b_in:
+                    gb_in = torch.cat([gq_b, gkv_b[:emb], gkv_b[ep:ep + emb]], 0)
             if need_e:
                 if ep != emb:                                 # the pad columns meet zero weight rows: they must be finite
                     gkv[:, emb:ep].zero_()

@@ -393,5 +393,8 @@ def test_tcgen05_gram_is_fp32_faithful(m, n1, n2):
     assert tuple(got.shape) == (n1, n2)
     fp32 = a.t() @ b
     assert rel_err(got, want) < max(TOL, 4 * rel_err(fp32, want)), (rel_err(got, want), rel_err(fp32, want))
-    # unpadded operands are copied, not rejected
-    assert rel_err(gram(a.contiguous(), b.contiguous()), want) < max(TOL, 4 * rel_err(fp32, want))
+    # unpadded operands are copied, not rejected; the column sums (bias gradients) come out of the same kernel
+    c2, sa, sb = gram(a.contiguous(), b.contiguous(), colsums=True)
+    assert rel_err(c2, want) < max(TOL, 4 * rel_err(fp32, want))
+    assert rel_err(sa, a.double().sum(0)) < max(TOL, 4 * rel_err(a.sum(0), a.double().sum(0)))
+    assert rel_err(sb, b.double().sum(0)) < max(TOL, 4 * rel_err(b.sum(0), b.double().sum(0)))
