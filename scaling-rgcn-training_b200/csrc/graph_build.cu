@@ -21,32 +21,32 @@ int fail(int code, const std::string& msg) {
 }
 const char* last_error_cstr() { return g_last_error.c_str(); }
 
-void Brc::release() {
-    void* ptrs[] = {perm, seg_ptr0, seg_ptr, seg_own, seg_rel, e_idx, e_w, raw_idx, raw_w,
-                    chunk_beg, chunk_end, chunk_out, bat_seg0, bat_info, units, e_own, tile_e0, tile_info, stile_e0, stile_rel};
-    for (void* p : ptrs)
-        if (p) cudaFree(p);
-    *this = Brc();
-}
+void Brc::release() { *this = Brc(); }   // (the arrays belong to the graph's arena)
 
 namespace {
 
+// arenas of the build in progress on this thread (set by graph_create_impl)
+thread_local Arena* t_persist = nullptr;
+thread_local Arena* t_scratch = nullptr;
+
 template <typename T>
-struct Dev {   // scratch buffer freed at scope exit
+cudaError_t palloc(T** p, size_t bytes) {   // persistent array of the graph being built
+    return t_persist->take(reinterpret_cast<void**>(p), bytes);
+}
+
+template <typename T>
+struct Dev {   // scratch buffer from the build's scratch arena; released by the enclosing ScratchScope
     T* p = nullptr;
     size_t n = 0;
     cudaError_t alloc(size_t count) {
         n = count;
-        return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        return t_scratch->take(reinterpret_cast<void**>(&p), std::max<size_t>(count, 1) * sizeof(T));
     }
-    T* take() {
-        T* r = p;
-        p = nullptr;
-        return r;
-    }
-    ~Dev() {
-        if (p) cudaFree(p);
-    }
+};
+struct ScratchScope {   // every scratch buffer taken inside the scope is handed back at its end
+    Arena::Mark m;
+    ScratchScope() : m(t_scratch->mark()) {}
+    ~ScratchScope() { t_scratch->rewind(m); }
 };
 
 constexpr int TPB = 256;
@@ -303,6 +303,7 @@ cudaError_t scan_inclusive(const T* in, T* out, int64_t n, cudaStream_t st) {
     size_t tmp_bytes = 0;
     cudaError_t e = cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, in, out, (int)n, st);
     if (e != cudaSuccess) return e;
+    ScratchScope scratch_scope;
     Dev<char> tmp;
     if ((e = tmp.alloc(tmp_bytes)) != cudaSuccess) return e;
     e = cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, in, out, (int)n, st);
@@ -314,6 +315,7 @@ cudaError_t scan_exclusive(const T* in, T* out, int64_t n, cudaStream_t st) {
     size_t tmp_bytes = 0;
     cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, out, (int)n, st);
     if (e != cudaSuccess) return e;
+    ScratchScope scratch_scope;
     Dev<char> tmp;
     if ((e = tmp.alloc(tmp_bytes)) != cudaSuccess) return e;
     e = cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, in, out, (int)n, st);
@@ -352,6 +354,7 @@ int build_stiles(Brc& b, cudaStream_t st) {
     const int32_t NT = b.num_tiles_noself;
     b.num_stiles = 0;
     if (NT <= 0) return 0;
+    ScratchScope scratch_scope;
     Dev<int32_t> runstart, head, pos;
     Dev<char> tmp;
     RGCN_CUDA(runstart.alloc(NT));
@@ -367,8 +370,8 @@ int build_stiles(Brc& b, cudaStream_t st) {
     RGCN_CUDA(scan_exclusive(head.p, pos.p, (int64_t)NT + 1, st));
     int32_t NS = 0;
     RGCN_CUDA(cudaMemcpy(&NS, pos.p + NT, 4, cudaMemcpyDeviceToHost));
-    RGCN_CUDA(cudaMalloc(&b.stile_e0, ((size_t)NS + 2) * 4));
-    RGCN_CUDA(cudaMalloc(&b.stile_rel, ((size_t)NS + 2) * 4));
+    RGCN_CUDA(palloc(&b.stile_e0, ((size_t)NS + 2) * 4));
+    RGCN_CUDA(palloc(&b.stile_rel, ((size_t)NS + 2) * 4));
     k_stile_fill<<<blocks_for(NT), TPB, 0, st>>>(head.p, pos.p, b.tile_e0, b.tile_info, NT, NS, b.stile_e0, b.stile_rel);
     RGCN_CUDA(cudaGetLastError());
     RGCN_CUDA(cudaStreamSynchronize(st));
@@ -417,13 +420,14 @@ int share_chunks(const Brc& fwd, Brc& rel, int64_t n_own, int64_t n_gat, int R, 
     if (NC != rel.num_chunks)   // both structures chunk the same (relation, dst) segments: a mismatch is a builder bug
         return fail(RGCN_ERR_INVALID_ARG, "share_chunks: FWD and FWD_REL disagree on the number of chunks");
     if (NC == 0) return 0;
+    ScratchScope scratch_scope;
     Dev<uint64_t> key, skey;
     Dev<int32_t> id, tmp_order;
     Dev<char> tmp;
     RGCN_CUDA(key.alloc(NC));
     RGCN_CUDA(skey.alloc(NC));
     RGCN_CUDA(id.alloc(NC));
-    RGCN_CUDA(cudaMalloc(&rel.chunk_out, (size_t)NC * 4));
+    RGCN_CUDA(palloc(&rel.chunk_out, (size_t)NC * 4));
     k_chunk_keys<<<blocks_for(fwd.num_seg), TPB, 0, st>>>(fwd.seg_ptr, fwd.seg_own, fwd.seg_rel, fwd.e_idx, fwd.num_seg,
                                                          (uint32_t)n_gat, (uint64_t)n_own, key.p, id.p);
     const int end_bit = bit_length((uint64_t)(R + 1) * (uint64_t)n_own);
@@ -448,6 +452,7 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const 
     Brc b;
     b.num_entries0 = n2;
     b.range_nodes = NR;
+    ScratchScope scratch_scope;
     Dev<uint64_t> key, skey;
     Dev<int32_t> eid, head, scan;
     RGCN_CUDA(key.alloc(n2));
@@ -455,7 +460,7 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const 
     RGCN_CUDA(eid.alloc(n2));
     RGCN_CUDA(head.alloc(n2));
     RGCN_CUDA(scan.alloc(n2));
-    RGCN_CUDA(cudaMalloc(&b.perm, std::max<int64_t>(n2, 1) * 4));
+    RGCN_CUDA(palloc(&b.perm, std::max<int64_t>(n2, 1) * 4));
     const uint64_t nranges = std::max<uint64_t>((uint64_t)((N + NR - 1) / NR), 1);
     const uint64_t self_base = nranges * (uint64_t)(R + 1) * (uint64_t)NR;
     k_keys<<<blocks_for(n2), TPB, 0, st>>>(own, rel, n2, R, NR, self_base, key.p, eid.p);
@@ -476,15 +481,15 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const 
     int32_t S = 0;
     if (n2 > 0) RGCN_CUDA(cudaMemcpy(&S, scan.p + (n2 - 1), 4, cudaMemcpyDeviceToHost));
     b.num_seg = S;
-    RGCN_CUDA(cudaMalloc(&b.seg_ptr0, (size_t)(S + 1) * 4));
-    RGCN_CUDA(cudaMalloc(&b.seg_ptr, (size_t)(S + 1) * 4));
-    RGCN_CUDA(cudaMalloc(&b.seg_own, std::max(S, 1) * 4));
-    RGCN_CUDA(cudaMalloc(&b.seg_rel, std::max(S, 1) * 4));
+    RGCN_CUDA(palloc(&b.seg_ptr0, (size_t)(S + 1) * 4));
+    RGCN_CUDA(palloc(&b.seg_ptr, (size_t)(S + 1) * 4));
+    RGCN_CUDA(palloc(&b.seg_own, std::max(S, 1) * 4));
+    RGCN_CUDA(palloc(&b.seg_rel, std::max(S, 1) * 4));
     k_seg_fill<<<blocks_for(n2), TPB, 0, st>>>(skey.p, head.p, scan.p, n2, R, NR, self_base, b.seg_ptr0, b.seg_own,
                                                b.seg_rel);
     k_set_i32<<<1, 1, 0, st>>>(b.seg_ptr0 + S, (int32_t)n2);
-    RGCN_CUDA(cudaMalloc(&b.raw_idx, std::max<int64_t>(n2, 1) * 4));
-    RGCN_CUDA(cudaMalloc(&b.raw_w, std::max<int64_t>(n2, 1) * 4));
+    RGCN_CUDA(palloc(&b.raw_idx, std::max<int64_t>(n2, 1) * 4));
+    RGCN_CUDA(palloc(&b.raw_w, std::max<int64_t>(n2, 1) * 4));
     k_raw<<<blocks_for(n2), TPB, 0, st>>>(b.perm, gat, w_entry, n2, b.raw_idx, b.raw_w);
 
     // chunking of long segments
@@ -502,11 +507,11 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const 
     RGCN_CUDA(cudaMemcpy(&NC, chunk_base.p + S, 4, cudaMemcpyDeviceToHost));
     b.num_entries = E3;
     b.num_chunks = NC;
-    RGCN_CUDA(cudaMalloc(&b.e_idx, ((size_t)std::max(E3, 1) + 16) * 4));   // +16: whole 16-byte chunks are staged
-    RGCN_CUDA(cudaMalloc(&b.e_w, ((size_t)std::max(E3, 1) + 16) * 4));
-    RGCN_CUDA(cudaMalloc(&b.chunk_beg, std::max(NC, 1) * 4));
-    RGCN_CUDA(cudaMalloc(&b.chunk_end, std::max(NC, 1) * 4));
-    RGCN_CUDA(cudaMalloc(&b.e_own, ((size_t)std::max(E3, 1) + 16) * 4));
+    RGCN_CUDA(palloc(&b.e_idx, ((size_t)std::max(E3, 1) + 16) * 4));   // +16: whole 16-byte chunks are staged
+    RGCN_CUDA(palloc(&b.e_w, ((size_t)std::max(E3, 1) + 16) * 4));
+    RGCN_CUDA(palloc(&b.chunk_beg, std::max(NC, 1) * 4));
+    RGCN_CUDA(palloc(&b.chunk_end, std::max(NC, 1) * 4));
+    RGCN_CUDA(palloc(&b.e_own, ((size_t)std::max(E3, 1) + 16) * 4));
     k_compact<<<blocks_for(n2), TPB, 0, st>>>(scan.p, b.seg_ptr0, b.seg_ptr, chunk_base.p, b.raw_idx, b.raw_w, n2, n_gat, T,
                                               CH, b.e_idx, b.e_w, b.chunk_beg, b.chunk_end, b.seg_own, b.e_own);
 
@@ -535,8 +540,8 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const 
         RGCN_CUDA(cudaMemcpy(&NB, bat_base.p + G, 4, cudaMemcpyDeviceToHost));
     }
     b.num_batches = NB;
-    RGCN_CUDA(cudaMalloc(&b.bat_seg0, std::max(NB, 1) * 4));
-    RGCN_CUDA(cudaMalloc(&b.bat_info, std::max(NB, 1) * 4));
+    RGCN_CUDA(palloc(&b.bat_seg0, std::max(NB, 1) * 4));
+    RGCN_CUDA(palloc(&b.bat_info, std::max(NB, 1) * 4));
     if (NB > 0)
         k_batch_fill<<<blocks_for(NB), TPB, 0, st>>>(bat_base.p, grp_seg.p, b.seg_rel, G, NB, b.bat_seg0, b.bat_info);
     {   // entry tiles
@@ -560,8 +565,8 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const 
             if (first_self_group >= 0)
                 RGCN_CUDA(cudaMemcpy(&b.num_tiles_noself, tile_base.p + first_self_group, 4, cudaMemcpyDeviceToHost));
         }
-        RGCN_CUDA(cudaMalloc(&b.tile_e0, ((size_t)std::max(NTL, 1) + 16) * 4));
-        RGCN_CUDA(cudaMalloc(&b.tile_info, ((size_t)std::max(NTL, 1) + 16) * 4));
+        RGCN_CUDA(palloc(&b.tile_e0, ((size_t)std::max(NTL, 1) + 16) * 4));
+        RGCN_CUDA(palloc(&b.tile_info, ((size_t)std::max(NTL, 1) + 16) * 4));
         if (NTL > 0)
             k_tile_fill<<<blocks_for(NTL), TPB, 0, st>>>(tile_base.p, grp_seg.p, b.seg_ptr, b.seg_rel, G, NTL, b.tile_e0,
                                                          b.tile_info);
@@ -570,7 +575,7 @@ int build_brc(const int32_t* own, const int32_t* gat, const int32_t* rel, const 
         const int64_t total = (int64_t)E3 + (int64_t)UNIT_BATCH_COST * NB;
         int64_t nu = std::min<int64_t>(UNIT_MAX, std::max<int64_t>(1, total / UNIT_MIN_COST));
         b.num_units = (int32_t)nu;
-        RGCN_CUDA(cudaMalloc(&b.units, (size_t)(nu + 1) * sizeof(int4)));
+        RGCN_CUDA(palloc(&b.units, (size_t)(nu + 1) * sizeof(int4)));
         k_units<<<blocks_for(nu + 1), TPB, 0, st>>>(b.bat_seg0, b.seg_ptr, NB, S, E3, (int32_t)nu, b.units);
     }
     RGCN_CUDA(cudaStreamSynchronize(st));
@@ -598,6 +603,7 @@ extern "C" void rgcn_graph_destroy(rgcn_graph* g) {
         if (i == RGCN_BRC_FWD_REL && g->rel_is_fwd) continue;
         g->brc[i].release();
     }
+    g->arena.free_all();
     if (g->side) cudaStreamDestroy(g->side);
     if (g->ev_fork) cudaEventDestroy(g->ev_fork);
     if (g->ev_join) cudaEventDestroy(g->ev_join);
@@ -610,6 +616,7 @@ namespace {
 int compute_edge_weights(const int32_t* dst32, const int32_t* rel32, int64_t E, int64_t N, int R, float* w_edge,
                          cudaStream_t st) {
     if (E == 0) return 0;
+    ScratchScope scratch_scope;
     Dev<uint64_t> key, skey;
     Dev<int32_t> eid, perm, head, scan, start;
     RGCN_CUDA(key.alloc(E));
@@ -644,6 +651,7 @@ int compute_edge_weights(const int32_t* dst32, const int32_t* rel32, int64_t E, 
 int build_side(const int32_t* own_g, const int32_t* gat_g, const int32_t* rel_g, const float* w_edge, int64_t E,
                int64_t num_all, int R, int64_t lo, int64_t hi, int NR, int T, int CH, cudaStream_t st, Brc* blocked,
                Brc* relmajor, bool push = false) {
+    ScratchScope scratch_scope;
     Dev<int32_t> flag, pos, own, gat, rel;
     Dev<float> w;
     RGCN_CUDA(flag.alloc(E + 1));
@@ -720,6 +728,26 @@ int graph_create_impl(const int64_t* src, int64_t src_stride, const int64_t* dst
     g->range_nodes = (int32_t)nr;
 
     const int64_t E = num_edges;
+    // arenas: the graph's own (persistent arrays) and this build's scratch; slabs sized to the graph so that a build
+    // makes a handful of device allocations instead of ~170
+    Arena scratch;
+    {
+        const size_t items = (size_t)(num_edges + num_nodes), mb2 = (size_t)2 << 20;
+        auto slab = [&](size_t per_item, size_t cap) { return std::min(cap, std::max(mb2, (items * per_item + mb2 - 1) & ~(mb2 - 1))); };
+        g->arena.slab_bytes = slab(48, (size_t)512 << 20);
+        scratch.slab_bytes = slab(96, (size_t)1024 << 20);
+    }
+    struct ArenaGuard {
+        Arena* s;
+        ~ArenaGuard() {
+            s->free_all();
+            t_scratch = nullptr;
+            t_persist = nullptr;
+        }
+    } arena_guard{&scratch};
+    t_persist = &g->arena;
+    t_scratch = &scratch;
+    ScratchScope scratch_scope;
     Dev<int32_t> src32, dst32, rel32;
     Dev<float> w_edge;
     Dev<int> err;
