@@ -422,7 +422,7 @@ int share_chunks(const Brc& fwd, Brc& rel, int64_t n_own, int64_t n_gat, int R, 
     if (NC == 0) return 0;
     ScratchScope scratch_scope;
     Dev<uint64_t> key, skey;
-    Dev<int32_t> id, tmp_order;
+    Dev<int32_t> id;
     Dev<char> tmp;
     RGCN_CUDA(key.alloc(NC));
     RGCN_CUDA(skey.alloc(NC));
