@@ -28,12 +28,16 @@ namespace rgcn {
 namespace {
 
 constexpr int GM = 128;                    // A columns per CTA (the M dimension of the MMA)
-constexpr int KB = 16;                     // rows (reduction index) per stage
-constexpr int BOX = 32 * KB * 4;           // one TMA box: 32 columns x 16 rows = 2 KB
-constexpr int A_TILE = (GM / 32) * BOX;    // 8 KB
+// rows (reduction index) per stage: 16 for wide operands (the drain tile leaves room for three 40 KB stages), 32 for
+// BN <= 96 (half as many TMA boxes and barrier round trips per byte)
+template <int KB>
+struct Cfg {
+    static constexpr int BOX = 32 * KB * 4;            // one TMA box: 32 columns x KB rows
+    static constexpr int A_TILE = (GM / 32) * BOX;
+    static constexpr int DRAIN_STAGES = 256 / KB;      // stages (256 rows) accumulated in tensor memory between two drains
+};
 constexpr int NUM_THREADS = 512;
 constexpr int ACC_COLS = 256, ACC_STAGES = 2;
-constexpr int DRAIN_STAGES = 16;           // stages (256 rows) accumulated in tensor memory between two drains
 constexpr int MAX_BN = 192;                // the shared-memory tile is BN x 128 floats
 
 struct GramArgs {
@@ -83,10 +87,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 }
 // MN-major 32-bit operand: atoms of 32 floats (M/N) x 4 rows (K); atoms along M/N are LBO apart (one TMA box each),
 // 4-row groups along K are SBO = 512 B apart (one tf32 instruction, K = 8, consumes two groups)
-__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, int box_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
-    d |= (uint64_t)(BOX >> 4) << 16;                     // leading byte offset: next 32-column atom
+    d |= (uint64_t)(box_bytes >> 4) << 16;               // leading byte offset: next 32-column atom
     d |= (uint64_t)(512 >> 4) << 32;                     // stride byte offset: next 4-row group
     d |= (uint64_t)1 << 46;                              // descriptor version (sm_100)
     d |= (uint64_t)1 << 61;                              // SWIZZLE_128B_BASE32B
@@ -120,8 +124,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+template <int KB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_gram3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GramArgs g) {
+    constexpr int BOX = Cfg<KB>::BOX, A_TILE = Cfg<KB>::A_TILE, DRAIN_STAGES = Cfg<KB>::DRAIN_STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -202,9 +208,9 @@ k_gram3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
 #pragma unroll
                 for (int k = 0; k < KB / 8; ++k) {       // tf32: 8 rows per instruction = two 512-byte groups
                     const uint32_t ko = (uint32_t)(k * 1024);
-                    umma_tf32(tmem_d, umma_desc_mn(a_hi + ko), umma_desc_mn(b_hi + ko), idesc, (in_acc | k) ? 1u : 0u);
-                    umma_tf32(tmem_d, umma_desc_mn(a_lo + ko), umma_desc_mn(b_hi + ko), idesc, 1u);
-                    umma_tf32(tmem_d, umma_desc_mn(a_hi + ko), umma_desc_mn(b_lo + ko), idesc, 1u);
+                    umma_tf32(tmem_d, umma_desc_mn(a_hi + ko, BOX), umma_desc_mn(b_hi + ko, BOX), idesc, (in_acc | k) ? 1u : 0u);
+                    umma_tf32(tmem_d, umma_desc_mn(a_lo + ko, BOX), umma_desc_mn(b_hi + ko, BOX), idesc, 1u);
+                    umma_tf32(tmem_d, umma_desc_mn(a_hi + ko, BOX), umma_desc_mn(b_lo + ko, BOX), idesc, 1u);
                 }
                 umma_commit(empty + s);
                 if (last) umma_commit(acc_full + a);
@@ -226,9 +232,10 @@ k_gram3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
         // 16-byte chunk tid % 8); the TMA swizzle XORs the 32-byte chunk index with row % 4, so the four floats of the
         // chunk are columns 32 box + 8 ((tid % 8) / 2 ^ (row & 3)) + 4 (tid & 1) .. + 3 — fixed per thread and i
         const bool want_a = g.a_colsum != nullptr, want_b = g.b_colsum != nullptr && mb == 0;
-        const int row_in_box = (tid & 127) >> 3;
+        constexpr int CPB = 8 * KB;                      // 16-byte chunks per box
+        const int row_in_box = (tid % CPB) >> 3;
         const int col_in_box = 8 * (((tid & 7) >> 1) ^ (row_in_box & 3)) + 4 * (tid & 1);
-        constexpr int A_IT = A_TILE / 16 / 256, B_IT = (MAX_BN / 32) * BOX / 16 / 256;
+        constexpr int A_IT = A_TILE / 16 / 256, B_IT = 3;   // B: at most 768 chunks (6 boxes of 2 KB or 3 boxes of 4 KB)
         float4 sa[A_IT], sb[B_IT];
 #pragma unroll
         for (int i = 0; i < A_IT; ++i) sa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -266,7 +273,7 @@ k_gram3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
         if (want_a) {
 #pragma unroll
             for (int i = 0; i < A_IT; ++i) {
-                float* p = colsum_s + 32 * ((tid >> 7) + 2 * i) + col_in_box;
+                float* p = colsum_s + 32 * ((tid + 256 * i) / CPB) + col_in_box;
                 atomicAdd(p, sa[i].x), atomicAdd(p + 1, sa[i].y), atomicAdd(p + 2, sa[i].z), atomicAdd(p + 3, sa[i].w);
             }
         }
@@ -274,7 +281,7 @@ k_gram3x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
 #pragma unroll
             for (int i = 0; i < B_IT; ++i) {
                 if (tid + 256 * i >= b_tile / 16) continue;
-                float* p = colsum_s + GM + 32 * ((tid >> 7) + 2 * i) + col_in_box;
+                float* p = colsum_s + GM + 32 * ((tid + 256 * i) / CPB) + col_in_box;
                 atomicAdd(p, sb[i].x), atomicAdd(p + 1, sb[i].y), atomicAdd(p + 2, sb[i].z), atomicAdd(p + 3, sb[i].w);
             }
         }
@@ -343,12 +350,12 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 // [rows, cols] row-major, box = 32 columns x KB rows, 128-byte swizzle of 32-byte chunks, out-of-range elements read as zero
-int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld) {
+int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int kb) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(RGCN_ERR_UNSUPPORTED, "rgcn_gram: cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {32, (cuuint32_t)KB};
+    cuuint32_t box[2] = {32, (cuuint32_t)kb};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -371,10 +378,6 @@ extern "C" int rgcn_gram3x_tf32(const float* a, int64_t lda, int32_t n1, const f
     if (a_colsum) RGCN_CUDA(cudaMemsetAsync(a_colsum, 0, (size_t)n1 * 4, st));
     if (b_colsum) RGCN_CUDA(cudaMemsetAsync(b_colsum, 0, (size_t)n2 * 4, st));
     if (rows == 0) return 0;
-    CUtensorMap ma, mbm;
-    int rc;
-    if ((rc = make_map(&ma, a, rows, n1, lda))) return rc;
-    if ((rc = make_map(&mbm, b, rows, n2, ldb))) return rc;
     GramArgs g{};
     g.rows = rows;
     g.n1 = n1;
@@ -384,7 +387,17 @@ extern "C" int rgcn_gram3x_tf32(const float* a, int64_t lda, int32_t n1, const f
     g.ldc = ldc;
     g.a_colsum = a_colsum;
     g.b_colsum = b_colsum;
-    const int stage_bytes = 2 * A_TILE + 2 * (g.BN / 32) * BOX;
+    static const bool kb32_on = [] {
+        const char* e = getenv("RGCN_B200_GRAM_KB32");
+        return !(e && e[0] == '0');
+    }();
+    const int KB = (kb32_on && g.BN <= 96) ? 32 : 16;
+    CUtensorMap ma, mbm;
+    int rc;
+    if ((rc = make_map(&ma, a, rows, n1, lda, KB))) return rc;
+    if ((rc = make_map(&mbm, b, rows, n2, ldb, KB))) return rc;
+    const int box = 32 * KB * 4, a_tile = (GM / 32) * box;
+    const int stage_bytes = 2 * a_tile + 2 * (g.BN / 32) * box;
     const int acc_bytes = g.BN * GM * 4;
     const int budget = 227 * 1024 - 1024 - 256 - 2048 /*column sums*/ - acc_bytes;
     g.stages = std::max(2, std::min(8, budget / stage_bytes));
@@ -397,10 +410,15 @@ extern "C" int rgcn_gram3x_tf32(const float* a, int64_t lda, int32_t n1, const f
     const int64_t kblocks = (rows + KB - 1) / KB;
     const int splits = (int)std::max<int64_t>(1, std::min<int64_t>(kblocks, sms / mblocks));
     g.rows_per_cta = (kblocks + splits - 1) / splits * KB;
-    RGCN_CUDA(cudaFuncSetAttribute(k_gram3x, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ProfScope prof(TAG_GEMM, n1, n2, st);
     note_launch(1);
-    k_gram3x<<<dim3((unsigned)splits, (unsigned)mblocks), NUM_THREADS, smem, st>>>(ma, mbm, g);
+    if (KB == 32) {
+        RGCN_CUDA(cudaFuncSetAttribute(k_gram3x<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_gram3x<32><<<dim3((unsigned)splits, (unsigned)mblocks), NUM_THREADS, smem, st>>>(ma, mbm, g);
+    } else {
+        RGCN_CUDA(cudaFuncSetAttribute(k_gram3x<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k_gram3x<16><<<dim3((unsigned)splits, (unsigned)mblocks), NUM_THREADS, smem, st>>>(ma, mbm, g);
+    }
     RGCN_CUDA(cudaGetLastError());
     return 0;
 }
