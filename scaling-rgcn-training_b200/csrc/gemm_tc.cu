@@ -2,12 +2,14 @@
 //
 //   C[M, N] = act( A[M, K] . W[N, K]^T + bias[N] )        fp32 in, fp32 out, fp32-faithful (3xTF32)
 //
-// replaces the transfer head of the reference (model/layers.py:105-107: lin2(tanh(lin1(E_cat))), two
-// nn.Linear calls = cuBLAS SGEMM there) where the hidden / embedding widths make the work a real dense
-// contraction (AM-shape: 1.67 M x 189 x 137 and x 137 x 63 per step, forward).  One persistent CTA per SM:
+// replaces the dense contractions of the reference's transfer heads (model/layers.py:105-107: lin2(tanh(lin1(E_cat))),
+// two nn.Linear calls = cuBLAS SGEMM there; :59-61: the in / out projections of nn.MultiheadAttention) and their
+// backward (dL/dh with the tanh backward in the epilogue) — AM-shape: 1.67 M x 189 x 137 and x 137 x 63 per step,
+// 5 M x 63 x 126 for the K | V projection.  One persistent CTA per SM, 16 warps:
 //
 //   warp 0      TMA producer   cp.async.bulk.tensor.2d (SASS UTMALDG) of the A tile [128 x 32 fp32] and the
-//                              pre-split W tiles (hi, lo) [BN x 32] into a 128B-swizzled ring, mbarrier tx
+//                              pre-split W tiles (hi, lo) [BN x 32] into a 128B-swizzled ring, mbarrier tx (W is
+//                              loaded once and stays resident when all its K blocks fit next to three A stages)
 //   warp 1      MMA issuer     one elected lane: per 32-column K block 4 x 3 tcgen05.mma.kind::tf32
 //                              (SASS UTCHMMA... UTC*MMA) — A_hi.W_hi, A_lo.W_hi, A_hi.W_lo — accumulating
 //                              in TENSOR MEMORY (two accumulator stages of 256 columns); tcgen05.commit

@@ -9,7 +9,7 @@
 // (descriptor layout type SWIZZLE_128B_BASE32B: atoms of 32 floats along M/N x 4 rows along K, the 32-byte chunks of a
 // row XORed with the row index), and the TMA unit writes exactly that (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): a box
 // of 32 columns x KB rows (KB = 16 or 32 rows per stage) lands as KB / 4 such atoms 512 B apart (SBO), the boxes of
-// one tile sit one box (LBO = 128 KB-bytes) apart.  (The plain 128-byte swizzle is accepted and returns zeros.)
+// one tile sit one box (LBO = 128 x KB bytes) apart.  (The plain 128-byte swizzle is accepted and returns zeros.)
 // Split-K: the row range is dealt over the CTAs.  The tensor core TRUNCATES when it adds into a tensor-memory
 // accumulator, which over thousands of rows becomes a bias (measured 3e-5 relative over 4 300 rows; cuBLAS fp32: 3e-6),
 // so an accumulator only ever holds 256 rows: it is then drained with round-to-nearest fp32 adds into a [BN x 128]
